@@ -1,0 +1,19 @@
+"""Public surface of the B200 Diff-UNet inference package."""
+from ._lib import DunetError, load as load_library
+from .inference import StitchBuffers, infer_volume, sliding_window_inference
+from .model import DEFAULT_FEATURES, DiffUNetB200
+from .schedule import DdimSchedule
+from .windows import axis_counts, scan_intervals, shard_range, window_starts
+
+
+def model_hub(model_name: str, **kwargs):
+    """Registration seam of the reference's string-keyed factory (models/utils/model_hub.py:15-50, utils.py:27-33):
+    ``"diff_unet_b200"`` (any name containing "diff" maps to ModelType.Diffusion there)."""
+    if model_name in ("diff_unet_b200", "diff_unet"):
+        return DiffUNetB200(**kwargs)
+    raise NotImplementedError(f"No such model : {model_name}")
+
+
+__all__ = ["DiffUNetB200", "DEFAULT_FEATURES", "DdimSchedule", "DunetError", "StitchBuffers", "axis_counts",
+           "infer_volume", "load_library", "model_hub", "scan_intervals", "shard_range", "sliding_window_inference",
+           "window_starts"]

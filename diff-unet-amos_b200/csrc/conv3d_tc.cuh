@@ -1,0 +1,225 @@
+// 3x3x3 convolution (stride 1, zero padding 1) as an implicit GEMM on the 5th-gen tensor cores (tcgen05 + TMEM),
+// operands staged by TMA.  Replaces nn.Conv3d inside MONAI Convolution (reference denoiser.py:56-58,
+// pretrained/basic_unet.py:59-62).
+//
+// GEMM view per CTA:  D[128 voxels x N_TILE couts] (x ZT z-slabs)  +=  A[128 x 16] * B[16 x N_TILE]   per tap, per K=16
+//
+//   * HBM activations are C8-planar bf16: act[n][c/8][z][y][x][c%8].  One TMA box (x:10, y:18, z:1, 8-channel
+//     chunks: CB_CH/8) lands a HALO PLANE of a 8x16 output tile in shared memory as [chunk][y][x][8ch] -- exactly the
+//     UMMA "K-major, no-swizzle" canonical layout (core matrix = 8 consecutive x voxels x 16 bytes).  Out-of-volume
+//     coordinates are zero-filled by TMA, which IS the convolution's zero padding.
+//   * A tap (tz,ty,tx) is not a new load: it is the same plane read through a matrix descriptor whose start address
+//     is shifted by (ty*10+tx)*16 bytes, and tz picks one of the resident planes.  One halo plane feeds 9 taps x up
+//     to 3 z-slabs = 27 MMAs-worth of A reads from shared memory instead of L2.
+//   * ZT z-slabs accumulate in ZT TMEM accumulators so each weight tap tile (streamed with cp.async.bulk through a
+//     small ring) is reused ZT times.
+//   * planes live in a ring of A_SLOTS plane-units; tz-major tap order releases plane 0 after the tz=0 taps, plane 1
+//     after tz=1, the rest at the end, so the producer prefetches the next input-channel block under the MMAs.
+//   * channel concat (UpCat, denoiser.py:190) is free: input-channel blocks [0,nb0) come from tensor map 0 (skip),
+//     the rest from tensor map 1 (upsampled).
+//
+// Warp roles (7 warps): 0 = plane producer (TMA), 1 = weight producer (bulk copy), 2 = MMA issuer + TMEM owner,
+// 3..6 = epilogue (TMEM -> registers -> bf16 -> coalesced 16-byte stores, one TMEM lane quadrant each).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "elementwise.cuh"
+#include "ptx.cuh"
+
+namespace dunet {
+
+constexpr int CONV_TX = 8, CONV_TY = 16;         // output tile in x, y  (= 128 GEMM rows)
+constexpr int CONV_HX = CONV_TX + 2, CONV_HY = CONV_TY + 2;
+constexpr int CONV_THREADS = 7 * 32;
+
+template <int CB_CH, int N_TILE, int ZT>
+struct ConvTc {
+  static constexpr int KCH = CB_CH / 8;                               // 16-byte K chunks per input-channel block
+  static constexpr int PLANE_BYTES = KCH * CONV_HY * CONV_HX * 16;    // 64 ch: 23040 B
+  static constexpr int A_LBO = CONV_HY * CONV_HX * 16;                // chunk -> chunk
+  static constexpr int A_SBO = CONV_HX * 16;                          // y -> y+1 (next 8-row group)
+  static constexpr int W_UNIT_BYTES = KCH * N_TILE * 16;              // one (tap, cin block, cout tile) weight tile
+  static constexpr int B_LBO = N_TILE * 16;
+  static constexpr int B_SBO = 128;
+  static constexpr int PLANES = ZT + 2;
+  static constexpr int A_SLOTS = (PLANES + 2) < 8 ? (PLANES + 2) : 8;
+  static constexpr int W_SLOTS = (32768 / W_UNIT_BYTES) < 2 ? 2 : ((32768 / W_UNIT_BYTES) > 8 ? 8 : (32768 / W_UNIT_BYTES));
+  static constexpr int TMEM_COLS = (ZT * N_TILE <= 32) ? 32 : (ZT * N_TILE <= 64) ? 64 : (ZT * N_TILE <= 128) ? 128
+                                   : (ZT * N_TILE <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(ZT * N_TILE <= 512, "accumulators exceed TMEM");
+  static_assert(A_SLOTS >= PLANES, "ring must hold one input-channel block");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+struct ConvTcArgs {
+  const __nv_bfloat16* w;  // packed [n_tile][cin_block][tap][KCH][N_TILE][8]
+  __nv_bfloat16* out;      // raw conv output, C8-planar, cout channels
+  int nb0, nb1;            // input-channel blocks taken from tensor map 0 / 1
+  int chunks0, chunks1;    // C/8 of source 0 / 1 (stride of the batch index in the folded 4th tensor-map dim)
+  int cout;
+  int D, H, W;
+  int tiles_x, tiles_y, tiles_z, n_tiles;
+};
+
+template <int CB_CH, int N_TILE, int ZT>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, ConvTcArgs a) {
+  using Cfg = ConvTc<CB_CH, N_TILE, ZT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = smem_base;
+  const uint32_t w_smem = a_smem + Cfg::A_SLOTS * Cfg::PLANE_BYTES;
+  const uint32_t bars = w_smem + Cfg::W_SLOTS * Cfg::W_UNIT_BYTES;
+  const uint32_t a_full = bars, a_empty = bars + 8 * Cfg::A_SLOTS;
+  const uint32_t w_full = bars + 16 * Cfg::A_SLOTS, w_empty = w_full + 8 * Cfg::W_SLOTS;
+  const uint32_t acc_full = w_empty + 8 * Cfg::W_SLOTS;
+  const uint32_t tmem_slot = acc_full + 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates (x fastest so that co-resident CTAs share halos and the same weight tile in L2)
+  int t = blockIdx.x;
+  const int tix = t % a.tiles_x; t /= a.tiles_x;
+  const int tiy = t % a.tiles_y; t /= a.tiles_y;
+  const int tiz = t % a.tiles_z; t /= a.tiles_z;
+  const int ntile = t % a.n_tiles; t /= a.n_tiles;
+  const int n = t;
+  const int x0 = tix * CONV_TX, y0 = tiy * CONV_TY, z0 = tiz * ZT;
+  const int ncb = a.nb0 + a.nb1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap0);
+    if (a.nb1 > 0) tma_prefetch_desc(&tmap1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // =============================== halo-plane producer (TMA) ===============================
+    if (elect_one_sync()) {
+      for (int cb = 0; cb < ncb; ++cb) {
+        const bool second = cb >= a.nb0;
+        const CUtensorMap* tm = second ? &tmap1 : &tmap0;
+        const int c3 = second ? n * a.chunks1 + (cb - a.nb0) * Cfg::KCH : n * a.chunks0 + cb * Cfg::KCH;
+        for (int p = 0; p < Cfg::PLANES; ++p) {
+          const int u = cb * Cfg::PLANES + p;
+          const int slot = u % Cfg::A_SLOTS, it = u / Cfg::A_SLOTS;
+          if (it > 0) mbar_wait(a_empty + 8 * slot, (it - 1) & 1);
+          mbar_arrive_expect_tx(a_full + 8 * slot, Cfg::PLANE_BYTES);
+          tma_load_4d(a_smem + slot * Cfg::PLANE_BYTES, tm, a_full + 8 * slot, (x0 - 1) * 8, y0 - 1, z0 + p - 1, c3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== weight-tile producer (bulk copy) ===============================
+    if (elect_one_sync()) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)ntile * ncb * 27 * Cfg::W_UNIT_BYTES;
+      const int nw = ncb * 27;
+      for (int w = 0; w < nw; ++w) {
+        const int slot = w % Cfg::W_SLOTS, it = w / Cfg::W_SLOTS;
+        if (it > 0) mbar_wait(w_empty + 8 * slot, (it - 1) & 1);
+        mbar_arrive_expect_tx(w_full + 8 * slot, Cfg::W_UNIT_BYTES);
+        bulk_load_1d(w_smem + slot * Cfg::W_UNIT_BYTES, wsrc + (size_t)w * Cfg::W_UNIT_BYTES, Cfg::W_UNIT_BYTES,
+                     w_full + 8 * slot);
+      }
+    }
+  } else if (warp == 2) {
+    // =============================== MMA issuer (one thread) ===============================
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE);
+      for (int cb = 0; cb < ncb; ++cb) {
+        int waited = 0;
+        for (int tz = 0; tz < 3; ++tz) {
+          for (int tyx = 0; tyx < 9; ++tyx) {
+            const int w = cb * 27 + tz * 9 + tyx;
+            const int ws = w % Cfg::W_SLOTS;
+            mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
+            tc_fence_after();
+            const uint32_t tap_off = ((tyx / 3) * CONV_HX + (tyx % 3)) * 16;
+            const uint32_t wb = w_smem + ws * Cfg::W_UNIT_BYTES;
+#pragma unroll
+            for (int s = 0; s < ZT; ++s) {
+              const int p = s + tz;
+              while (waited <= p) {
+                const int u = cb * Cfg::PLANES + waited;
+                mbar_wait(a_full + 8 * (u % Cfg::A_SLOTS), (u / Cfg::A_SLOTS) & 1);
+                tc_fence_after();
+                ++waited;
+              }
+              const int u = cb * Cfg::PLANES + p;
+              const uint32_t ab = a_smem + (u % Cfg::A_SLOTS) * Cfg::PLANE_BYTES + tap_off;
+#pragma unroll
+              for (int k = 0; k < CB_CH / 16; ++k) {
+                const uint64_t ad = make_smem_desc(ab + k * 2 * Cfg::A_LBO, Cfg::A_LBO, Cfg::A_SBO);
+                const uint64_t bd = make_smem_desc(wb + k * 2 * Cfg::B_LBO, Cfg::B_LBO, Cfg::B_SBO);
+                umma_bf16(tmem_base + s * N_TILE, ad, bd, idesc, (cb | tz | tyx | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(w_empty + 8 * ws);  // weight slot free once these MMAs retire
+          }
+          // planes whose last reader was this tz phase go back to the producer
+          if (tz < 2) {
+            umma_commit(a_empty + 8 * ((cb * Cfg::PLANES + tz) % Cfg::A_SLOTS));
+          } else {
+            for (int p = 2; p < Cfg::PLANES; ++p) umma_commit(a_empty + 8 * ((cb * Cfg::PLANES + p) % Cfg::A_SLOTS));
+          }
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // =============================== epilogue: TMEM -> bf16 -> HBM ===============================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int r = q * 32 + lane;  // GEMM row = voxel (y = r / 8, x = r % 8)
+    const int x = x0 + (r & 7), y = y0 + (r >> 3);
+    const bool xy_ok = x < a.W && y < a.H;
+    const int out_chunks = a.cout / 8;
+    const long long plane_vox = (long long)a.D * a.H * a.W;
+#pragma unroll 1
+    for (int s = 0; s < ZT; ++s) {
+      const int z = z0 + s;
+      const bool ok = xy_ok && z < a.D;
+      const long long vofs = ((long long)z * a.H + y) * a.W + x;
+#pragma unroll 1
+      for (int j = 0; j < N_TILE / 16; ++j) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + s * N_TILE + j * 16, v);
+        if (ok) {
+          const int c8 = (ntile * N_TILE + j * 16) / 8;
+          BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + c8) * plane_vox + vofs;
+          float lo[8], hi[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+          dst[0] = float_to_bf8(lo);
+          dst[plane_vox] = float_to_bf8(hi);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace dunet

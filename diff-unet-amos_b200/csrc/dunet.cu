@@ -1,0 +1,862 @@
+// libdunet_b200.so -- C ABI (include/dunet.h) + host-side plan for the Diff-UNet DDIM inference path on B200.
+// Host code here only sequences kernels on the caller's stream; all arithmetic is in the sm_100a kernels.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/dunet.h"
+#include "conv3d_ref.cuh"
+#include "conv3d_tc.cuh"
+#include "elementwise.cuh"
+
+using namespace dunet;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------ errors / utils
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) return fail(DUNET_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                                        __FILE__, __LINE__);                                             \
+  } while (0)
+#define LAUNCH_CHECK()                                                                                   \
+  do {                                                                                                   \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                                  \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ != cudaSuccess) return fail(DUNET_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                                        __FILE__, __LINE__);                                             \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int r__ = (expr);        \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+// ---- optional live profiling of the conv launches (bench.py roofline) ----
+struct ProfRec { cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;       // event pool, reused across enable() calls
+static size_t g_prof_used = 0;
+static double g_prof_flops = 0.0;
+
+static inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+static inline int grid_for(long long total, int threads, int cap = 148 * 16) {
+  long long b = (total + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_driver_entry() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(DUNET_E_CUDA, "cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// Tensor map over a C8-planar activation: dims (x*8+c8 : W*8, y : H, z : D, plane : batch*chunks), box = one halo plane.
+static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, int H, int W, int kch) {
+  TRY(load_driver_entry());
+  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+  cuuint32_t box[4] = {CONV_HX * 8, CONV_HY, 1, (cuuint32_t)kch};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DUNET_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d D=%d planes=%d)",
+                                     (int)r, W, H, D, planes);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// conv weights fp32 [coutr][cinr][27] -> bf16 [n_tile][cin block][tap][k chunk][N_TILE][8]   (see conv3d_tc.cuh)
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
+                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles) {
+  const int kch = cb_ch / 8;
+  const long long total = (long long)n_tiles * ncb * 27 * kch * n_tile * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int j = (int)(t % 8); t /= 8;
+    const int col = (int)(t % n_tile); t /= n_tile;
+    const int k = (int)(t % kch); t /= kch;
+    const int tap = (int)(t % 27); t /= 27;
+    const int cb = (int)(t % ncb); t /= ncb;
+    const int nt = (int)t;
+    const int co = nt * n_tile + col;
+    const int lc = cb * cb_ch + k * 8 + j;
+    int ci = -1;
+    if (lc < c0p) { if (lc < c0r) ci = lc; }
+    else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
+    float v = 0.f;
+    if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+// transposed-conv weights fp32 [cinr][coutr][8] -> bf16 [tap][cinp][coutp]
+__global__ void pack_deconv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cinr, int coutr, int cinp,
+                                     int coutp) {
+  const long long total = 8LL * cinp * coutp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % coutp);
+    const int ci = (int)((i / coutp) % cinp);
+    const int tap = (int)(i / ((long long)coutp * cinp));
+    float v = 0.f;
+    if (ci < cinr && co < coutr) v = w[((long long)ci * coutr + co) * 8 + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+// copy `n` floats into a zero-padded buffer of n_pad floats, optionally strided rows: dst[r][0..cols_pad) <- src[r][0..cols)
+__global__ void copy_pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
+                                     int rows_pad, int cols_pad) {
+  const long long total = (long long)rows_pad * cols_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols_pad), r = (int)(i / cols_pad);
+    dst[i] = (r < rows && c < cols) ? src[(long long)r * cols + c] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct ConvW {
+  int c0r = 0, c1r = 0, c0p = 0, c1p = 0, coutr = 0, coutp = 0;
+  int cb_ch = 64, n_tile = 64, nb0 = 0, nb1 = 0, n_tiles = 1;
+  bf16* packed = nullptr;
+  float* w32 = nullptr;  // debug copy of the original fp32 weight
+  float *gamma = nullptr, *beta = nullptr;
+  bool have_w = false, have_cb = false, have_g = false, have_b = false;
+  void shape(int c0r_, int c0p_, int c1r_, int c1p_, int coutr_) {
+    c0r = c0r_; c0p = c0p_; c1r = c1r_; c1p = c1p_; coutr = coutr_;
+    coutp = pad_to(coutr, 64);
+    cb_ch = (c1p == 0 && c0p == 32) ? 32 : 64;
+    n_tile = (coutp % 128 == 0) ? 128 : 64;
+    n_tiles = coutp / n_tile;
+    nb0 = c0p / cb_ch; nb1 = c1p / cb_ch;
+  }
+  size_t packed_elems() const { return (size_t)n_tiles * (nb0 + nb1) * 27 * cb_ch * n_tile; }
+};
+struct TwoConvW {
+  ConvW a, b;
+  float *tp_w = nullptr, *tp_b = nullptr;  // temb_proj [coutr][512], [coutr]
+  bool has_temb = false, have_tpw = false, have_tpb = false;
+};
+struct DeconvW {
+  int cinr = 0, cinp = 0, coutr = 0, coutp = 0;
+  bf16* packed = nullptr;
+  float* bias = nullptr;
+  bool have_w = false, have_b = false;
+};
+
+enum SlotKind { K_CONV_W, K_CONV_B, K_IN_G, K_IN_B, K_TP_W, K_TP_B, K_DENSE, K_DECONV_W, K_DECONV_B, K_FINAL_W, K_FINAL_B };
+struct Slot {
+  SlotKind kind;
+  void* obj;
+  int idx;  // K_DENSE: 0..3
+  std::vector<int64_t> shape;
+  bool seen = false;
+};
+
+struct WsLayout {
+  size_t in_pack, raw, mid, partial, x_t, total;
+  size_t emb[5], epool[5], x[5], dpool[5], up[5], u[5];
+};
+
+struct dunet_plan {
+  dunet_cfg cfg;
+  int C, D[5], H[5], W[5];
+  long long V[5];
+  int fr[6], fp[6];       // real / padded features
+  int upr[5], upp[5];     // upsampled channels of upcat_l (index l = 4..1)
+  int uoutr[5], uoutp[5]; // output channels of upcat_l
+  int in_pad = 32;
+  TwoConvW enc[5], den[5], upc[5];  // upc index = l (1..4)
+  DeconvW dec[5];
+  float* dense[4] = {nullptr, nullptr, nullptr, nullptr};  // temb dense.0 w,b ; dense.1 w,b
+  float *final_w = nullptr, *final_b = nullptr;            // [C][f5p], [C]
+  std::unordered_map<std::string, Slot> slots;
+  // schedule
+  int n_steps = 0;
+  std::vector<int> tmap;
+  std::vector<float> sr, srm1, acp;
+  int* d_tmap = nullptr;
+  // temb bias table [n_steps + 1][row]; the extra row is scratch for timesteps outside the schedule
+  float* temb_table = nullptr;
+  int temb_row = 0, temb_off[9];
+  bool committed = false;
+  std::vector<void*> owned;
+};
+
+static int dev_alloc(dunet_plan* p, void** out, size_t bytes) {
+  CUDA_TRY(cudaMalloc(out, bytes ? bytes : 16));
+  p->owned.push_back(*out);
+  return 0;
+}
+
+static void add_slot(dunet_plan* p, const std::string& key, SlotKind kind, void* obj, std::vector<int64_t> shape, int idx = 0) {
+  Slot s; s.kind = kind; s.obj = obj; s.idx = idx; s.shape = std::move(shape);
+  p->slots[key] = s;
+}
+static void add_convblock_slots(dunet_plan* p, const std::string& pre, ConvW* c) {
+  add_slot(p, pre + ".conv.weight", K_CONV_W, c, {c->coutr, c->c0r + c->c1r, 3, 3, 3});
+  add_slot(p, pre + ".conv.bias", K_CONV_B, c, {c->coutr});
+  add_slot(p, pre + ".adn.N.weight", K_IN_G, c, {c->coutr});
+  add_slot(p, pre + ".adn.N.bias", K_IN_B, c, {c->coutr});
+}
+static void add_twoconv_slots(dunet_plan* p, const std::string& pre, TwoConvW* t) {
+  if (t->has_temb) {
+    add_slot(p, pre + ".temb_proj.weight", K_TP_W, t, {t->a.coutr, 512});
+    add_slot(p, pre + ".temb_proj.bias", K_TP_B, t, {t->a.coutr});
+  }
+  add_convblock_slots(p, pre + ".conv_0", &t->a);
+  add_convblock_slots(p, pre + ".conv_1", &t->b);
+}
+
+static WsLayout ws_layout(const dunet_plan* p, int B) {
+  WsLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  auto act = [&](int ch, int lvl) -> size_t { return (size_t)((size_t)B * ch * (size_t)p->V[lvl] * sizeof(bf16)); };
+  L.in_pack = take(act(p->in_pad, 0));
+  size_t raw_max = 0, part_max = 0;
+  auto upd = [&](int ch, int lvl) {
+    raw_max = std::max(raw_max, act(ch, lvl));
+    part_max = std::max(part_max, (size_t)B * (ch / 8) * 128 * 16 * sizeof(float));
+  };
+  for (int l = 0; l < 5; ++l) upd(p->fp[l], l);
+  for (int l = 4; l >= 1; --l) upd(p->uoutp[l], l - 1);
+  L.raw = take(raw_max);
+  L.mid = take(raw_max);
+  L.partial = take(part_max);
+  L.x_t = take((size_t)B * p->C * p->V[0] * sizeof(float));
+  for (int l = 0; l < 5; ++l) {
+    L.emb[l] = take(act(p->fp[l], l));
+    L.x[l] = take(act(p->fp[l], l));
+    L.epool[l] = l ? take(act(p->fp[l - 1], l)) : 0;
+    L.dpool[l] = l ? take(act(p->fp[l - 1], l)) : 0;
+    L.up[l] = l ? take(act(p->upp[l], l - 1)) : 0;
+    L.u[l] = l ? take(act(p->uoutp[l], l - 1)) : 0;
+  }
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------ layer launchers
+template <int CB_CH, int N_TILE, int ZT>
+static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTcArgs& a, int batch, cudaStream_t st) {
+  using Cfg = ConvTc<CB_CH, N_TILE, ZT>;
+  static bool attr_set = false;
+  auto kern = conv3d_tc_kernel<CB_CH, N_TILE, ZT>;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long grid = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * batch;
+  if (g_prof_on) {
+    if (g_prof_used == g_prof.size()) {
+      ProfRec rec;
+      CUDA_TRY(cudaEventCreate(&rec.a));
+      CUDA_TRY(cudaEventCreate(&rec.b));
+      g_prof.push_back(rec);
+    }
+    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].a, st));
+  }
+  kern<<<(unsigned)grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, a);
+  LAUNCH_CHECK();
+  if (g_prof_on) {
+    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].b, st));
+    ++g_prof_used;
+  }
+  return 0;
+}
+
+constexpr int CONV_ZT = 4;
+
+static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const bf16* src1, bf16* out, int lvl, int B,
+                    cudaStream_t st) {
+  const int D = p->D[lvl], H = p->H[lvl], W = p->W[lvl];
+  if (p->cfg.flags & DUNET_FLAG_REF_CONV) {
+    if (!c.w32) return fail(DUNET_E_STATE, "DUNET_FLAG_REF_CONV needs DUNET_FLAG_KEEP_FP32_WEIGHTS");
+    // the debug kernel writes only the chunks holding real output channels; padded chunks must still be zero
+    CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * c.coutp * p->V[lvl] * sizeof(bf16), st));
+    conv3d_ref_kernel<<<grid_for((long long)B * ((c.coutr + 7) / 8) * p->V[lvl], 128, 148 * 64), 128, 0, st>>>(
+        src0, c.c0r, c.c0p / 8, src1, c.c1r, c.c1p / 8, c.w32, out, c.coutr, c.coutp / 8, D, H, W, B);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  if (g_prof_on) g_prof_flops += 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
+  CUtensorMap t0, t1;
+  TRY(make_act_tmap(&t0, src0, B * (c.c0p / 8), D, H, W, c.cb_ch / 8));
+  if (c.nb1 > 0) TRY(make_act_tmap(&t1, src1, B * (c.c1p / 8), D, H, W, c.cb_ch / 8));
+  else t1 = t0;
+  ConvTcArgs a;
+  a.w = c.packed; a.out = out; a.nb0 = c.nb0; a.nb1 = c.nb1; a.chunks0 = c.c0p / 8; a.chunks1 = c.c1p / 8;
+  a.cout = c.coutp; a.D = D; a.H = H; a.W = W;
+  a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + CONV_ZT - 1) / CONV_ZT;
+  a.n_tiles = c.n_tiles;
+  if (c.cb_ch == 32 && c.n_tile == 64) return launch_conv_tc<32, 64, CONV_ZT>(t0, t1, a, B, st);
+  if (c.cb_ch == 32 && c.n_tile == 128) return launch_conv_tc<32, 128, CONV_ZT>(t0, t1, a, B, st);
+  if (c.cb_ch == 64 && c.n_tile == 64) return launch_conv_tc<64, 64, CONV_ZT>(t0, t1, a, B, st);
+  if (c.cb_ch == 64 && c.n_tile == 128) return launch_conv_tc<64, 128, CONV_ZT>(t0, t1, a, B, st);
+  return fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
+}
+
+static int stats_nseg(long long vox) {
+  long long n = (vox + 8191) / 8192;
+  return (int)std::min<long long>(std::max<long long>(n, 1), 128);
+}
+
+// raw conv output -> IN statistics -> fused normalise/activation(/bias/add/pool)
+static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, float* partial, const float* bias,
+                    const bf16* add, bf16* out, bf16* pooled, int lvl, int B, cudaStream_t st) {
+  const int planes = B * (c.coutp / 8);
+  const int nseg = stats_nseg(p->V[lvl]);
+  in_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(raw, partial, p->V[lvl], nseg);
+  LAUNCH_CHECK();
+  NormActArgs a;
+  a.raw = raw; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias; a.add = add;
+  a.out = out; a.pooled = pooled; a.chunks = c.coutp / 8; a.D = p->D[lvl]; a.H = p->H[lvl]; a.W = p->W[lvl];
+  a.eps = 1e-5f; a.slope = 0.1f;
+  if (pooled) {
+    const long long work = p->V[lvl] / 8;
+    norm_act_kernel<true><<<dim3(grid_for(work, NORM_THREADS, 512), planes), NORM_THREADS, 0, st>>>(a);
+  } else {
+    norm_act_kernel<false><<<dim3(grid_for(p->V[lvl], NORM_THREADS * 4, 512), planes), NORM_THREADS, 0, st>>>(a);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int run_twoconv(const dunet_plan* p, const TwoConvW& t, const bf16* src0, const bf16* src1, const float* temb_bias,
+                       const bf16* add, bf16* out, bf16* pooled, int lvl, int B, uint8_t* ws, const WsLayout& L,
+                       cudaStream_t st) {
+  bf16* raw = reinterpret_cast<bf16*>(ws + L.raw);
+  bf16* mid = reinterpret_cast<bf16*>(ws + L.mid);
+  float* partial = reinterpret_cast<float*>(ws + L.partial);
+  TRY(run_conv(p, t.a, src0, src1, raw, lvl, B, st));
+  TRY(run_norm(p, t.a, raw, partial, temb_bias, nullptr, mid, nullptr, lvl, B, st));
+  TRY(run_conv(p, t.b, mid, nullptr, raw, lvl, B, st));
+  TRY(run_norm(p, t.b, raw, partial, nullptr, add, out, pooled, lvl, B, st));
+  return 0;
+}
+
+static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf16* out, int lvl_in, int B, cudaStream_t st) {
+  const long long total = (long long)B * (d.coutp / 8) * 8 * p->V[lvl_in];
+  deconv2_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in, d.cinp, d.packed, d.bias, out, d.coutp, p->D[lvl_in],
+                                                                  p->H[lvl_in], p->W[lvl_in], B);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_call(const dunet_plan* p, int B, const void* ws) {
+  if (!p) return fail(DUNET_E_INVALID, "plan is NULL");
+  if (!p->committed) return fail(DUNET_E_STATE, "plan not committed (dunet_plan_commit)");
+  if (B < 1 || B > p->cfg.batch_max) return fail(DUNET_E_INVALID, "batch %d outside [1, %d]", B, p->cfg.batch_max);
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 255u)) return fail(DUNET_E_INVALID, "workspace must be non-NULL and 256-byte aligned");
+  return 0;
+}
+
+static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
+  bf16* in_pack = reinterpret_cast<bf16*>(ws + L.in_pack);
+  pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
+      image, p->cfg.in_channels, nullptr, 0, in_pack, p->in_pad, p->V[0], B);
+  LAUNCH_CHECK();
+  for (int l = 0; l < 5; ++l) {
+    const bf16* src = l ? reinterpret_cast<bf16*>(ws + L.epool[l]) : in_pack;
+    bf16* pooled = l < 4 ? reinterpret_cast<bf16*>(ws + L.epool[l + 1]) : nullptr;
+    TRY(run_twoconv(p, p->enc[l], src, nullptr, nullptr, nullptr, reinterpret_cast<bf16*>(ws + L.emb[l]), pooled, l, B,
+                    ws, L, st));
+  }
+  return 0;
+}
+
+// U-Net body given in_pack = cat([image, x_t]); leaves u1 in ws.u[1]
+static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
+  bf16* in_pack = reinterpret_cast<bf16*>(ws + L.in_pack);
+  for (int l = 0; l < 5; ++l) {
+    const bf16* src = l ? reinterpret_cast<bf16*>(ws + L.dpool[l]) : in_pack;
+    bf16* pooled = l < 4 ? reinterpret_cast<bf16*>(ws + L.dpool[l + 1]) : nullptr;
+    TRY(run_twoconv(p, p->den[l], src, nullptr, temb_row + p->temb_off[l], reinterpret_cast<bf16*>(ws + L.emb[l]),
+                    reinterpret_cast<bf16*>(ws + L.x[l]), pooled, l, B, ws, L, st));
+  }
+  const bf16* prev = reinterpret_cast<bf16*>(ws + L.x[4]);
+  for (int l = 4; l >= 1; --l) {
+    bf16* up = reinterpret_cast<bf16*>(ws + L.up[l]);
+    TRY(run_deconv(p, p->dec[l], prev, up, l, B, st));
+    TRY(run_twoconv(p, p->upc[l], reinterpret_cast<bf16*>(ws + L.x[l - 1]), up, temb_row + p->temb_off[5 + (4 - l)], nullptr,
+                    reinterpret_cast<bf16*>(ws + L.u[l]), nullptr, l - 1, B, ws, L, st));
+    prev = reinterpret_cast<bf16*>(ws + L.u[l]);
+  }
+  return 0;
+}
+
+static int launch_temb(dunet_plan* p, const int* d_t, int rows, float* table, cudaStream_t st) {
+  TembArgs a;
+  a.w0 = p->dense[0]; a.b0 = p->dense[1]; a.w1 = p->dense[2]; a.b1 = p->dense[3];
+  const TwoConvW* blocks[9] = {&p->den[0], &p->den[1], &p->den[2], &p->den[3], &p->den[4],
+                               &p->upc[4], &p->upc[3], &p->upc[2], &p->upc[1]};
+  for (int i = 0; i < 9; ++i) {
+    a.pw[i] = blocks[i]->tp_w; a.pb[i] = blocks[i]->tp_b; a.pc[i] = blocks[i]->a.coutr; a.poff[i] = p->temb_off[i];
+  }
+  a.row = p->temb_row; a.tmap = d_t; a.table = table;
+  temb_table_kernel<<<rows, 512, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) {
+  final_ddim_kernel<<<grid_for((long long)a.batch * a.vox, 128, 148 * 32), 128, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ================================================================================================== C ABI
+extern "C" {
+
+int dunet_version(void) { return DUNET_VERSION; }
+const char* dunet_last_error(void) { return g_err.c_str(); }
+uint64_t dunet_launch_count(void) { return g_launches.load(); }
+
+int dunet_profile_enable(int32_t on) {
+  g_prof_used = 0;
+  g_prof_flops = 0.0;
+  g_prof_on = on != 0;
+  return 0;
+}
+
+int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_flops) {
+  if (!conv_ms || !conv_launches || !conv_flops) return fail(DUNET_E_INVALID, "NULL argument");
+  double total = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
+    total += ms;
+  }
+  *conv_ms = total; *conv_launches = g_prof_used; *conv_flops = g_prof_flops;
+  return 0;
+}
+
+int dunet_debug_barrier_timeouts(uint32_t* out_flag) {
+  if (!out_flag) return fail(DUNET_E_INVALID, "out_flag is NULL");
+  CUDA_TRY(cudaMemcpyFromSymbol(out_flag, g_barrier_timeout_flag, sizeof(uint32_t)));
+  return 0;
+}
+
+int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
+  if (!out || !cfg) return fail(DUNET_E_INVALID, "NULL argument");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(DUNET_E_UNSUPPORTED, "libdunet_b200 needs an sm_100a device (found sm_%d%d); there is no fallback path", prop.major, prop.minor);
+  if (cfg->in_channels != 1) return fail(DUNET_E_UNSUPPORTED, "only in_channels == 1 is implemented");
+  if (cfg->num_classes < 1 || cfg->num_classes + cfg->in_channels > 32 || cfg->num_classes > FINAL_MAX_C)
+    return fail(DUNET_E_UNSUPPORTED, "num_classes must be in [1, 31]");
+  for (int d = 0; d < 3; ++d)
+    if (cfg->patch[d] < 32 || cfg->patch[d] % 16) return fail(DUNET_E_INVALID, "patch edge %d must be a multiple of 16 and >= 32", cfg->patch[d]);
+  for (int i = 0; i < 6; ++i)
+    if (cfg->features[i] < 1 || cfg->features[i] > 2048) return fail(DUNET_E_INVALID, "features[%d] = %d out of range", i, cfg->features[i]);
+  if (cfg->features[4] % 2 || cfg->features[3] % 2 || cfg->features[2] % 2)
+    return fail(DUNET_E_INVALID, "features[2..4] must be even (UpCat halves the channels)");
+  if (cfg->batch_max < 1 || cfg->num_steps < 1 || cfg->num_steps > 1000) return fail(DUNET_E_INVALID, "bad batch_max / num_steps");
+  if (pad_to(cfg->features[5], 64) > FINAL_MAX_F) return fail(DUNET_E_UNSUPPORTED, "features[5] > %d not implemented", FINAL_MAX_F);
+
+  dunet_plan* p = new dunet_plan();
+  p->cfg = *cfg;
+  p->C = cfg->num_classes;
+  for (int l = 0; l < 5; ++l) {
+    p->D[l] = cfg->patch[0] >> l; p->H[l] = cfg->patch[1] >> l; p->W[l] = cfg->patch[2] >> l;
+    p->V[l] = (long long)p->D[l] * p->H[l] * p->W[l];
+  }
+  for (int i = 0; i < 6; ++i) { p->fr[i] = cfg->features[i]; p->fp[i] = pad_to(cfg->features[i], 64); }
+  // UpCat(in=f[l], cat=f[l-1], out, halves): denoiser.py:276-280
+  for (int l = 4; l >= 1; --l) {
+    p->upr[l] = (l == 1) ? p->fr[1] : p->fr[l] / 2;
+    p->upp[l] = pad_to(p->upr[l], 64);
+    p->uoutr[l] = (l == 1) ? p->fr[5] : p->fr[l - 1];
+    p->uoutp[l] = pad_to(p->uoutr[l], 64);
+  }
+  // encoder (no temb), pretrained/basic_unet.py:491-494
+  for (int l = 0; l < 5; ++l) {
+    TwoConvW& e = p->enc[l];
+    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0]);
+    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l]);
+    e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l]);
+    TwoConvW& d = p->den[l];
+    d.has_temb = true;
+    if (l == 0) d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0]);
+    else d.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l]);
+    d.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l]);
+  }
+  for (int l = 4; l >= 1; --l) {
+    TwoConvW& u = p->upc[l];
+    u.has_temb = true;
+    u.a.shape(p->fr[l - 1], p->fp[l - 1], p->upr[l], p->upp[l], p->uoutr[l]);  // cat([skip, up]) denoiser.py:190
+    u.b.shape(p->uoutr[l], p->uoutp[l], 0, 0, p->uoutr[l]);
+    DeconvW& d = p->dec[l];
+    d.cinr = p->fr[l]; d.cinp = p->fp[l]; d.coutr = p->upr[l]; d.coutp = p->upp[l];
+  }
+  // checkpoint keys
+  add_twoconv_slots(p, "embed_model.conv_0", &p->enc[0]);
+  for (int l = 1; l < 5; ++l) add_twoconv_slots(p, "embed_model.down." + std::to_string(l - 1) + ".convs", &p->enc[l]);
+  add_slot(p, "model.temb.dense.0.weight", K_DENSE, p, {512, 128}, 0);
+  add_slot(p, "model.temb.dense.0.bias", K_DENSE, p, {512}, 1);
+  add_slot(p, "model.temb.dense.1.weight", K_DENSE, p, {512, 512}, 2);
+  add_slot(p, "model.temb.dense.1.bias", K_DENSE, p, {512}, 3);
+  add_twoconv_slots(p, "model.conv_0", &p->den[0]);
+  for (int l = 1; l < 5; ++l) add_twoconv_slots(p, "model.down_" + std::to_string(l) + ".convs", &p->den[l]);
+  for (int l = 4; l >= 1; --l) {
+    const std::string pre = "model.upcat_" + std::to_string(l);
+    add_slot(p, pre + ".upsample.deconv.weight", K_DECONV_W, &p->dec[l], {p->dec[l].cinr, p->dec[l].coutr, 2, 2, 2});
+    add_slot(p, pre + ".upsample.deconv.bias", K_DECONV_B, &p->dec[l], {p->dec[l].coutr});
+    add_twoconv_slots(p, pre + ".convs", &p->upc[l]);
+  }
+  add_slot(p, "model.final_conv.weight", K_FINAL_W, p, {p->C, p->fr[5], 1, 1, 1});
+  add_slot(p, "model.final_conv.bias", K_FINAL_B, p, {p->C});
+  // temb bias table geometry: 9 TwoConv blocks in forward order
+  {
+    const TwoConvW* blocks[9] = {&p->den[0], &p->den[1], &p->den[2], &p->den[3], &p->den[4],
+                                 &p->upc[4], &p->upc[3], &p->upc[2], &p->upc[1]};
+    int off = 0;
+    for (int i = 0; i < 9; ++i) { p->temb_off[i] = off; off += blocks[i]->a.coutp; }
+    p->temb_row = off;
+  }
+  *out = p;
+  return 0;
+}
+
+void dunet_plan_destroy(dunet_plan* p) {
+  if (!p) return;
+  for (void* q : p->owned) cudaFree(q);
+  delete p;
+}
+
+int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, const int64_t* shape, int32_t ndim, void* stream) {
+  if (!p || !key || !src || !shape) return fail(DUNET_E_INVALID, "NULL argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto it = p->slots.find(key);
+  if (it == p->slots.end()) return fail(DUNET_E_INVALID, "unexpected checkpoint key '%s'", key);
+  Slot& s = it->second;
+  if ((int)s.shape.size() != ndim) return fail(DUNET_E_INVALID, "key '%s': expected %zu dims, got %d", key, s.shape.size(), ndim);
+  for (int i = 0; i < ndim; ++i)
+    if (s.shape[i] != shape[i]) return fail(DUNET_E_INVALID, "key '%s': dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)s.shape[i]);
+  if (!aligned16(src)) return fail(DUNET_E_INVALID, "key '%s': pointer not 16-byte aligned", key);
+  p->committed = false;
+  switch (s.kind) {
+    case K_CONV_W: {
+      ConvW* c = static_cast<ConvW*>(s.obj);
+      if (!c->packed) TRY(dev_alloc(p, (void**)&c->packed, c->packed_elems() * sizeof(bf16)));
+      const int cinr = c->c0r + c->c1r;
+      pack_conv_w_kernel<<<grid_for((long long)c->packed_elems(), 256), 256, 0, st>>>(
+          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->nb0 + c->nb1, c->n_tiles);
+      LAUNCH_CHECK();
+      if (p->cfg.flags & DUNET_FLAG_KEEP_FP32_WEIGHTS) {
+        const size_t bytes = (size_t)c->coutr * cinr * 27 * sizeof(float);
+        if (!c->w32) TRY(dev_alloc(p, (void**)&c->w32, bytes));
+        CUDA_TRY(cudaMemcpyAsync(c->w32, src, bytes, cudaMemcpyDeviceToDevice, st));
+      }
+      c->have_w = true;
+      break;
+    }
+    case K_CONV_B:  // a per-channel constant before InstanceNorm is removed by the mean subtraction
+      static_cast<ConvW*>(s.obj)->have_cb = true;
+      break;
+    case K_IN_G:
+    case K_IN_B: {
+      ConvW* c = static_cast<ConvW*>(s.obj);
+      float** dst = s.kind == K_IN_G ? &c->gamma : &c->beta;
+      if (!*dst) TRY(dev_alloc(p, (void**)dst, c->coutp * sizeof(float)));
+      copy_pad_rows_kernel<<<1, 256, 0, st>>>(src, *dst, 1, c->coutr, 1, c->coutp);  // padded channels: gamma = beta = 0
+      LAUNCH_CHECK();
+      (s.kind == K_IN_G ? c->have_g : c->have_b) = true;
+      break;
+    }
+    case K_TP_W:
+    case K_TP_B: {
+      TwoConvW* t = static_cast<TwoConvW*>(s.obj);
+      const size_t n = s.kind == K_TP_W ? (size_t)t->a.coutr * 512 : (size_t)t->a.coutr;
+      float** dst = s.kind == K_TP_W ? &t->tp_w : &t->tp_b;
+      if (!*dst) TRY(dev_alloc(p, (void**)dst, n * sizeof(float)));
+      CUDA_TRY(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      (s.kind == K_TP_W ? t->have_tpw : t->have_tpb) = true;
+      break;
+    }
+    case K_DENSE: {
+      size_t n = 1;
+      for (auto d : s.shape) n *= (size_t)d;
+      if (!p->dense[s.idx]) TRY(dev_alloc(p, (void**)&p->dense[s.idx], n * sizeof(float)));
+      CUDA_TRY(cudaMemcpyAsync(p->dense[s.idx], src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    }
+    case K_DECONV_W: {
+      DeconvW* d = static_cast<DeconvW*>(s.obj);
+      const size_t n = 8ull * d->cinp * d->coutp;
+      if (!d->packed) TRY(dev_alloc(p, (void**)&d->packed, n * sizeof(bf16)));
+      pack_deconv_w_kernel<<<grid_for((long long)n, 256), 256, 0, st>>>(src, d->packed, d->cinr, d->coutr, d->cinp, d->coutp);
+      LAUNCH_CHECK();
+      d->have_w = true;
+      break;
+    }
+    case K_DECONV_B: {
+      DeconvW* d = static_cast<DeconvW*>(s.obj);
+      if (!d->bias) TRY(dev_alloc(p, (void**)&d->bias, d->coutp * sizeof(float)));
+      copy_pad_rows_kernel<<<1, 256, 0, st>>>(src, d->bias, 1, d->coutr, 1, d->coutp);
+      LAUNCH_CHECK();
+      d->have_b = true;
+      break;
+    }
+    case K_FINAL_W: {
+      if (!p->final_w) TRY(dev_alloc(p, (void**)&p->final_w, (size_t)p->C * p->fp[5] * sizeof(float)));
+      copy_pad_rows_kernel<<<grid_for((long long)p->C * p->fp[5], 256), 256, 0, st>>>(src, p->final_w, p->C, p->fr[5], p->C, p->fp[5]);
+      LAUNCH_CHECK();
+      break;
+    }
+    case K_FINAL_B: {
+      if (!p->final_b) TRY(dev_alloc(p, (void**)&p->final_b, p->C * sizeof(float)));
+      CUDA_TRY(cudaMemcpyAsync(p->final_b, src, p->C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      break;
+    }
+  }
+  s.seen = true;
+  return 0;
+}
+
+int dunet_plan_set_schedule(dunet_plan* p, int32_t n, const int32_t* tmap, const float* sr, const float* srm1, const float* acp) {
+  if (!p || !tmap || !sr || !srm1 || !acp) return fail(DUNET_E_INVALID, "NULL argument");
+  if (n != p->cfg.num_steps) return fail(DUNET_E_INVALID, "schedule has %d steps, plan was created for %d", n, p->cfg.num_steps);
+  p->n_steps = n;
+  p->tmap.assign(tmap, tmap + n);
+  p->sr.assign(sr, sr + n); p->srm1.assign(srm1, srm1 + n); p->acp.assign(acp, acp + n);
+  for (int i = 0; i < n; ++i)
+    if (!(srm1[i] > 0.f) || tmap[i] < 0) return fail(DUNET_E_INVALID, "schedule entry %d invalid", i);
+  p->committed = false;
+  return 0;
+}
+
+int dunet_plan_commit(dunet_plan* p, void* stream) {
+  if (!p) return fail(DUNET_E_INVALID, "plan is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (auto& kv : p->slots)
+    if (!kv.second.seen) return fail(DUNET_E_STATE, "checkpoint key '%s' was never set (%zu keys expected)", kv.first.c_str(), p->slots.size());
+  if (p->n_steps == 0) return fail(DUNET_E_STATE, "schedule not set (dunet_plan_set_schedule)");
+  if (!p->d_tmap) TRY(dev_alloc(p, (void**)&p->d_tmap, (p->n_steps + 1) * sizeof(int)));
+  if (!p->temb_table) TRY(dev_alloc(p, (void**)&p->temb_table, (size_t)(p->n_steps + 1) * p->temb_row * sizeof(float)));
+  CUDA_TRY(cudaMemsetAsync(p->temb_table, 0, (size_t)(p->n_steps + 1) * p->temb_row * sizeof(float), st));
+  CUDA_TRY(cudaMemcpyAsync(p->d_tmap, p->tmap.data(), p->n_steps * sizeof(int), cudaMemcpyHostToDevice, st));
+  TRY(launch_temb(p, p->d_tmap, p->n_steps, p->temb_table, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // host vector above must outlive the copy; commit is a setup-time call
+  p->committed = true;
+  return 0;
+}
+
+int dunet_workspace_bytes(const dunet_plan* p, int32_t batch, size_t* out) {
+  if (!p || !out) return fail(DUNET_E_INVALID, "NULL argument");
+  if (batch < 1 || batch > p->cfg.batch_max) return fail(DUNET_E_INVALID, "batch %d outside [1, %d]", batch, p->cfg.batch_max);
+  *out = ws_layout(p, batch).total;
+  return 0;
+}
+
+int dunet_encode(dunet_plan* p, const float* image, int32_t B, void* workspace, void* stream) {
+  TRY(check_call(p, B, workspace));
+  if (!image || !aligned16(image)) return fail(DUNET_E_INVALID, "image must be a 16-byte aligned device pointer");
+  return encode_impl(p, image, B, static_cast<uint8_t*>(workspace), ws_layout(p, B), static_cast<cudaStream_t>(stream));
+}
+
+int dunet_get_embedding(dunet_plan* p, int32_t level, float* out, int32_t B, void* workspace, void* stream) {
+  TRY(check_call(p, B, workspace));
+  if (level < 0 || level > 4 || !out) return fail(DUNET_E_INVALID, "bad level / NULL out");
+  const WsLayout L = ws_layout(p, B);
+  unpack_c8_kernel<<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + L.emb[level]), p->fp[level], out, p->fr[level], p->V[level], B);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_set_embedding(dunet_plan* p, int32_t level, const float* in, int32_t B, void* workspace, void* stream) {
+  TRY(check_call(p, B, workspace));
+  if (level < 0 || level > 4 || !in) return fail(DUNET_E_INVALID, "bad level / NULL in");
+  const WsLayout L = ws_layout(p, B);
+  pack_c8_kernel<<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, p->fr[level], nullptr, 0, reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + L.emb[level]), p->fp[level],
+      p->V[level], B);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int32_t t_original, float* logits_out,
+                       int32_t B, void* workspace, void* stream) {
+  TRY(check_call(p, B, workspace));
+  if (!x_t || !image || !logits_out) return fail(DUNET_E_INVALID, "NULL tensor argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const WsLayout L = ws_layout(p, B);
+  int row = -1;
+  for (int i = 0; i < p->n_steps; ++i)
+    if (p->tmap[i] == t_original) row = i;
+  if (row < 0) {  // timestep outside the respaced schedule (training-style call): build its row in the scratch slot
+    row = p->n_steps;
+    CUDA_TRY(cudaMemcpyAsync(p->d_tmap + row, &t_original, sizeof(int), cudaMemcpyHostToDevice, st));
+    TRY(launch_temb(p, p->d_tmap + row, 1, p->temb_table + (size_t)row * p->temb_row, st));
+  }
+  pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
+      image, p->cfg.in_channels, x_t, p->C, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
+  LAUNCH_CHECK();
+  TRY(unet_body(p, p->temb_table + (size_t)row * p->temb_row, B, ws, L, st));
+  FinalDdimArgs a;
+  memset(&a, 0, sizeof a);
+  a.feat = reinterpret_cast<bf16*>(ws + L.u[1]); a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
+  a.image = image; a.logits_out = logits_out; a.in_pad = p->in_pad; a.vox = p->V[0]; a.batch = B;
+  a.r = 1.f; a.m = 1.f; a.abp = 1.f;
+  return launch_final(p, a, st);
+}
+
+int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
+                      float* final_x, int32_t B, int32_t run_encoder, void* workspace, void* stream) {
+  TRY(check_call(p, B, workspace));
+  if (!image || !noise || !acc_out) return fail(DUNET_E_INVALID, "NULL tensor argument");
+  if (!aligned16(image) || !aligned16(noise) || !aligned16(acc_out)) return fail(DUNET_E_INVALID, "tensors must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const WsLayout L = ws_layout(p, B);
+  const size_t state_bytes = (size_t)B * p->C * p->V[0] * sizeof(float);
+  float* x_t = reinterpret_cast<float*>(ws + L.x_t);
+  if (run_encoder) TRY(encode_impl(p, image, B, ws, L, st));
+  CUDA_TRY(cudaMemcpyAsync(x_t, noise, state_bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(acc_out, 0, state_bytes, st));
+  pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
+      image, p->cfg.in_channels, x_t, p->C, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
+  LAUNCH_CHECK();
+  for (int i = p->n_steps - 1, k = 0; i >= 0; --i, ++k) {  // gaussian_diffusion.py:694 indices high -> low
+    TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st));
+    FinalDdimArgs a;
+    memset(&a, 0, sizeof a);
+    a.feat = reinterpret_cast<bf16*>(ws + L.u[1]); a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
+    a.image = image; a.x_t = x_t; a.acc = acc_out;
+    a.logits_out = per_step_logits ? per_step_logits + (size_t)k * B * p->C * p->V[0] : nullptr;
+    a.next_in = i > 0 ? reinterpret_cast<bf16*>(ws + L.in_pack) : nullptr;
+    a.in_pad = p->in_pad; a.vox = p->V[0]; a.batch = B;
+    a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
+    TRY(launch_final(p, a, st));
+  }
+  if (final_x) CUDA_TRY(cudaMemcpyAsync(final_x, x_t, state_bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+static int check_box(const int32_t v[3], const int32_t pd[3], const int32_t s[3]) {
+  for (int d = 0; d < 3; ++d)
+    if (pd[d] < 1 || v[d] < 1 || s[d] < 0 || s[d] + pd[d] > v[d])
+      return fail(DUNET_E_INVALID, "window [%d, %d) outside volume extent %d on axis %d", s[d], s[d] + pd[d], v[d], d);
+  return 0;
+}
+
+int dunet_crop_window(const float* volume, const int32_t v[3], float* patch, const int32_t pd[3], const int32_t s[3], void* stream) {
+  if (!volume || !patch || !v || !pd || !s) return fail(DUNET_E_INVALID, "NULL argument");
+  TRY(check_box(v, pd, s));
+  crop_window_kernel<<<grid_for((long long)pd[0] * pd[1] * pd[2], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      volume, patch, v[0], v[1], v[2], pd[0], pd[1], pd[2], s[0], s[1], s[2]);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_stitch_add(float* out_volume, const int32_t v[3], int32_t channels, const float* patch, const int32_t pd[3],
+                     const int32_t s[3], void* stream) {
+  if (!out_volume || !patch || !v || !pd || !s || channels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  TRY(check_box(v, pd, s));
+  stitch_add_kernel<<<grid_for((long long)channels * pd[0] * pd[1] * pd[2], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out_volume, patch, channels, v[0], v[1], v[2], pd[0], pd[1], pd[2], s[0], s[1], s[2]);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_finalize(float* out_volume, const int32_t v[3], int32_t channels, const int32_t* cd, const int32_t* ch,
+                   const int32_t* cw, uint8_t* binary, uint8_t* argmax_labels, void* stream) {
+  if (!out_volume || !v || !cd || !ch || !cw || channels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  finalize_kernel<<<grid_for((long long)v[0] * v[1] * v[2], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out_volume, cd, ch, cw, binary, argmax_labels, channels, v[0], v[1], v[2]);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t c1, const float* weight, int32_t cout,
+                       float* out, int32_t B, const int32_t dims[3], int32_t use_ref, void* stream) {
+  if (!src0 || !weight || !out || !dims || c0 < 1 || cout < 1 || B < 1) return fail(DUNET_E_INVALID, "bad argument");
+  if (c1 > 0 && !src1) return fail(DUNET_E_INVALID, "src1 is NULL but c1 > 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dunet_plan tmp;  // only geometry fields are used by run_conv
+  memset(&tmp.cfg, 0, sizeof tmp.cfg);
+  tmp.cfg.flags = use_ref ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : 0;
+  tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
+  tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
+  ConvW c;
+  const bool small = (c1 == 0 && c0 <= 32);
+  c.shape(c0, small ? 32 : pad_to(c0, 64), c1, c1 > 0 ? pad_to(c1, 64) : 0, cout);
+  if (c1 > 0 && (c0 % 8)) return fail(DUNET_E_UNSUPPORTED, "concat needs c0 %% 8 == 0");
+  const long long vox = tmp.V[0];
+  bf16 *a0 = nullptr, *a1 = nullptr, *raw = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&a0, (size_t)B * c.c0p * vox * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&raw, (size_t)B * c.coutp * vox * sizeof(bf16), st));
+  pack_c8_kernel<<<grid_for((long long)B * (c.c0p / 8) * vox, 256), 256, 0, st>>>(src0, c0, nullptr, 0, a0, c.c0p, vox, B);
+  LAUNCH_CHECK();
+  if (c1 > 0) {
+    CUDA_TRY(cudaMallocAsync((void**)&a1, (size_t)B * c.c1p * vox * sizeof(bf16), st));
+    pack_c8_kernel<<<grid_for((long long)B * (c.c1p / 8) * vox, 256), 256, 0, st>>>(src1, c1, nullptr, 0, a1, c.c1p, vox, B);
+    LAUNCH_CHECK();
+  }
+  int rc = 0;
+  if (use_ref) {
+    c.w32 = const_cast<float*>(weight);
+  } else {
+    CUDA_TRY(cudaMallocAsync((void**)&c.packed, c.packed_elems() * sizeof(bf16), st));
+    pack_conv_w_kernel<<<grid_for((long long)c.packed_elems(), 256), 256, 0, st>>>(
+        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.nb0 + c.nb1, c.n_tiles);
+    LAUNCH_CHECK();
+  }
+  rc = run_conv(&tmp, c, a0, a1, raw, 0, B, st);
+  if (rc == 0) {
+    unpack_c8_kernel<<<grid_for((long long)B * (c.coutp / 8) * vox, 256), 256, 0, st>>>(raw, c.coutp, out, cout, vox, B);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(DUNET_E_CUDA, "unpack launch failed");
+  }
+  cudaFreeAsync(a0, st);
+  cudaFreeAsync(raw, st);
+  if (a1) cudaFreeAsync(a1, st);
+  if (c.packed) cudaFreeAsync(c.packed, st);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+"""Window driver + Engine.infer equivalent for the B200 path.
+
+``sliding_window_inference`` keeps the positional signature the reference uses at engine.py:173-177
+(``(inputs, roi_size, sw_batch_size, predictor, overlap, **kwargs)``; MONAI constant blend).
+Grid / count map are integer host math (windows.py); crop, stitch (``out[slices] += pred`` in window order) and
+``out /= count`` (+ sigmoid > 0.5, engine.py:179-180) run in CUDA kernels through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .windows import axis_counts, window_starts
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class StitchBuffers:
+    """Output accumulator of one volume: fp32 [C, D, H, W] sums + per-axis integer coverage counts."""
+
+    def __init__(self, channels: int, vol: Sequence[int], roi: Sequence[int], overlap: float, device):
+        self.vol = tuple(int(v) for v in vol)
+        self.roi = tuple(int(r) for r in roi)
+        self.channels = channels
+        self.out = torch.zeros((channels,) + self.vol, dtype=torch.float32, device=device)
+        self.counts = [torch.from_numpy(c).to(device) for c in axis_counts(self.vol, self.roi, overlap)]
+
+    def add(self, patch: torch.Tensor, start) -> None:
+        _lib.check(_lib.load().dunet_stitch_add(_ptr(self.out), _lib.i32x3(self.vol), self.channels, _ptr(patch),
+                                               _lib.i32x3(self.roi), _lib.i32x3(start), _stream()))
+
+    def finalize(self, binary: bool = False, argmax: bool = False):
+        b = torch.empty((self.channels,) + self.vol, dtype=torch.uint8, device=self.out.device) if binary else None
+        a = torch.empty(self.vol, dtype=torch.uint8, device=self.out.device) if argmax else None
+        _lib.check(_lib.load().dunet_finalize(_ptr(self.out), _lib.i32x3(self.vol), self.channels, _ptr(self.counts[0]),
+                                             _ptr(self.counts[1]), _ptr(self.counts[2]), _ptr(b), _ptr(a), _stream()))
+        return self.out, b, a
+
+
+def _pad_to_roi(inputs: torch.Tensor, roi) -> Tuple[torch.Tensor, list]:
+    pad = []
+    for k in range(inputs.dim() - 1, 1, -1):
+        diff = max(roi[k - 2] - inputs.shape[k], 0)
+        half = diff // 2
+        pad.extend([half, diff - half])
+    if any(pad):
+        inputs = F.pad(inputs, pad=pad, mode="constant", value=0.0)
+    return inputs, pad
+
+
+def crop_windows(volume: torch.Tensor, starts, roi) -> torch.Tensor:
+    """volume [1, D, H, W] fp32 -> [len(starts), 1, *roi] via the crop kernel."""
+    lib = _lib.load()
+    vol = tuple(volume.shape[-3:])
+    out = torch.empty((len(starts), 1) + tuple(roi), dtype=torch.float32, device=volume.device)
+    for j, s in enumerate(starts):
+        _lib.check(lib.dunet_crop_window(_ptr(volume), _lib.i32x3(vol), _ptr(out[j]), _lib.i32x3(roi), _lib.i32x3(s), _stream()))
+    return out
+
+
+def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable[..., torch.Tensor],
+                             overlap: float = 0.25, mode: str = "constant", window_range: Optional[Tuple[int, int]] = None,
+                             finalize: bool = True, **kwargs):
+    """Constant-blend sliding window on the GPU.  ``predictor(window_batch, **kwargs)`` -> [b, C, *roi].
+
+    ``window_range=(lo, hi)`` restricts the run to a contiguous shard of the window list (multi-GPU); with
+    ``finalize=False`` the un-normalised StitchBuffers is returned instead of the blended volume.
+    """
+    if mode != "constant":
+        raise NotImplementedError("only the blend mode the reference uses (constant) is implemented")
+    if not inputs.is_cuda:
+        raise RuntimeError("sliding_window_inference runs on the GPU only (no CPU fallback)")
+    if inputs.shape[1] != 1:
+        raise NotImplementedError("single-channel inputs only")
+    roi = tuple(int(r) for r in (roi_size if not isinstance(roi_size, int) else (roi_size,) * 3))
+    inputs = inputs.float().contiguous()
+    orig = tuple(inputs.shape[2:])
+    inputs, pad = _pad_to_roi(inputs, roi)
+    inputs = inputs.contiguous()
+    vol = tuple(inputs.shape[2:])
+    starts = window_starts(vol, roi, overlap)
+    n_win = len(starts)
+    lo, hi = (0, n_win) if window_range is None else window_range
+    outs = []
+    with torch.cuda.device(inputs.device):
+        for n in range(inputs.shape[0]):
+            buf = None
+            for g in range(lo, hi, sw_batch_size):
+                grp = starts[g:min(g + sw_batch_size, hi)]
+                batch = crop_windows(inputs[n], grp, roi)
+                pred = predictor(batch, **kwargs)
+                if pred.dtype != torch.float32 or not pred.is_contiguous():
+                    pred = pred.float().contiguous()
+                if buf is None:
+                    buf = StitchBuffers(pred.shape[1], vol, roi, overlap, inputs.device)
+                for j, s in enumerate(grp):
+                    buf.add(pred[j], s)
+            outs.append(buf)
+    if not finalize:
+        return outs
+    res = torch.stack([b.finalize()[0] for b in outs])
+    if any(pad):
+        sl = [slice(None), slice(None)]
+        for d in range(3):
+            lo_ = pad[(2 - d) * 2]
+            sl.append(slice(lo_, lo_ + orig[d]))
+        res = res[tuple(sl)].contiguous()
+    return res
+
+
+@torch.no_grad()
+def infer_volume(model, image: torch.Tensor, sw_batch_size: int = 4, overlap: float = 0.25, noise_fn=None):
+    """``Engine.infer`` for a diffusion model (engine.py:167-182): window driver with pred_type="ddim_sample", then
+    ``(sigmoid(out) > 0.5).float()``.  Returns (blended fp32 volume, binary labels as float)."""
+    roi = model.patch
+    counter = {"w": 0}
+
+    def predictor(batch, pred_type=None):
+        nz = None
+        if noise_fn is not None:
+            nz = noise_fn(counter["w"], batch.shape[0])
+        counter["w"] += batch.shape[0]
+        return model(image=batch, pred_type=pred_type, noise=nz)
+
+    out = sliding_window_inference(image, roi, sw_batch_size, predictor, overlap, pred_type="ddim_sample")
+    labels = (torch.sigmoid(out) > 0.5).float()
+    return out, labels

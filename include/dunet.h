@@ -1,0 +1,140 @@
+/* dunet.h -- C ABI of libdunet_b200.so: the B200-native Diff-UNet DDIM sliding-window inference path.
+ *
+ * The reference (aarchiiive/diff-unet-amos) has no FFI of its own: its seams are Python objects.
+ * Each entry point below names the reference interface it replaces (file:line under /root/reference) -- this is what
+ * a ctypes/cffi binding on the reference side binds.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative DUNET_E_* code on failure; dunet_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread.  Nothing throws across the ABI.
+ *   - the CALLER owns every buffer (inputs, outputs, workspace).  A plan owns only packed weights, the time-embedding
+ *     table and the DDIM coefficient tables.  No hidden allocation after dunet_plan_commit(), no hidden
+ *     synchronisation: all work is enqueued on the caller's stream (a cudaStream_t passed as void*).
+ *   - device pointers must be 16-byte aligned; the workspace pointer 256-byte aligned (checked).
+ *   - boundary tensors are fp32, NCDHW, contiguous -- the reference's layout.  bf16 channels-last staging is internal.
+ *   - a plan is not thread-safe (one plan per GPU / stream); distinct plans are independent.
+ *   - there is NO CPU fallback: every function that computes requires a CUDA device of compute capability 10.x.
+ */
+#ifndef DUNET_H_
+#define DUNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUNET_VERSION 100 /* 0.1.0 */
+
+enum {
+  DUNET_OK = 0,
+  DUNET_E_INVALID = -1,   /* bad argument / shape / alignment */
+  DUNET_E_CUDA = -2,      /* CUDA runtime or driver error (message carries the CUDA error string) */
+  DUNET_E_STATE = -3,     /* call order violated (weights missing, plan not committed, ...) */
+  DUNET_E_UNSUPPORTED = -4 /* configuration outside what the kernels implement */
+};
+
+/* dunet_cfg.flags */
+#define DUNET_FLAG_REF_CONV 1u /* debug: run 3x3x3 convs on the CUDA-core reference kernel instead of tcgen05 (tests) */
+#define DUNET_FLAG_KEEP_FP32_WEIGHTS 2u /* debug: keep fp32 copies of conv weights (needed by DUNET_FLAG_REF_CONV) */
+
+typedef struct dunet_plan dunet_plan;
+
+/* Mirrors DiffUNet.__init__(spatial_dims=3, in_channels, out_channels, image_size, spatial_size, features, ...)
+ * (models/diff_unet.py:10-21) plus the sampler settings hard-coded in Diffusion.__init__
+ * (models/diffusion/diffusion.py:38-45: 10 respaced DDIM steps). */
+typedef struct dunet_cfg {
+  int32_t num_classes;  /* out_channels C; the denoiser input has in_channels + C channels (denoiser.py:298) */
+  int32_t in_channels;  /* image channels; only 1 is implemented (AMOS/BTCV/MSD CT) */
+  int32_t patch[3];     /* window (D, H, W); each a multiple of 16 and >= 32 */
+  int32_t features[6];  /* models/diff_unet.py:17, default {64,64,128,256,512,64} */
+  int32_t batch_max;    /* windows processed together (the reference loops at batch 1, diffusion.py:88-89) */
+  int32_t num_steps;    /* DDIM steps N of space_timesteps(1000, [N]) */
+  uint32_t flags;
+} dunet_cfg;
+
+int dunet_version(void);
+const char* dunet_last_error(void);
+
+/* replaces: DiffUNet(...) construction, models/diff_unet.py:9-35 */
+int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg);
+void dunet_plan_destroy(dunet_plan* plan);
+
+/* replaces: model.load_state_dict(torch.load(path)['model']), test.py:85-91.  `key` is the reference checkpoint key
+ * (e.g. "model.upcat_4.upsample.deconv.weight"); `dev_ptr` an fp32 device tensor in the reference's
+ * own layout ([Cout,Cin,3,3,3] convs, [Cin,Cout,2,2,2] transposed convs).  The plan re-packs into its kernel layout. */
+int dunet_plan_set_weight(dunet_plan* plan, const char* key, const float* dev_ptr, const int64_t* shape, int32_t ndim,
+                          void* stream);
+
+/* replaces: SpacedDiffusion tables + _WrappedModel timestep map (guided_diffusion/respace.py:72-86,123-129;
+ * gaussian_diffusion.py:131-147).  Host arrays of length n_steps; the float tables are the float64 tables cast to fp32
+ * exactly as _extract_into_tensor does (gaussian_diffusion.py:914). */
+int dunet_plan_set_schedule(dunet_plan* plan, int32_t n_steps, const int32_t* timestep_map,
+                            const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod,
+                            const float* alphas_cumprod_prev);
+
+/* Validates that all weights + schedule are present and builds the per-(step, TwoConv) time-embedding bias table
+ * (TimeStepEmbedder + temb_proj, models/diffusion/utils.py:31-54, denoiser.py:51-52,65). */
+int dunet_plan_commit(dunet_plan* plan, void* stream);
+
+int dunet_workspace_bytes(const dunet_plan* plan, int32_t batch, size_t* out_bytes);
+
+/* replaces: BasicUNetEncoder.forward(image), models/basic_unet/pretrained/basic_unet.py:496-512.
+ * image: [batch, 1, D, H, W] fp32.  The five feature maps stay in the workspace (bf16) for the denoiser. */
+int dunet_encode(dunet_plan* plan, const float* image, int32_t batch, void* workspace, void* stream);
+/* copies feature map `level` (0..4) out as fp32 NCDHW [batch, features[level], D>>level, ...] / back in */
+int dunet_get_embedding(dunet_plan* plan, int32_t level, float* out, int32_t batch, void* workspace, void* stream);
+int dunet_set_embedding(dunet_plan* plan, int32_t level, const float* in, int32_t batch, void* workspace, void* stream);
+
+/* replaces: BasicUNetRDenoiser.forward(x, t, image=, embeddings=), models/basic_unet/denoiser.py:284-312, as called
+ * from GaussianDiffusion.p_mean_variance (gaussian_diffusion.py:259).  `t_original` is the ORIGINAL timestep (after
+ * the respace remap), identical for the whole batch.  Embeddings are those left in the workspace by dunet_encode /
+ * dunet_set_embedding.  logits_out: [batch, C, D, H, W] fp32. */
+int dunet_denoise_step(dunet_plan* plan, const float* x_t, const float* image, int32_t t_original, float* logits_out,
+                       int32_t batch, void* workspace, void* stream);
+
+/* replaces: Diffusion.ddim_sample(image) for a batch of windows (models/diffusion/diffusion.py:86-102), i.e.
+ * embed_model + SpacedDiffusion.ddim_sample_loop (gaussian_diffusion.py:626-716) + the sum of the N clamped x0
+ * predictions.  noise: [batch, C, D, H, W] fp32 initial x_T (gaussian_diffusion.py:690-693); acc_out receives
+ * sum_k clamp(model_output_k, -1, 1); per_step_logits (nullable): [n_steps, batch, C, D, H, W] raw model outputs in
+ * loop order (t high -> low); final_x (nullable): the last sample.  run_encoder == 0 skips the encoder and uses the
+ * embeddings already in the workspace (the reference's ddim_sample_loop(model, shape, model_kwargs={image, embeddings})
+ * seam, gaussian_diffusion.py:626-665). */
+int dunet_ddim_sample(dunet_plan* plan, const float* image, const float* noise, float* acc_out, float* per_step_logits,
+                      float* final_x, int32_t batch, int32_t run_encoder, void* workspace, void* stream);
+
+/* replaces: the body of monai.inferers.sliding_window_inference as called at engine.py:173-177 (constant blend):
+ * window crop, `out[slices] += pred`, `out /= count`, and Engine.infer's sigmoid+threshold (engine.py:179-180). */
+int dunet_crop_window(const float* volume, const int32_t vol_dims[3], float* patch, const int32_t patch_dims[3],
+                      const int32_t start[3], void* stream);
+int dunet_stitch_add(float* out_volume, const int32_t vol_dims[3], int32_t channels, const float* patch,
+                     const int32_t patch_dims[3], const int32_t start[3], void* stream);
+/* counts_d/h/w: device int32 arrays, number of windows covering each coordinate along that axis (the window grid is a
+ * Cartesian product so count(z,y,x) = counts_d[z]*counts_h[y]*counts_w[x]).  binary/argmax_labels nullable. */
+int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channels, const int32_t* counts_d,
+                   const int32_t* counts_h, const int32_t* counts_w, uint8_t* binary, uint8_t* argmax_labels,
+                   void* stream);
+
+/* Stand-alone operator (also the unit-test seam of the tensor-core kernel): y = conv3d(cat([src0, src1]), weight),
+ * 3x3x3, stride 1, zero padding 1, no bias.  fp32 NCDHW in/out, bf16 operands + fp32 accumulation inside.
+ * replaces: nn.Conv3d inside MONAI Convolution (denoiser.py:56-58).  use_ref_kernel != 0 selects the debug CUDA-core
+ * kernel.  Allocates its own scratch with cudaMallocAsync on `stream`. */
+int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t c1, const float* weight, int32_t cout,
+                       float* out, int32_t batch, const int32_t dims[3], int32_t use_ref_kernel, void* stream);
+
+/* Live kernel timing for bench.py's roofline: when enabled, every 3x3x3-conv launch is bracketed by CUDA events on the
+ * launching stream.  dunet_profile_read synchronises those events and returns, since the last enable: summed conv
+ * kernel time (ms), number of conv launches, and their ALGORITHMIC flops 2*B*V*Cout*27*Cin (real channels only). */
+int dunet_profile_enable(int32_t on);
+int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_flops);
+
+/* Device-side pipeline watchdog: non-zero if a bounded mbarrier wait expired inside a kernel (kernel bug). */
+int dunet_debug_barrier_timeouts(uint32_t* out_flag);
+/* Number of kernels this library has launched on the calling process since load (bench.py's gpu_launches). */
+uint64_t dunet_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUNET_H_ */

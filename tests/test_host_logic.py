@@ -1,0 +1,106 @@
+"""CPU tests of the product's host logic: window grid, schedule tables, parameter init / checkpoint keys, and the
+C-ABI library exporting every symbol include/dunet.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import diff_unet_amos_b200 as pkg
+from diff_unet_amos_b200 import _lib, windows
+from diff_unet_amos_b200.schedule import DdimSchedule
+from oracle import oracle_ddim, oracle_sliding
+from tests.util import GOLDEN, SMALL
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("vol,roi,ov", [((512, 512, 160), (96, 96, 96), 0.25), ((512, 512, 160), (96, 96, 96), 0.8),
+                                        ((512, 512, 160), (128, 128, 128), 0.25), ((48, 48, 40), (32, 32, 32), 0.25),
+                                        ((96, 200, 96), (96, 96, 96), 0.5), ((97, 131, 33), (32, 48, 32), 0.1),
+                                        ((32, 32, 32), (32, 32, 32), 0.25)])
+def test_window_grid_bit_exact_vs_oracle(vol, roi, ov):
+    ours = windows.window_starts(vol, roi, ov)
+    ref = oracle_sliding.window_grid(vol, roi, ov)
+    assert ours.dtype == np.int64 and np.array_equal(ours, ref)
+    cnt = oracle_sliding.count_map(vol, roi, ref)
+    cd, ch, cw = windows.axis_counts(vol, roi, ov)
+    assert np.array_equal(cd[:, None, None] * ch[None, :, None] * cw[None, None, :], cnt)
+
+
+def test_known_answers():
+    assert len(windows.window_starts((512, 512, 160), (96, 96, 96), 0.25)) == 98
+    assert len(windows.window_starts((512, 512, 160), (96, 96, 96), 0.8)) == 2645
+    assert windows.scan_intervals((512, 512, 160), (96, 96, 96), 0.8) == (19, 19, 19)
+
+
+def test_shard_ranges_cover_and_balance():
+    for n in (98, 2645, 8, 1, 50):
+        for world in (1, 2, 4, 8):
+            spans = [windows.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert max(hi - lo for lo, hi in (windows.shard_range(98, r, 8) for r in range(8))) == 13  # 94 % ceiling
+
+
+@pytest.mark.parametrize("n", [10, 25])
+def test_schedule_matches_reference_tables(n):
+    gold = json.load(open(os.path.join(GOLDEN, "ddim_tables.json")))[str(n)]
+    s = DdimSchedule.build(n)
+    assert s.timestep_map == gold["timestep_map"]
+    for key in ("alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"):
+        ref = np.array([float.fromhex(h) for h in gold[key]])
+        assert np.array_equal(getattr(s, key), ref), key
+    o = oracle_ddim.SpacedSchedule(n)
+    assert np.array_equal(o.alphas_cumprod, s.alphas_cumprod)
+
+
+def test_closed_form_constants():
+    a, b = DdimSchedule.build(10).closed_form()
+    assert np.allclose(a, [1.0, 0.97365769, 0.50212764, 0.33832169, 0.24135542, 0.16651885, 0.10488461, 0.05837202,
+                           0.02833401, 0.01197097], atol=5e-6)
+    assert np.allclose(b[1:3], [0.02813009, 0.55989865], atol=5e-6) and abs(b[0]) < 1e-12
+
+
+@pytest.mark.parametrize("name,cout,feats", [("C16_default", 16, None), ("C2_small", 2, SMALL)])
+def test_parameter_init_and_keys_match_reference(name, cout, feats):
+    gold = json.load(open(os.path.join(GOLDEN, "weights_fingerprint.json")))[name]
+    torch.manual_seed(0)
+    m = pkg.DiffUNetB200(in_channels=1, out_channels=cout, **({"features": feats} if feats else {}))
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(gold["fingerprint"].keys())
+    for k, v in sd.items():
+        d = v.double().flatten()
+        assert [float(d.sum()), float(d.abs().sum()), float(d[0]), float(d[-1])] == gold["fingerprint"][k], k
+    # round trip through the reference's key names
+    m2 = pkg.DiffUNetB200(in_channels=1, out_channels=cout, **({"features": feats} if feats else {}))
+    m2.load_state_dict(sd)
+    assert all(torch.equal(a, b) for a, b in zip(m2.state_dict().values(), sd.values()))
+
+
+def test_forward_dispatch_errors():
+    m = pkg.DiffUNetB200(in_channels=1, out_channels=2, features=SMALL, image_size=32, spatial_size=32)
+    with pytest.raises(NotImplementedError):
+        m(image=torch.zeros(1, 1, 32, 32, 32), pred_type="nope")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(image=torch.zeros(1, 1, 32, 32, 32), pred_type="ddim_sample")
+    x, t, nz = m(x=torch.zeros(2, 2, 8, 8, 8), pred_type="q_sample")
+    assert x.shape == (2, 2, 8, 8, 8) and t.shape == (2,)
+    with pytest.raises(NotImplementedError):
+        pkg.model_hub("swin_unetr")
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "dunet.h")).read()
+    declared = set(re.findall(r"\b(dunet_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dunet_version() == 100
+    assert ctypes.sizeof(_lib.DunetCfg) == 4 * 14
