@@ -126,7 +126,7 @@ def encoder_forward(sd: Dict[str, torch.Tensor], image: torch.Tensor) -> List[to
 def sinusoid_embedding(t: torch.Tensor, dim: int = TEMB_DIM) -> torch.Tensor:
     """get_timestep_embedding (models/diffusion/utils.py:6-25)."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))).to(t.device)
     arg = t.float()[:, None] * freq[None, :]
     return torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
 

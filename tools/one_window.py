@@ -1,0 +1,37 @@
+"""Run ONE 96^3 window (C=16, default features, DDIM-10) through the B200 path: the ncu / timing target.
+usage: python tools/one_window.py [--batch B] [--reps R] [--steps N]"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import diff_unet_amos_b200 as pkg
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--S", type=int, default=96)
+ap.add_argument("--C", type=int, default=16)
+ap.add_argument("--ddim", type=int, default=10)
+a = ap.parse_args()
+torch.manual_seed(0)
+m = pkg.DiffUNetB200(in_channels=1, out_channels=a.C, image_size=a.S, spatial_size=a.S, batch_max=a.batch, num_steps=a.ddim).cuda().eval()
+image = torch.rand(a.batch, 1, a.S, a.S, a.S, device="cuda")
+noise = torch.randn(a.batch, a.C, a.S, a.S, a.S, device="cuda")
+with torch.no_grad():
+    m(image=image, pred_type="ddim_sample", noise=noise)  # warm-up: packs weights, allocates the workspace
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.reps):
+        out = m(image=image, pred_type="ddim_sample", noise=noise)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+ms = e0.elapsed_time(e1) / a.reps
+print(f"window batch {a.batch}: {ms:.2f} ms per call ({ms / a.batch:.2f} ms/window, {1e3 * a.batch / ms:.1f} patches/s), "
+      f"host wall {1e3 * (t1 - t0) / a.reps:.2f} ms, out range [{out.min().item():.2f}, {out.max().item():.2f}]")
