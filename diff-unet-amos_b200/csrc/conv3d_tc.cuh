@@ -18,6 +18,14 @@
 //   * channel concat (UpCat, denoiser.py:190) is free: input-channel blocks [0,nb0) come from tensor map 0 (skip),
 //     the rest from tensor map 1 (upsampled).
 //
+// The same kernel, instantiated with MODE_DECONV2, is the 2x2x2 stride-2 transposed convolution (MONAI UpSample "deconv",
+// denoiser.py:161-170): no halo, one "tap", N = (tap, cout) columns, and an epilogue that adds the bias and scatters
+// each column group to its (2z+dz, 2y+dy, 2x+dx) output voxel.
+// Deep U-Net levels (few voxels, thousands of input channels) split the input-channel blocks over `ksplit` CTAs that
+// write fp32 partial tiles; splitk_reduce_stats_kernel sums them in a fixed order.
+// InstanceNorm statistics (sum, sum of squares per channel, from the fp32 accumulators) are reduced in the epilogue
+// with a warp butterfly and written as one deterministic partial row per CTA.
+//
 // Warp roles (7 warps): 0 = plane producer (TMA), 1 = weight producer (bulk copy), 2 = MMA issuer + TMEM owner,
 // 3..6 = epilogue (TMEM -> registers -> bf16 -> coalesced 16-byte stores, one TMEM lane quadrant each).
 #pragma once
@@ -30,25 +38,29 @@
 
 namespace dunet {
 
-constexpr int CONV_TX = 8, CONV_TY = 16;         // output tile in x, y  (= 128 GEMM rows)
-constexpr int CONV_HX = CONV_TX + 2, CONV_HY = CONV_TY + 2;
+constexpr int CONV_TX = 8, CONV_TY = 16;  // output tile in x, y  (= 128 GEMM rows)
 constexpr int CONV_THREADS = 7 * 32;
+constexpr int MODE_CONV3 = 0, MODE_DECONV2 = 1;
 
-template <int CB_CH, int N_TILE, int ZT>
+template <int CB_CH, int N_TILE, int ZT, int MODE>
 struct ConvTc {
-  static constexpr int KCH = CB_CH / 8;                               // 16-byte K chunks per input-channel block
-  static constexpr int PLANE_BYTES = KCH * CONV_HY * CONV_HX * 16;    // 64 ch: 23040 B
-  static constexpr int A_LBO = CONV_HY * CONV_HX * 16;                // chunk -> chunk
-  static constexpr int A_SBO = CONV_HX * 16;                          // y -> y+1 (next 8-row group)
-  static constexpr int W_UNIT_BYTES = KCH * N_TILE * 16;              // one (tap, cin block, cout tile) weight tile
+  static constexpr int HALO = MODE == MODE_CONV3 ? 1 : 0;
+  static constexpr int HX = CONV_TX + 2 * HALO, HY = CONV_TY + 2 * HALO;
+  static constexpr int TZ = MODE == MODE_CONV3 ? 3 : 1, TYX = MODE == MODE_CONV3 ? 9 : 1, TAPS = TZ * TYX;
+  static constexpr int KCH = CB_CH / 8;                     // 16-byte K chunks per input-channel block
+  static constexpr int PLANE_BYTES = KCH * HY * HX * 16;    // conv, 64 ch: 23040 B
+  static constexpr int A_LBO = HY * HX * 16;                // chunk -> chunk
+  static constexpr int A_SBO = HX * 16;                     // y -> y+1 (next 8-row group)
+  static constexpr int W_UNIT_BYTES = KCH * N_TILE * 16;    // one (tap, cin block, cout tile) weight tile
   static constexpr int B_LBO = N_TILE * 16;
   static constexpr int B_SBO = 128;
-  static constexpr int PLANES = ZT + 2;
-  static constexpr int A_SLOTS = (PLANES + 2) < 8 ? (PLANES + 2) : 8;
+  static constexpr int PLANES = ZT + 2 * HALO;
+  static constexpr int A_SLOTS = 8;
   static constexpr int W_SLOTS = (32768 / W_UNIT_BYTES) < 2 ? 2 : ((32768 / W_UNIT_BYTES) > 8 ? 8 : (32768 / W_UNIT_BYTES));
   static constexpr int TMEM_COLS = (ZT * N_TILE <= 32) ? 32 : (ZT * N_TILE <= 64) ? 64 : (ZT * N_TILE <= 128) ? 128
                                    : (ZT * N_TILE <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int RED_BYTES = 4 * N_TILE * 2 * 4;      // epilogue statistics exchange between the 4 warps
+  static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + RED_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(ZT * N_TILE <= 512, "accumulators exceed TMEM");
   static_assert(A_SLOTS >= PLANES, "ring must hold one input-channel block");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -56,27 +68,67 @@ struct ConvTc {
 
 struct ConvTcArgs {
   const __nv_bfloat16* w;  // packed [n_tile][cin_block][tap][KCH][N_TILE][8]
-  __nv_bfloat16* out;      // raw conv output, C8-planar, cout channels
+  __nv_bfloat16* out;      // bf16 C8-planar output (raw conv output / transposed-conv result), `cout` channels
+  float* out_partial;      // split-K only: fp32 partial tiles [ks][n][cout/8][voxels][8]
+  float* stats;            // fused IN statistics [n*cout/8 + chunk][tiles per sample][16] (conv, ksplit == 1) or nullptr
+  const float* bias;       // transposed conv: bias[cout]
   int nb0, nb1;            // input-channel blocks taken from tensor map 0 / 1
   int chunks0, chunks1;    // C/8 of source 0 / 1 (stride of the batch index in the folded 4th tensor-map dim)
-  int cout;
-  int D, H, W;
-  int tiles_x, tiles_y, tiles_z, n_tiles;
+  int cout;                // channels of the output tensor (padded)
+  int D, H, W;             // INPUT spatial size (the transposed conv writes a 2D x 2H x 2W volume)
+  int tiles_x, tiles_y, tiles_z, n_tiles, ksplit, batch;
+  long long* dbg;          // optional per-CTA clock64 timeline (8 slots per CTA)
 };
 
-template <int CB_CH, int N_TILE, int ZT>
+// butterfly transpose-reduce: every lane enters with 32 values, lane l leaves with the warp-wide sum of value l
+__device__ __forceinline__ float warp_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float keep = up ? v[16 + i] : v[i], send = up ? v[i] : v[16 + i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float keep = up ? v[8 + i] : v[i], send = up ? v[i] : v[8 + i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float keep = up ? v[4 + i] : v[i], send = up ? v[i] : v[4 + i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float keep = up ? v[2 + i] : v[i], send = up ? v[i] : v[2 + i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+template <int CB_CH, int N_TILE, int ZT, int MODE>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, ConvTcArgs a) {
-  using Cfg = ConvTc<CB_CH, N_TILE, ZT>;
+  using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
   const uint32_t w_smem = a_smem + Cfg::A_SLOTS * Cfg::PLANE_BYTES;
-  const uint32_t bars = w_smem + Cfg::W_SLOTS * Cfg::W_UNIT_BYTES;
+  const uint32_t red_smem = w_smem + Cfg::W_SLOTS * Cfg::W_UNIT_BYTES;
+  const uint32_t bars = red_smem + Cfg::RED_BYTES;
   const uint32_t a_full = bars, a_empty = bars + 8 * Cfg::A_SLOTS;
   const uint32_t w_full = bars + 16 * Cfg::A_SLOTS, w_empty = w_full + 8 * Cfg::W_SLOTS;
   const uint32_t acc_full = w_empty + 8 * Cfg::W_SLOTS;
   const uint32_t tmem_slot = acc_full + 8;
+  float* red = reinterpret_cast<float*>(smem_raw + (red_smem - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -86,11 +138,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   const int tiy = t % a.tiles_y; t /= a.tiles_y;
   const int tiz = t % a.tiles_z; t /= a.tiles_z;
   const int ntile = t % a.n_tiles; t /= a.n_tiles;
+  const int ks = t % a.ksplit; t /= a.ksplit;
   const int n = t;
   const int x0 = tix * CONV_TX, y0 = tiy * CONV_TY, z0 = tiz * ZT;
   const int ncb = a.nb0 + a.nb1;
+  const int cb_lo = (int)((long long)ks * ncb / a.ksplit), cb_hi = (int)((long long)(ks + 1) * ncb / a.ksplit);
 
   if (threadIdx.x == 0) {
+    if (a.dbg) a.dbg[blockIdx.x * 8 + 0] = clock64();
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
     mbar_init(acc_full, 1);
@@ -111,26 +166,28 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // =============================== halo-plane producer (TMA) ===============================
+    // =============================== input-plane producer (TMA) ===============================
     if (elect_one_sync()) {
-      for (int cb = 0; cb < ncb; ++cb) {
+      for (int cb = cb_lo; cb < cb_hi; ++cb) {
         const bool second = cb >= a.nb0;
         const CUtensorMap* tm = second ? &tmap1 : &tmap0;
         const int c3 = second ? n * a.chunks1 + (cb - a.nb0) * Cfg::KCH : n * a.chunks0 + cb * Cfg::KCH;
         for (int p = 0; p < Cfg::PLANES; ++p) {
-          const int u = cb * Cfg::PLANES + p;
+          const int u = (cb - cb_lo) * Cfg::PLANES + p;
           const int slot = u % Cfg::A_SLOTS, it = u / Cfg::A_SLOTS;
           if (it > 0) mbar_wait(a_empty + 8 * slot, (it - 1) & 1);
           mbar_arrive_expect_tx(a_full + 8 * slot, Cfg::PLANE_BYTES);
-          tma_load_4d(a_smem + slot * Cfg::PLANE_BYTES, tm, a_full + 8 * slot, (x0 - 1) * 8, y0 - 1, z0 + p - 1, c3);
+          tma_load_4d(a_smem + slot * Cfg::PLANE_BYTES, tm, a_full + 8 * slot, (x0 - Cfg::HALO) * 8, y0 - Cfg::HALO,
+                      z0 + p - Cfg::HALO, c3);
         }
       }
     }
   } else if (warp == 1) {
     // =============================== weight-tile producer (bulk copy) ===============================
     if (elect_one_sync()) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + (size_t)ntile * ncb * 27 * Cfg::W_UNIT_BYTES;
-      const int nw = ncb * 27;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) +
+                            ((size_t)ntile * ncb + cb_lo) * Cfg::TAPS * Cfg::W_UNIT_BYTES;
+      const int nw = (cb_hi - cb_lo) * Cfg::TAPS;
       for (int w = 0; w < nw; ++w) {
         const int slot = w % Cfg::W_SLOTS, it = w / Cfg::W_SLOTS;
         if (it > 0) mbar_wait(w_empty + 8 * slot, (it - 1) & 1);
@@ -143,76 +200,135 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
     // =============================== MMA issuer (one thread) ===============================
     if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE);
-      for (int cb = 0; cb < ncb; ++cb) {
+      for (int cb = cb_lo; cb < cb_hi; ++cb) {
+        const int ubase = (cb - cb_lo) * Cfg::PLANES;
         int waited = 0;
-        for (int tz = 0; tz < 3; ++tz) {
-          for (int tyx = 0; tyx < 9; ++tyx) {
-            const int w = cb * 27 + tz * 9 + tyx;
+#pragma unroll 1
+        for (int tz = 0; tz < Cfg::TZ; ++tz) {
+#pragma unroll 1
+          for (int tyx = 0; tyx < Cfg::TYX; ++tyx) {
+            const int w = (cb - cb_lo) * Cfg::TAPS + tz * Cfg::TYX + tyx;
             const int ws = w % Cfg::W_SLOTS;
             mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
             tc_fence_after();
-            const uint32_t tap_off = ((tyx / 3) * CONV_HX + (tyx % 3)) * 16;
+            const uint32_t tap_off = ((tyx / 3) * Cfg::HX + (tyx % 3)) * 16;
             const uint32_t wb = w_smem + ws * Cfg::W_UNIT_BYTES;
 #pragma unroll
             for (int s = 0; s < ZT; ++s) {
               const int p = s + tz;
               while (waited <= p) {
-                const int u = cb * Cfg::PLANES + waited;
+                const int u = ubase + waited;
                 mbar_wait(a_full + 8 * (u % Cfg::A_SLOTS), (u / Cfg::A_SLOTS) & 1);
                 tc_fence_after();
                 ++waited;
               }
-              const int u = cb * Cfg::PLANES + p;
+              const int u = ubase + p;
               const uint32_t ab = a_smem + (u % Cfg::A_SLOTS) * Cfg::PLANE_BYTES + tap_off;
 #pragma unroll
               for (int k = 0; k < CB_CH / 16; ++k) {
                 const uint64_t ad = make_smem_desc(ab + k * 2 * Cfg::A_LBO, Cfg::A_LBO, Cfg::A_SBO);
                 const uint64_t bd = make_smem_desc(wb + k * 2 * Cfg::B_LBO, Cfg::B_LBO, Cfg::B_SBO);
-                umma_bf16(tmem_base + s * N_TILE, ad, bd, idesc, (cb | tz | tyx | k) != 0 ? 1u : 0u);
+                umma_bf16(tmem_base + s * N_TILE, ad, bd, idesc, ((cb - cb_lo) | tz | tyx | k) != 0 ? 1u : 0u);
               }
             }
             umma_commit(w_empty + 8 * ws);  // weight slot free once these MMAs retire
+            if (a.dbg && w == 0) a.dbg[blockIdx.x * 8 + 1] = clock64();
           }
           // planes whose last reader was this tz phase go back to the producer
-          if (tz < 2) {
-            umma_commit(a_empty + 8 * ((cb * Cfg::PLANES + tz) % Cfg::A_SLOTS));
+          if (tz < Cfg::TZ - 1) {
+            umma_commit(a_empty + 8 * ((ubase + tz) % Cfg::A_SLOTS));
           } else {
-            for (int p = 2; p < Cfg::PLANES; ++p) umma_commit(a_empty + 8 * ((cb * Cfg::PLANES + p) % Cfg::A_SLOTS));
+            for (int p = tz; p < Cfg::PLANES; ++p) umma_commit(a_empty + 8 * ((ubase + p) % Cfg::A_SLOTS));
           }
         }
       }
       umma_commit(acc_full);
+      if (a.dbg) a.dbg[blockIdx.x * 8 + 2] = clock64();
     }
   } else {
-    // =============================== epilogue: TMEM -> bf16 -> HBM ===============================
+    // =============================== epilogue: TMEM -> registers -> HBM ===============================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (a.dbg && warp == 3 && lane == 0) a.dbg[blockIdx.x * 8 + 3] = clock64();
     const int r = q * 32 + lane;  // GEMM row = voxel (y = r / 8, x = r % 8)
     const int x = x0 + (r & 7), y = y0 + (r >> 3);
     const bool xy_ok = x < a.W && y < a.H;
     const int out_chunks = a.cout / 8;
-    const long long plane_vox = (long long)a.D * a.H * a.W;
+    const long long in_vox = (long long)a.D * a.H * a.W;
+    const bool do_stats = (MODE == MODE_CONV3) && a.stats != nullptr;
 #pragma unroll 1
-    for (int s = 0; s < ZT; ++s) {
-      const int z = z0 + s;
-      const bool ok = xy_ok && z < a.D;
-      const long long vofs = ((long long)z * a.H + y) * a.W + x;
+    for (int j = 0; j < N_TILE / 16; ++j) {
+      float st[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) st[i] = 0.f;
+      const int gcol = ntile * N_TILE + j * 16;
 #pragma unroll 1
-      for (int j = 0; j < N_TILE / 16; ++j) {
+      for (int s = 0; s < ZT; ++s) {
+        const int z = z0 + s;
+        const bool ok = xy_ok && z < a.D;
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + s * N_TILE + j * 16, v);
-        if (ok) {
-          const int c8 = (ntile * N_TILE + j * 16) / 8;
-          BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + c8) * plane_vox + vofs;
-          float lo[8], hi[8];
+        if constexpr (MODE == MODE_CONV3) {
+          const long long vofs = ((long long)z * a.H + y) * a.W + x;
+          if (a.out_partial) {
+            if (ok) {
+              float4* dst = reinterpret_cast<float4*>(a.out_partial) +
+                            ((((long long)ks * a.batch + n) * out_chunks + gcol / 8) * in_vox + vofs) * 2;
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+              dst[in_vox * 2] = make_float4(v[8], v[9], v[10], v[11]);
+              dst[in_vox * 2 + 1] = make_float4(v[12], v[13], v[14], v[15]);
+            }
+          } else {
+            if (ok) {
+              BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + gcol / 8) * in_vox + vofs;
+              float lo[8], hi[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
-          dst[0] = float_to_bf8(lo);
-          dst[plane_vox] = float_to_bf8(hi);
+              for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+              dst[0] = float_to_bf8(lo);
+              dst[in_vox] = float_to_bf8(hi);
+            }
+            if (do_stats) {
+              const float m = ok ? 1.f : 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float xv = v[i] * m;
+                st[i] += xv;
+                st[16 + i] = fmaf(xv, xv, st[16 + i]);
+              }
+            }
+          }
+        } else {
+          if (ok) {
+            const int tap = gcol / a.cout, co = gcol % a.cout;
+            const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
+            const long long ovox = in_vox * 8;
+            BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + co / 8) * ovox +
+                       ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;
+            float lo[8], hi[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { lo[i] = v[i] + a.bias[co + i]; hi[i] = v[8 + i] + a.bias[co + 8 + i]; }
+            dst[0] = float_to_bf8(lo);
+            dst[ovox] = float_to_bf8(hi);
+          }
         }
       }
+      if (do_stats) red[q * (N_TILE * 2) + j * 32 + lane] = warp_reduce32(st, lane);
     }
+    if (do_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      const int i = q * 32 + lane;                     // 0..127
+      const int nseg = a.tiles_x * a.tiles_y * a.tiles_z;
+      const int tile_lin = (tiz * a.tiles_y + tiy) * a.tiles_x + tix;
+      for (int e = i; e < N_TILE * 2; e += 128) {
+        const float tot = (red[e] + red[N_TILE * 2 + e]) + (red[2 * N_TILE * 2 + e] + red[3 * N_TILE * 2 + e]);
+        const int l = e & 31, col = (e >> 5) * 16 + (l & 15), stat = l >> 4;
+        const int chunk = (ntile * N_TILE + col) >> 3;
+        a.stats[(((long long)n * out_chunks + chunk) * nseg + tile_lin) * 16 + stat * 8 + (col & 7)] = tot;
+      }
+    }
+    if (a.dbg && warp == 3 && lane == 0) a.dbg[blockIdx.x * 8 + 4] = clock64();
     tc_fence_before();
   }
   __syncthreads();

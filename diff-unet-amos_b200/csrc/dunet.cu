@@ -86,11 +86,11 @@ static int load_driver_entry() {
 }
 
 // Tensor map over a C8-planar activation: dims (x*8+c8 : W*8, y : H, z : D, plane : batch*chunks), box = one halo plane.
-static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, int H, int W, int kch) {
+static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, int H, int W, int kch, int halo) {
   TRY(load_driver_entry());
   cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-  cuuint32_t box[4] = {CONV_HX * 8, CONV_HY, 1, (cuuint32_t)kch};
+  cuuint32_t box[4] = {(cuuint32_t)(CONV_TX + 2 * halo) * 8, (cuuint32_t)(CONV_TY + 2 * halo), 1, (cuuint32_t)kch};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -139,6 +139,27 @@ __global__ void pack_deconv_w_kernel(const float* __restrict__ w, bf16* __restri
     out[i] = __float2bfloat16_rn(v);
   }
 }
+// transposed-conv weights fp32 [cinr][coutr][8] -> tensor-core B operand bf16 [n_tile][cin block][k chunk][128][8] where
+// GEMM column = tap * coutp + cout  (tap = dz*4 + dy*2 + dx)
+__global__ void pack_deconv_tc_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cinr, int coutr, int cinp,
+                                        int coutp) {
+  const int n_tile = 128, kch = 8, ncb = cinp / 64, n_tiles = 8 * coutp / n_tile;
+  const long long total = (long long)n_tiles * ncb * kch * n_tile * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int j = (int)(t % 8); t /= 8;
+    const int col = (int)(t % n_tile); t /= n_tile;
+    const int k = (int)(t % kch); t /= kch;
+    const int cb = (int)(t % ncb); t /= ncb;
+    const int nt = (int)t;
+    const int gcol = nt * n_tile + col, tap = gcol / coutp, co = gcol % coutp;
+    const int ci = cb * 64 + k * 8 + j;
+    float v = 0.f;
+    if (ci < cinr && co < coutr) v = w[((long long)ci * coutr + co) * 8 + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
 // copy `n` floats into a zero-padded buffer of n_pad floats, optionally strided rows: dst[r][0..cols_pad) <- src[r][0..cols)
 __global__ void copy_pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
                                      int rows_pad, int cols_pad) {
@@ -175,7 +196,8 @@ struct TwoConvW {
 };
 struct DeconvW {
   int cinr = 0, cinp = 0, coutr = 0, coutp = 0;
-  bf16* packed = nullptr;
+  bf16* packed = nullptr;     // CUDA-core debug kernel layout [tap][cinp][coutp]
+  bf16* packed_tc = nullptr;  // tensor-core layout, see pack_deconv_tc_w_kernel
   float* bias = nullptr;
   bool have_w = false, have_b = false;
 };
@@ -190,7 +212,7 @@ struct Slot {
 };
 
 struct WsLayout {
-  size_t in_pack, raw, mid, partial, x_t, total;
+  size_t in_pack, raw, mid, partial, ss, splitk, x_t, total;
   size_t emb[5], epool[5], x[5], dpool[5], up[5], u[5];
 };
 
@@ -244,22 +266,52 @@ static void add_twoconv_slots(dunet_plan* p, const std::string& pre, TwoConvW* t
   add_convblock_slots(p, pre + ".conv_1", &t->b);
 }
 
+constexpr int CONV_ZT = 4;
+
+struct ConvGeom { int tiles_x, tiles_y, tiles_z, tiles, ksplit; };
+
+// tiling + split-K decision for one conv layer at U-Net level `lvl` with batch B (deterministic: depends on shapes only)
+static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
+  ConvGeom g;
+  g.tiles_x = (p->W[lvl] + CONV_TX - 1) / CONV_TX;
+  g.tiles_y = (p->H[lvl] + CONV_TY - 1) / CONV_TY;
+  g.tiles_z = (p->D[lvl] + CONV_ZT - 1) / CONV_ZT;
+  g.tiles = g.tiles_x * g.tiles_y * g.tiles_z;
+  // the split factor must not depend on the batch: a window's result is bit-identical whatever it is batched with
+  (void)B;
+  const int ctas = g.tiles * c.n_tiles, ncb = c.nb0 + c.nb1;
+  g.ksplit = 1;
+  if (ncb >= 2 && ctas < 96) g.ksplit = std::max(1, std::min(ncb, 148 / ctas));
+  return g;
+}
+
+static int stats_nseg(long long vox) {
+  long long n = (vox + 8191) / 8192;
+  return (int)std::min<long long>(std::max<long long>(n, 1), 128);
+}
+
 static WsLayout ws_layout(const dunet_plan* p, int B) {
   WsLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   auto act = [&](int ch, int lvl) -> size_t { return (size_t)((size_t)B * ch * (size_t)p->V[lvl] * sizeof(bf16)); };
   L.in_pack = take(act(p->in_pad, 0));
-  size_t raw_max = 0, part_max = 0;
-  auto upd = [&](int ch, int lvl) {
-    raw_max = std::max(raw_max, act(ch, lvl));
-    part_max = std::max(part_max, (size_t)B * (ch / 8) * 128 * 16 * sizeof(float));
+  size_t raw_max = 0, part_max = 0, ss_max = 0, split_max = 0;
+  auto upd = [&](const ConvW& c, int lvl) {
+    raw_max = std::max(raw_max, act(c.coutp, lvl));
+    const ConvGeom g = conv_geom(p, c, lvl, B);
+    const size_t planes = (size_t)B * (c.coutp / 8);
+    part_max = std::max(part_max, planes * std::max(g.tiles, 128) * 16 * sizeof(float));
+    ss_max = std::max(ss_max, planes * 16 * sizeof(float));
+    if (g.ksplit > 1) split_max = std::max(split_max, (size_t)g.ksplit * B * c.coutp * (size_t)p->V[lvl] * sizeof(float));
   };
-  for (int l = 0; l < 5; ++l) upd(p->fp[l], l);
-  for (int l = 4; l >= 1; --l) upd(p->uoutp[l], l - 1);
+  for (int l = 0; l < 5; ++l) { upd(p->enc[l].a, l); upd(p->enc[l].b, l); upd(p->den[l].a, l); upd(p->den[l].b, l); }
+  for (int l = 4; l >= 1; --l) { upd(p->upc[l].a, l - 1); upd(p->upc[l].b, l - 1); }
   L.raw = take(raw_max);
   L.mid = take(raw_max);
   L.partial = take(part_max);
+  L.ss = take(ss_max);
+  L.splitk = take(split_max);
   L.x_t = take((size_t)B * p->C * p->V[0] * sizeof(float));
   for (int l = 0; l < 5; ++l) {
     L.emb[l] = take(act(p->fp[l], l));
@@ -274,16 +326,18 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
 }
 
 // ------------------------------------------------------------------------------------------------ layer launchers
-template <int CB_CH, int N_TILE, int ZT>
-static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTcArgs& a, int batch, cudaStream_t st) {
-  using Cfg = ConvTc<CB_CH, N_TILE, ZT>;
+static long long* g_conv_dbg = nullptr;  // optional per-CTA timeline buffer (tools only)
+
+template <int CB_CH, int N_TILE, int ZT, int MODE>
+static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTcArgs& a, cudaStream_t st) {
+  using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
   static bool attr_set = false;
-  auto kern = conv3d_tc_kernel<CB_CH, N_TILE, ZT>;
+  auto kern = conv3d_tc_kernel<CB_CH, N_TILE, ZT, MODE>;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const long long grid = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * batch;
+  const long long grid = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
   if (g_prof_on) {
     if (g_prof_used == g_prof.size()) {
       ProfRec rec;
@@ -302,11 +356,11 @@ static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const Co
   return 0;
 }
 
-constexpr int CONV_ZT = 4;
-
-static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const bf16* src1, bf16* out, int lvl, int B,
-                    cudaStream_t st) {
+// 3x3x3 conv -> raw bf16 output + InstanceNorm partial statistics [plane][*nseg_out][16] in `partial`
+static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const bf16* src1, bf16* out, float* partial,
+                    float* splitk, int* nseg_out, int lvl, int B, cudaStream_t st) {
   const int D = p->D[lvl], H = p->H[lvl], W = p->W[lvl];
+  const int planes = B * (c.coutp / 8);
   if (p->cfg.flags & DUNET_FLAG_REF_CONV) {
     if (!c.w32) return fail(DUNET_E_STATE, "DUNET_FLAG_REF_CONV needs DUNET_FLAG_KEEP_FP32_WEIGHTS");
     // the debug kernel writes only the chunks holding real output channels; padded chunks must still be zero
@@ -314,41 +368,58 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
     conv3d_ref_kernel<<<grid_for((long long)B * ((c.coutr + 7) / 8) * p->V[lvl], 128, 148 * 64), 128, 0, st>>>(
         src0, c.c0r, c.c0p / 8, src1, c.c1r, c.c1p / 8, c.w32, out, c.coutr, c.coutp / 8, D, H, W, B);
     LAUNCH_CHECK();
+    if (partial) {
+      const int nseg = stats_nseg(p->V[lvl]);
+      in_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(out, partial, p->V[lvl], nseg);
+      LAUNCH_CHECK();
+      *nseg_out = nseg;
+    }
     return 0;
   }
   if (g_prof_on) g_prof_flops += 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
   CUtensorMap t0, t1;
-  TRY(make_act_tmap(&t0, src0, B * (c.c0p / 8), D, H, W, c.cb_ch / 8));
-  if (c.nb1 > 0) TRY(make_act_tmap(&t1, src1, B * (c.c1p / 8), D, H, W, c.cb_ch / 8));
+  TRY(make_act_tmap(&t0, src0, B * (c.c0p / 8), D, H, W, c.cb_ch / 8, 1));
+  if (c.nb1 > 0) TRY(make_act_tmap(&t1, src1, B * (c.c1p / 8), D, H, W, c.cb_ch / 8, 1));
   else t1 = t0;
+  const ConvGeom g = conv_geom(p, c, lvl, B);
   ConvTcArgs a;
+  memset(&a, 0, sizeof a);
   a.w = c.packed; a.out = out; a.nb0 = c.nb0; a.nb1 = c.nb1; a.chunks0 = c.c0p / 8; a.chunks1 = c.c1p / 8;
   a.cout = c.coutp; a.D = D; a.H = H; a.W = W;
-  a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + CONV_ZT - 1) / CONV_ZT;
-  a.n_tiles = c.n_tiles;
-  if (c.cb_ch == 32 && c.n_tile == 64) return launch_conv_tc<32, 64, CONV_ZT>(t0, t1, a, B, st);
-  if (c.cb_ch == 32 && c.n_tile == 128) return launch_conv_tc<32, 128, CONV_ZT>(t0, t1, a, B, st);
-  if (c.cb_ch == 64 && c.n_tile == 64) return launch_conv_tc<64, 64, CONV_ZT>(t0, t1, a, B, st);
-  if (c.cb_ch == 64 && c.n_tile == 128) return launch_conv_tc<64, 128, CONV_ZT>(t0, t1, a, B, st);
-  return fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
+  a.tiles_x = g.tiles_x; a.tiles_y = g.tiles_y; a.tiles_z = g.tiles_z; a.n_tiles = c.n_tiles; a.batch = B;
+  a.ksplit = (splitk && partial) ? g.ksplit : 1;
+  a.dbg = g_conv_dbg;
+  if (a.ksplit > 1) a.out_partial = splitk;
+  else a.stats = partial;
+  int rc;
+  if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
+  else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
+  else return fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
+  TRY(rc);
+  if (a.ksplit > 1) {
+    const int nseg = stats_nseg(p->V[lvl]);
+    splitk_reduce_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(
+        splitk, a.ksplit, (long long)B * c.coutp * p->V[lvl], out, partial, p->V[lvl], nseg);
+    LAUNCH_CHECK();
+    *nseg_out = nseg;
+  } else if (partial) {
+    *nseg_out = g.tiles;
+  }
+  return 0;
 }
 
-static int stats_nseg(long long vox) {
-  long long n = (vox + 8191) / 8192;
-  return (int)std::min<long long>(std::max<long long>(n, 1), 128);
-}
-
-// raw conv output -> IN statistics -> fused normalise/activation(/bias/add/pool)
-static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, float* partial, const float* bias,
-                    const bf16* add, bf16* out, bf16* pooled, int lvl, int B, cudaStream_t st) {
+// statistics -> affine map -> fused normalise/activation(/bias/add/pool)
+static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, const float* partial, int nseg, float* ss,
+                    const float* bias, const bf16* add, bf16* out, bf16* pooled, int lvl, int B, cudaStream_t st) {
   const int planes = B * (c.coutp / 8);
-  const int nseg = stats_nseg(p->V[lvl]);
-  in_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(raw, partial, p->V[lvl], nseg);
+  stats_finalize_kernel<<<planes, 256, 0, st>>>(partial, nseg, c.gamma, c.beta, c.coutp / 8, (double)p->V[lvl], 1e-5f, ss);
   LAUNCH_CHECK();
   NormActArgs a;
-  a.raw = raw; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias; a.add = add;
+  a.raw = raw; a.ss = ss; a.bias = bias; a.add = add;
   a.out = out; a.pooled = pooled; a.chunks = c.coutp / 8; a.D = p->D[lvl]; a.H = p->H[lvl]; a.W = p->W[lvl];
-  a.eps = 1e-5f; a.slope = 0.1f;
+  a.slope = 0.1f;
   if (pooled) {
     const long long work = p->V[lvl] / 8;
     norm_act_kernel<true><<<dim3(grid_for(work, NORM_THREADS, 512), planes), NORM_THREADS, 0, st>>>(a);
@@ -365,19 +436,34 @@ static int run_twoconv(const dunet_plan* p, const TwoConvW& t, const bf16* src0,
   bf16* raw = reinterpret_cast<bf16*>(ws + L.raw);
   bf16* mid = reinterpret_cast<bf16*>(ws + L.mid);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
-  TRY(run_conv(p, t.a, src0, src1, raw, lvl, B, st));
-  TRY(run_norm(p, t.a, raw, partial, temb_bias, nullptr, mid, nullptr, lvl, B, st));
-  TRY(run_conv(p, t.b, mid, nullptr, raw, lvl, B, st));
-  TRY(run_norm(p, t.b, raw, partial, nullptr, add, out, pooled, lvl, B, st));
+  float* ss = reinterpret_cast<float*>(ws + L.ss);
+  float* splitk = reinterpret_cast<float*>(ws + L.splitk);
+  int nseg = 0;
+  TRY(run_conv(p, t.a, src0, src1, raw, partial, splitk, &nseg, lvl, B, st));
+  TRY(run_norm(p, t.a, raw, partial, nseg, ss, temb_bias, nullptr, mid, nullptr, lvl, B, st));
+  TRY(run_conv(p, t.b, mid, nullptr, raw, partial, splitk, &nseg, lvl, B, st));
+  TRY(run_norm(p, t.b, raw, partial, nseg, ss, nullptr, add, out, pooled, lvl, B, st));
   return 0;
 }
 
 static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf16* out, int lvl_in, int B, cudaStream_t st) {
-  const long long total = (long long)B * (d.coutp / 8) * 8 * p->V[lvl_in];
-  deconv2_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in, d.cinp, d.packed, d.bias, out, d.coutp, p->D[lvl_in],
-                                                                  p->H[lvl_in], p->W[lvl_in], B);
-  LAUNCH_CHECK();
-  return 0;
+  if (p->cfg.flags & DUNET_FLAG_REF_CONV) {  // CUDA-core debug kernel
+    const long long total = (long long)B * (d.coutp / 8) * 8 * p->V[lvl_in];
+    deconv2_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in, d.cinp, d.packed, d.bias, out, d.coutp, p->D[lvl_in],
+                                                                    p->H[lvl_in], p->W[lvl_in], B);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  const int D = p->D[lvl_in], H = p->H[lvl_in], W = p->W[lvl_in];
+  CUtensorMap t0;
+  TRY(make_act_tmap(&t0, in, B * (d.cinp / 8), D, H, W, 8, 0));
+  ConvTcArgs a;
+  memset(&a, 0, sizeof a);
+  a.w = d.packed_tc; a.out = out; a.bias = d.bias; a.nb0 = d.cinp / 64; a.nb1 = 0; a.chunks0 = d.cinp / 8; a.chunks1 = 0;
+  a.cout = d.coutp; a.D = D; a.H = H; a.W = W;
+  a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + CONV_ZT - 1) / CONV_ZT;
+  a.n_tiles = 8 * d.coutp / 128; a.ksplit = 1; a.batch = B; a.dbg = nullptr;
+  return launch_conv_tc<64, 128, CONV_ZT, MODE_DECONV2>(t0, t0, a, st);
 }
 
 static int check_call(const dunet_plan* p, int B, const void* ws) {
@@ -437,7 +523,11 @@ static int launch_temb(dunet_plan* p, const int* d_t, int rows, float* table, cu
 }
 
 static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) {
-  final_ddim_kernel<<<grid_for((long long)a.batch * a.vox, 128, 148 * 32), 128, 0, st>>>(a);
+  const int grid = grid_for((long long)a.batch * a.vox, 256, 148 * 8);
+  if (a.C <= 4) final_ddim_kernel<4><<<grid, 256, 0, st>>>(a);
+  else if (a.C <= 8) final_ddim_kernel<8><<<grid, 256, 0, st>>>(a);
+  else if (a.C <= 16) final_ddim_kernel<16><<<grid, 256, 0, st>>>(a);
+  else final_ddim_kernel<32><<<grid, 256, 0, st>>>(a);
   LAUNCH_CHECK();
   return 0;
 }
@@ -628,6 +718,9 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       const size_t n = 8ull * d->cinp * d->coutp;
       if (!d->packed) TRY(dev_alloc(p, (void**)&d->packed, n * sizeof(bf16)));
       pack_deconv_w_kernel<<<grid_for((long long)n, 256), 256, 0, st>>>(src, d->packed, d->cinr, d->coutr, d->cinp, d->coutp);
+      LAUNCH_CHECK();
+      if (!d->packed_tc) TRY(dev_alloc(p, (void**)&d->packed_tc, n * sizeof(bf16)));
+      pack_deconv_tc_w_kernel<<<grid_for((long long)n, 256), 256, 0, st>>>(src, d->packed_tc, d->cinr, d->coutr, d->cinp, d->coutp);
       LAUNCH_CHECK();
       d->have_w = true;
       break;
@@ -846,7 +939,8 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
         weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.nb0 + c.nb1, c.n_tiles);
     LAUNCH_CHECK();
   }
-  rc = run_conv(&tmp, c, a0, a1, raw, 0, B, st);
+  int nseg_unused = 0;
+  rc = run_conv(&tmp, c, a0, a1, raw, nullptr, nullptr, &nseg_unused, 0, B, st);
   if (rc == 0) {
     unpack_c8_kernel<<<grid_for((long long)B * (c.coutp / 8) * vox, 256), 256, 0, st>>>(raw, c.coutp, out, cout, vox, B);
     g_launches.fetch_add(1);
@@ -857,6 +951,48 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   if (a1) cudaFreeAsync(a1, st);
   if (c.packed) cudaFreeAsync(c.packed, st);
   return rc;
+}
+
+int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, const float* bias, int32_t cout, float* out,
+                         int32_t B, const int32_t dims[3], int32_t use_ref, void* stream) {
+  if (!src || !weight || !bias || !out || !dims || cin < 1 || cout < 1 || B < 1) return fail(DUNET_E_INVALID, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dunet_plan tmp;
+  memset(&tmp.cfg, 0, sizeof tmp.cfg);
+  tmp.cfg.flags = use_ref ? DUNET_FLAG_REF_CONV : 0;
+  tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
+  tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
+  DeconvW d;
+  d.cinr = cin; d.cinp = pad_to(cin, 64); d.coutr = cout; d.coutp = pad_to(cout, 64);
+  const long long vox = tmp.V[0];
+  const size_t nw = 8ull * d.cinp * d.coutp;
+  bf16 *a0 = nullptr, *o = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&a0, (size_t)B * d.cinp * vox * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&o, (size_t)B * d.coutp * vox * 8 * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&d.packed, nw * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&d.packed_tc, nw * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&d.bias, d.coutp * sizeof(float), st));
+  pack_c8_kernel<<<grid_for((long long)B * (d.cinp / 8) * vox, 256), 256, 0, st>>>(src, cin, nullptr, 0, a0, d.cinp, vox, B);
+  LAUNCH_CHECK();
+  pack_deconv_w_kernel<<<grid_for((long long)nw, 256), 256, 0, st>>>(weight, d.packed, cin, cout, d.cinp, d.coutp);
+  LAUNCH_CHECK();
+  pack_deconv_tc_w_kernel<<<grid_for((long long)nw, 256), 256, 0, st>>>(weight, d.packed_tc, cin, cout, d.cinp, d.coutp);
+  LAUNCH_CHECK();
+  copy_pad_rows_kernel<<<1, 256, 0, st>>>(bias, d.bias, 1, cout, 1, d.coutp);
+  LAUNCH_CHECK();
+  int rc = run_deconv(&tmp, d, a0, o, 0, B, st);
+  if (rc == 0) {
+    unpack_c8_kernel<<<grid_for((long long)B * (d.coutp / 8) * vox * 8, 256), 256, 0, st>>>(o, d.coutp, out, cout, vox * 8, B);
+    g_launches.fetch_add(1);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(DUNET_E_CUDA, "unpack launch failed");
+  }
+  cudaFreeAsync(a0, st); cudaFreeAsync(o, st); cudaFreeAsync(d.packed, st); cudaFreeAsync(d.packed_tc, st); cudaFreeAsync(d.bias, st);
+  return rc;
+}
+
+int dunet_debug_set_conv_timeline(int64_t* dev_buffer) {
+  g_conv_dbg = reinterpret_cast<long long*>(dev_buffer);
+  return 0;
 }
 
 }  // extern "C"

@@ -124,6 +124,62 @@ __global__ void __launch_bounds__(STATS_THREADS) in_stats_kernel(const __nv_bflo
   }
 }
 
+// Split-K epilogue: sum the fp32 partial tiles of the ksplit CTAs in a fixed order, write the bf16 raw conv output and
+// the InstanceNorm partial statistics of the (un-rounded) sums.  partial: [ks][plane][vox][8] fp32.
+__global__ void __launch_bounds__(STATS_THREADS) splitk_reduce_stats_kernel(const float* __restrict__ part, int ksplit,
+                                                                            long long split_stride /*floats*/,
+                                                                            __nv_bfloat16* __restrict__ raw,
+                                                                            float* __restrict__ partial, long long vox,
+                                                                            int nseg) {
+  const int plane = blockIdx.y, seg = blockIdx.x;
+  const float4* p = reinterpret_cast<const float4*>(part) + (long long)plane * vox * 2;
+  BF8* o = reinterpret_cast<BF8*>(raw) + (long long)plane * vox;
+  long long per = (vox + nseg - 1) / nseg;
+  long long lo = seg * per, hi = min(vox, lo + per);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (long long v = lo + threadIdx.x; v < hi; v += STATS_THREADS) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    for (int k = 0; k < ksplit; ++k) {
+      const float4 a0 = p[(long long)k * (split_stride / 4) + v * 2], a1 = p[(long long)k * (split_stride / 4) + v * 2 + 1];
+      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+      f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+    }
+    o[v] = float_to_bf8(f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      q[j] = fmaf(f[j], f[j], q[j]);
+    }
+  }
+  __shared__ float red[STATS_THREADS / 32][16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o2);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o2);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[warp][j] = s[j];
+      red[warp][8 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int w = 0; w < STATS_THREADS / 32; ++w) t += red[w][threadIdx.x];
+    partial[((long long)plane * nseg + seg) * 16 + threadIdx.x] = t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Fused normalise pass (reference TwoConv / MONAI ADN "NDA", denoiser.py:56-67, 300-304):
 //   y = LeakyReLU_0.1( (x - mean) * rsqrt(var + 1e-5) * gamma + beta )  [+ temb bias_c]  [+ encoder feature]
@@ -132,37 +188,52 @@ __global__ void __launch_bounds__(STATS_THREADS) in_stats_kernel(const __nv_bflo
 // ---------------------------------------------------------------------------------------------------------------
 struct NormActArgs {
   const __nv_bfloat16* raw;
-  const float* partial;    // from in_stats_kernel / conv epilogue: [plane][nseg][16]
-  int nseg;
-  const float* gamma;      // [C]
-  const float* beta;       // [C]
+  const float* ss;         // from stats_finalize_kernel: [plane][16] = 8 scales (rstd*gamma), 8 shifts (beta - mean*scale)
   const float* bias;       // [C] additive after activation (temb projection) or nullptr
   const __nv_bfloat16* add;  // C8-planar tensor added after activation (encoder feature) or nullptr
   __nv_bfloat16* out;
   __nv_bfloat16* pooled;   // POOL only
   int chunks;              // C/8
   int D, H, W;
-  float eps, slope;
+  float slope;
 };
 
 constexpr int NORM_THREADS = 256;
 
+// Second stage of the InstanceNorm statistics: fixed-order fp64 reduction of the per-CTA / per-segment partial rows
+// [plane][nseg][16] into the affine map of the normalisation (biased variance, eps inside the sqrt, as F.instance_norm).
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __restrict__ partial, int nseg,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, int chunks, double count,
+                                                             float eps, float* __restrict__ ss) {
+  __shared__ double red[16][16];
+  const int plane = blockIdx.x, e = threadIdx.x & 15, g0 = threadIdx.x >> 4;
+  double acc = 0.0;
+  for (int g = g0; g < nseg; g += 16) acc += (double)partial[((long long)plane * nseg + g) * 16 + e];
+  red[g0][e] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double s = 0.0, q = 0.0;
+    for (int g = 0; g < 16; ++g) {
+      s += red[g][threadIdx.x];
+      q += red[g][8 + threadIdx.x];
+    }
+    const int c = (plane % chunks) * 8 + threadIdx.x;
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float scale = rstd * gamma[c];
+    ss[plane * 16 + threadIdx.x] = scale;
+    ss[plane * 16 + 8 + threadIdx.x] = beta[c] - (float)mean * scale;
+  }
+}
+
 __device__ __forceinline__ void norm_prologue(const NormActArgs& a, int plane, float* sc, float* sh, float* bi) {
   if (threadIdx.x < 8) {
     const int c = (plane % a.chunks) * 8 + threadIdx.x;
-    double s = 0.0, q = 0.0;
-    for (int g = 0; g < a.nseg; ++g) {
-      s += (double)a.partial[((long long)plane * a.nseg + g) * 16 + threadIdx.x];
-      q += (double)a.partial[((long long)plane * a.nseg + g) * 16 + 8 + threadIdx.x];
-    }
-    const double cnt = (double)a.D * a.H * a.W;
-    const double mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    const float scale = rstd * a.gamma[c];
-    sc[threadIdx.x] = scale;
-    sh[threadIdx.x] = a.beta[c] - (float)mean * scale;
+    sc[threadIdx.x] = a.ss[plane * 16 + threadIdx.x];
+    sh[threadIdx.x] = a.ss[plane * 16 + 8 + threadIdx.x];
     bi[threadIdx.x] = a.bias ? a.bias[c] : 0.f;
   }
   __syncthreads();
@@ -188,18 +259,34 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_act_kernel(NormActArgs a) {
   const BF8* add = a.add ? reinterpret_cast<const BF8*>(a.add) + plane * vox : nullptr;
   BF8* out = reinterpret_cast<BF8*>(a.out) + plane * vox;
   if constexpr (!POOL) {
-    for (long long v = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; v < vox;
-         v += (long long)gridDim.x * NORM_THREADS) {
-      float f[8];
-      bf8_to_float(in[v], f);
-      norm_apply(f, sc, sh, bi, a.slope);
-      if (add) {
-        float g[8];
-        bf8_to_float(add[v], g);
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    const long long stride = (long long)gridDim.x * NORM_THREADS;
+    for (long long v0 = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; v0 < vox; v0 += stride * U) {
+      BF8 xin[U], ain[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += g[j];
+      for (int u = 0; u < U; ++u) {
+        const long long v = v0 + u * stride;
+        if (v < vox) {
+          xin[u] = in[v];
+          if (add) ain[u] = add[v];
+        }
       }
-      out[v] = float_to_bf8(f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long v = v0 + u * stride;
+        if (v < vox) {
+          float f[8];
+          bf8_to_float(xin[u], f);
+          norm_apply(f, sc, sh, bi, a.slope);
+          if (add) {
+            float g[8];
+            bf8_to_float(ain[u], g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += g[j];
+          }
+          out[v] = float_to_bf8(f);
+        }
+      }
     }
   } else {
     const int D2 = a.D / 2, H2 = a.H / 2, W2 = a.W / 2;
@@ -305,11 +392,17 @@ struct FinalDdimArgs {
 constexpr int FINAL_MAX_C = 32;
 constexpr int FINAL_MAX_F = 128;
 
-__global__ void __launch_bounds__(128) final_ddim_kernel(FinalDdimArgs a) {
-  __shared__ float sw[FINAL_MAX_C * FINAL_MAX_F];
-  __shared__ float sb[FINAL_MAX_C];
-  for (int i = threadIdx.x; i < a.C * a.F; i += blockDim.x) sw[i] = a.w[i];
-  for (int i = threadIdx.x; i < a.C; i += blockDim.x) sb[i] = a.b[i];
+// CP = classes padded to a multiple of 4 (template: 4, 8, 16, 32).  Weights sit transposed in shared memory as
+// [F][CP] so one 16-byte LDS feeds 4 class accumulators.
+template <int CP>
+__global__ void __launch_bounds__(256) final_ddim_kernel(FinalDdimArgs a) {
+  __shared__ __align__(16) float sw[FINAL_MAX_F * CP];
+  __shared__ float sb[CP];
+  for (int i = threadIdx.x; i < a.F * CP; i += blockDim.x) {
+    const int c = i % CP, k = i / CP;
+    sw[i] = c < a.C ? a.w[c * a.F + k] : 0.f;
+  }
+  for (int i = threadIdx.x; i < CP; i += blockDim.x) sb[i] = i < a.C ? a.b[i] : 0.f;
   __syncthreads();
   const float s_abp = sqrtf(a.abp), s_1mabp = sqrtf(1.f - a.abp - 0.f);
   const int fch = a.F / 8;
@@ -318,26 +411,29 @@ __global__ void __launch_bounds__(128) final_ddim_kernel(FinalDdimArgs a) {
        i += (long long)gridDim.x * blockDim.x) {
     const long long v = i % a.vox;
     const int n = (int)(i / a.vox);
-    float lg[FINAL_MAX_C];
+    float lg[CP];
 #pragma unroll
-    for (int c = 0; c < FINAL_MAX_C; ++c) lg[c] = (c < a.C) ? sb[c] : 0.f;
+    for (int c = 0; c < CP; ++c) lg[c] = sb[c];
     const BF8* fp = reinterpret_cast<const BF8*>(a.feat) + (long long)n * fch * a.vox + v;
     for (int k = 0; k < fch; ++k) {
       float f[8];
       bf8_to_float(fp[(long long)k * a.vox], f);
 #pragma unroll
-      for (int c = 0; c < FINAL_MAX_C; ++c) {
-        if (c < a.C) {
-          const float* wr = sw + c * a.F + k * 8;
+      for (int j = 0; j < 8; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(sw + (k * 8 + j) * CP);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) lg[c] = fmaf(f[j], wr[j], lg[c]);
+        for (int c4 = 0; c4 < CP / 4; ++c4) {
+          const float4 w4 = wr[c4];
+          lg[c4 * 4 + 0] = fmaf(f[j], w4.x, lg[c4 * 4 + 0]);
+          lg[c4 * 4 + 1] = fmaf(f[j], w4.y, lg[c4 * 4 + 1]);
+          lg[c4 * 4 + 2] = fmaf(f[j], w4.z, lg[c4 * 4 + 2]);
+          lg[c4 * 4 + 3] = fmaf(f[j], w4.w, lg[c4 * 4 + 3]);
         }
       }
     }
-    float xn[FINAL_MAX_C];
+    // DDIM update (x_t given) or plain logits; lg[] is overwritten with x_{t-1} for the re-pack below
 #pragma unroll
-    for (int c = 0; c < FINAL_MAX_C; ++c) {
-      xn[c] = 0.f;
+    for (int c = 0; c < CP; ++c) {
       if (c < a.C) {
         const long long o = ((long long)n * a.C + c) * a.vox + v;
         if (a.logits_out) a.logits_out[o] = lg[c];
@@ -348,29 +444,28 @@ __global__ void __launch_bounds__(128) final_ddim_kernel(FinalDdimArgs a) {
           const float xp = x0 * s_abp + s_1mabp * eps;
           a.x_t[o] = xp;
           a.acc[o] += x0;
-          xn[c] = xp;
+          lg[c] = xp;
         }
+      } else {
+        lg[c] = 0.f;
       }
     }
     if (a.next_in) {
+      // channel order cat([image, x]) (denoiser.py:298): packed channel 0 = image, 1..C = x_{t-1}, rest zero
       const float img = a.image[(long long)n * a.vox + v];
       const int chunks = a.in_pad / 8;
       BF8* np = reinterpret_cast<BF8*>(a.next_in) + (long long)n * chunks * a.vox + v;
-      for (int k = 0; k < chunks; ++k) {
-        float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ch = k * 8 + j;  // channel order cat([image, x]) (denoiser.py:298)
-          float val = 0.f;
-          if (ch == 0) val = img;
-          else if (ch - 1 < a.C) {
+      for (int k = 0; k < 4; ++k) {
+        if (k < chunks) {
+          float f[8];
 #pragma unroll
-            for (int c = 0; c < FINAL_MAX_C; ++c)
-              if (c == ch - 1) val = xn[c];
+          for (int j = 0; j < 8; ++j) {
+            const int ch = k * 8 + j;
+            f[j] = ch == 0 ? img : ((ch - 1) < CP ? lg[(ch - 1) < CP ? (ch - 1) : 0] : 0.f);
           }
-          f[j] = val;
+          np[(long long)k * a.vox] = float_to_bf8(f);
         }
-        np[(long long)k * a.vox] = float_to_bf8(f);
       }
     }
   }

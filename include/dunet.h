@@ -123,6 +123,15 @@ int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channel
 int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t c1, const float* weight, int32_t cout,
                        float* out, int32_t batch, const int32_t dims[3], int32_t use_ref_kernel, void* stream);
 
+/* Stand-alone transposed convolution k=2 s=2 + bias: y = conv_transpose3d(src, weight[cin, cout, 2, 2, 2], bias).
+ * replaces: nn.ConvTranspose3d inside MONAI UpSample(mode="deconv") (denoiser.py:161-170, 181).  fp32 NCDHW in/out. */
+int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, const float* bias, int32_t cout, float* out,
+                         int32_t batch, const int32_t dims[3], int32_t use_ref_kernel, void* stream);
+
+/* tools only: when non-NULL every conv CTA writes 8 clock64 stamps to dev_buffer[cta * 8 ..] (kernel start, first MMA
+ * batch issued, last MMA committed, accumulators complete, epilogue done). */
+int dunet_debug_set_conv_timeline(int64_t* dev_buffer);
+
 /* Live kernel timing for bench.py's roofline: when enabled, every 3x3x3-conv launch is bracketed by CUDA events on the
  * launching stream.  dunet_profile_read synchronises those events and returns, since the last enable: summed conv
  * kernel time (ms), number of conv launches, and their ALGORITHMIC flops 2*B*V*Cout*27*Cin (real channels only). */
