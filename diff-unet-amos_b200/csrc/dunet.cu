@@ -16,6 +16,7 @@
 #include "../../include/dunet.h"
 #include "conv3d_ref.cuh"
 #include "conv3d_tc.cuh"
+#include "conv3d_tc64.cuh"
 #include "elementwise.cuh"
 
 using namespace dunet;
@@ -125,6 +126,31 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict
     out[i] = __float2bfloat16_rn(v);
   }
 }
+// conv weights for the Cout = 64 z-stacked kernel (conv3d_tc64.cuh): bf16 [cin block][ty*3+tx][k chunk][192][8] with
+// row = (2 - tz) * 64 + cout
+__global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
+                                     int c0p, int c1r, int cb_ch, int ncb) {
+  const int kch = cb_ch / 8;
+  const long long total = (long long)ncb * 9 * kch * 192 * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int j = (int)(t % 8); t /= 8;
+    const int row = (int)(t % 192); t /= 192;
+    const int k = (int)(t % kch); t /= kch;
+    const int tyx = (int)(t % 9); t /= 9;
+    const int cb = (int)t;
+    const int tz = 2 - row / 64, co = row % 64;
+    const int tap = tz * 9 + tyx;
+    const int lc = cb * cb_ch + k * 8 + j;
+    int ci = -1;
+    if (lc < c0p) { if (lc < c0r) ci = lc; }
+    else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
+    float v = 0.f;
+    if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
 // transposed-conv weights fp32 [cinr][coutr][8] -> bf16 [tap][cinp][coutp]
 __global__ void pack_deconv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cinr, int coutr, int cinp,
                                      int coutp) {
@@ -176,6 +202,7 @@ struct ConvW {
   int c0r = 0, c1r = 0, c0p = 0, c1p = 0, coutr = 0, coutp = 0;
   int cb_ch = 64, n_tile = 64, nb0 = 0, nb1 = 0, n_tiles = 1;
   bf16* packed = nullptr;
+  bf16* packed64 = nullptr;  // z-stacked layout for the Cout = 64 kernel (coutp == 64 only)
   float* w32 = nullptr;  // debug copy of the original fp32 weight
   float *gamma = nullptr, *beta = nullptr;
   bool have_w = false, have_cb = false, have_g = false, have_b = false;
@@ -356,6 +383,42 @@ static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const Co
   return 0;
 }
 
+static int g_num_sms = 0;
+
+template <int CB_CH>
+static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTc64Args& a, cudaStream_t st) {
+  using Cfg = ConvTc64<CB_CH, CONV_ZT>;
+  static bool attr_set = false;
+  auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT>;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  if (!g_num_sms) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.batch;
+  const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
+  if (g_prof_on) {
+    if (g_prof_used == g_prof.size()) {
+      ProfRec rec;
+      CUDA_TRY(cudaEventCreate(&rec.a));
+      CUDA_TRY(cudaEventCreate(&rec.b));
+      g_prof.push_back(rec);
+    }
+    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].a, st));
+  }
+  kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, a);
+  LAUNCH_CHECK();
+  if (g_prof_on) {
+    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].b, st));
+    ++g_prof_used;
+  }
+  return 0;
+}
+
 // 3x3x3 conv -> raw bf16 output + InstanceNorm partial statistics [plane][*nseg_out][16] in `partial`
 static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const bf16* src1, bf16* out, float* partial,
                     float* splitk, int* nseg_out, int lvl, int B, cudaStream_t st) {
@@ -382,12 +445,22 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
   if (c.nb1 > 0) TRY(make_act_tmap(&t1, src1, B * (c.c1p / 8), D, H, W, c.cb_ch / 8, 1));
   else t1 = t0;
   const ConvGeom g = conv_geom(p, c, lvl, B);
+  const int want_split = (splitk && partial) ? g.ksplit : 1;
+  if (c.packed64 && want_split == 1 && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {
+    ConvTc64Args b;
+    memset(&b, 0, sizeof b);
+    b.w = c.packed64; b.out = out; b.stats = partial; b.nb0 = c.nb0; b.nb1 = c.nb1; b.chunks0 = c.c0p / 8; b.chunks1 = c.c1p / 8;
+    b.D = D; b.H = H; b.W = W; b.tiles_x = g.tiles_x; b.tiles_y = g.tiles_y; b.tiles_z = g.tiles_z; b.batch = B;
+    TRY(c.cb_ch == 32 ? launch_conv_tc64<32>(t0, t1, b, st) : launch_conv_tc64<64>(t0, t1, b, st));
+    if (partial) *nseg_out = g.tiles;
+    return 0;
+  }
   ConvTcArgs a;
   memset(&a, 0, sizeof a);
   a.w = c.packed; a.out = out; a.nb0 = c.nb0; a.nb1 = c.nb1; a.chunks0 = c.c0p / 8; a.chunks1 = c.c1p / 8;
   a.cout = c.coutp; a.D = D; a.H = H; a.W = W;
   a.tiles_x = g.tiles_x; a.tiles_y = g.tiles_y; a.tiles_z = g.tiles_z; a.n_tiles = c.n_tiles; a.batch = B;
-  a.ksplit = (splitk && partial) ? g.ksplit : 1;
+  a.ksplit = want_split;
   a.dbg = g_conv_dbg;
   if (a.ksplit > 1) a.out_partial = splitk;
   else a.stats = partial;
@@ -399,7 +472,7 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
   else return fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
   TRY(rc);
   if (a.ksplit > 1) {
-    const int nseg = stats_nseg(p->V[lvl]);
+    const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
     splitk_reduce_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(
         splitk, a.ksplit, (long long)B * c.coutp * p->V[lvl], out, partial, p->V[lvl], nseg);
     LAUNCH_CHECK();
@@ -675,6 +748,13 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       pack_conv_w_kernel<<<grid_for((long long)c->packed_elems(), 256), 256, 0, st>>>(
           src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->nb0 + c->nb1, c->n_tiles);
       LAUNCH_CHECK();
+      if (c->coutp == 64) {
+        const size_t n64 = (size_t)(c->nb0 + c->nb1) * 9 * c->cb_ch * 192;
+        if (!c->packed64) TRY(dev_alloc(p, (void**)&c->packed64, n64 * sizeof(bf16)));
+        pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(src, c->packed64, c->coutr, cinr, c->c0r, c->c0p,
+                                                                             c->c1r, c->cb_ch, c->nb0 + c->nb1);
+        LAUNCH_CHECK();
+      }
       if (p->cfg.flags & DUNET_FLAG_KEEP_FP32_WEIGHTS) {
         const size_t bytes = (size_t)c->coutr * cinr * 27 * sizeof(float);
         if (!c->w32) TRY(dev_alloc(p, (void**)&c->w32, bytes));
@@ -912,7 +992,7 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dunet_plan tmp;  // only geometry fields are used by run_conv
   memset(&tmp.cfg, 0, sizeof tmp.cfg);
-  tmp.cfg.flags = use_ref ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : 0;
+  tmp.cfg.flags = use_ref == 1 ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : 0;
   tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
   tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
   ConvW c;
@@ -931,13 +1011,20 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
     LAUNCH_CHECK();
   }
   int rc = 0;
-  if (use_ref) {
+  if (use_ref == 1) {
     c.w32 = const_cast<float*>(weight);
   } else {
     CUDA_TRY(cudaMallocAsync((void**)&c.packed, c.packed_elems() * sizeof(bf16), st));
     pack_conv_w_kernel<<<grid_for((long long)c.packed_elems(), 256), 256, 0, st>>>(
         weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.nb0 + c.nb1, c.n_tiles);
     LAUNCH_CHECK();
+    if (c.coutp == 64 && use_ref != 2) {
+      const size_t n64 = (size_t)(c.nb0 + c.nb1) * 9 * c.cb_ch * 192;
+      CUDA_TRY(cudaMallocAsync((void**)&c.packed64, n64 * sizeof(bf16), st));
+      pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(weight, c.packed64, c.coutr, c0 + c1, c.c0r, c.c0p,
+                                                                           c.c1r, c.cb_ch, c.nb0 + c.nb1);
+      LAUNCH_CHECK();
+    }
   }
   int nseg_unused = 0;
   rc = run_conv(&tmp, c, a0, a1, raw, nullptr, nullptr, &nseg_unused, 0, B, st);
@@ -950,6 +1037,7 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   cudaFreeAsync(raw, st);
   if (a1) cudaFreeAsync(a1, st);
   if (c.packed) cudaFreeAsync(c.packed, st);
+  if (c.packed64) cudaFreeAsync(c.packed64, st);
   return rc;
 }
 

@@ -431,24 +431,36 @@ __global__ void __launch_bounds__(256) final_ddim_kernel(FinalDdimArgs a) {
         }
       }
     }
-    // DDIM update (x_t given) or plain logits; lg[] is overwritten with x_{t-1} for the re-pack below
+    // DDIM update (x_t given) or plain logits; lg[] is overwritten with x_{t-1} for the re-pack below.
+    // All loads are issued before any store so the 2*C independent 4-byte loads overlap (the state tensors are planar).
+    const long long o0 = (long long)n * a.C * a.vox + v;
+    if (a.x_t) {
+      float xt[CP], ac[CP];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      if (c < a.C) {
-        const long long o = ((long long)n * a.C + c) * a.vox + v;
-        if (a.logits_out) a.logits_out[o] = lg[c];
-        if (a.x_t) {
-          const float x0 = fminf(fmaxf(lg[c], -1.f), 1.f);
-          const float xt = a.x_t[o];
-          const float eps = (a.r * xt - x0) / a.m;
-          const float xp = x0 * s_abp + s_1mabp * eps;
-          a.x_t[o] = xp;
-          a.acc[o] += x0;
-          lg[c] = xp;
+      for (int c = 0; c < CP; ++c) {
+        if (c < a.C) {
+          xt[c] = a.x_t[o0 + c * a.vox];
+          ac[c] = a.acc[o0 + c * a.vox];
         }
-      } else {
-        lg[c] = 0.f;
       }
+#pragma unroll
+      for (int c = 0; c < CP; ++c) {
+        if (c < a.C) {
+          if (a.logits_out) a.logits_out[o0 + c * a.vox] = lg[c];
+          const float x0 = fminf(fmaxf(lg[c], -1.f), 1.f);
+          const float eps = (a.r * xt[c] - x0) / a.m;
+          const float xp = x0 * s_abp + s_1mabp * eps;
+          a.x_t[o0 + c * a.vox] = xp;
+          a.acc[o0 + c * a.vox] = ac[c] + x0;
+          lg[c] = xp;
+        } else {
+          lg[c] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < a.C && a.logits_out) a.logits_out[o0 + c * a.vox] = lg[c];
     }
     if (a.next_in) {
       // channel order cat([image, x]) (denoiser.py:298): packed channel 0 = image, 1..C = x_{t-1}, rest zero

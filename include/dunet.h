@@ -39,6 +39,8 @@ enum {
 #define DUNET_FLAG_REF_CONV 1u /* debug: run 3x3x3 convs on the CUDA-core reference kernel instead of tcgen05 (tests) */
 #define DUNET_FLAG_KEEP_FP32_WEIGHTS 2u /* debug: keep fp32 copies of conv weights (needed by DUNET_FLAG_REF_CONV) */
 
+#define DUNET_FLAG_GENERIC_CONV 4u /* debug: route Cout = 64 convs through the generic tcgen05 kernel (no z-stacking) */
+
 typedef struct dunet_plan dunet_plan;
 
 /* Mirrors DiffUNet.__init__(spatial_dims=3, in_channels, out_channels, image_size, spatial_size, features, ...)
@@ -118,6 +120,7 @@ int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channel
 
 /* Stand-alone operator (also the unit-test seam of the tensor-core kernel): y = conv3d(cat([src0, src1]), weight),
  * 3x3x3, stride 1, zero padding 1, no bias.  fp32 NCDHW in/out, bf16 operands + fp32 accumulation inside.
+ * use_ref_kernel: 0 = production tcgen05 kernels, 1 = CUDA-core debug kernel, 2 = generic tcgen05 kernel only.
  * replaces: nn.Conv3d inside MONAI Convolution (denoiser.py:56-58).  use_ref_kernel != 0 selects the debug CUDA-core
  * kernel.  Allocates its own scratch with cudaMallocAsync on `stream`. */
 int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t c1, const float* weight, int32_t cout,

@@ -21,13 +21,13 @@ def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _conv_op(src0, w, src1=None, ref=False):
+def _conv_op(src0, w, src1=None, ref=0):
     lib = _lib.load()
     B, c0, D, H, W = src0.shape
     c1 = 0 if src1 is None else src1.shape[1]
     out = torch.empty((B, w.shape[0], D, H, W), device="cuda")
     _lib.check(lib.dunet_op_conv3x3x3(_p(src0), c0, _p(src1), c1, _p(w.contiguous()), w.shape[0], _p(out), B,
-                                      _lib.i32x3((D, H, W)), 1 if ref else 0,
+                                      _lib.i32x3((D, H, W)), int(ref),
                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     return out
@@ -50,9 +50,10 @@ def test_conv3x3x3_tensor_core_vs_fp64(c0, c1, cout, B, dims):
     w = torch.randn(cout, c0 + c1, 3, 3, 3, device="cuda") / (27 * (c0 + c1)) ** 0.5
     xin = _bf(s0 if s1 is None else torch.cat([s0, s1], 1))
     exp = F.conv3d(xin.double(), _bf(w).double(), padding=1).float()
-    got = _conv_op(s0, w, s1)
-    assert rel_l2(got, exp) < 4e-3  # one bf16 rounding of the output (2^-9 max relative)
-    assert (got - exp).abs().max() <= 2 ** -7 * exp.abs().max()
+    for kernel in (0, 2):  # 0: production dispatch (z-stacked kernel when Cout <= 64), 2: generic tcgen05 kernel
+        got = _conv_op(s0, w, s1, ref=kernel)
+        assert rel_l2(got, exp) < 4e-3  # one bf16 rounding of the output (2^-9 max relative)
+        assert (got - exp).abs().max() <= 2 ** -7 * exp.abs().max()
 
 
 def test_conv_zero_padding_is_exact():

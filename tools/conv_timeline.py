@@ -30,8 +30,9 @@ for name, c0, c1, cout, dims in [("64->64 96^3", 64, 0, 64, (96, 96, 96)), ("64+
         lib.dunet_debug_set_conv_timeline(None)
     t = dbg.view(-1, 8).cpu()
     t = t[t[:, 0] != 0][:, :5].double()
-    d = t[:, 1:] - t[:, :-1]
     flops = 2.0 * x0[0, 0].numel() * cout * 27 * (c0 + c1)
     print(f"{name}: kernel {ms.value * 1e3:.1f} us  {flops / ms.value / 1e9:.0f} TFLOP/s  ctas {len(t)}")
-    print("   mean cycles: start->first MMA issued %.0f | MMA issue span %.0f | issue-end->acc complete %.0f | epilogue %.0f | total %.0f"
-          % (d[:, 0].mean(), d[:, 1].mean(), d[:, 2].mean(), d[:, 3].mean(), (t[:, 4] - t[:, 0]).mean()))
+    if len(t):
+        d = t[:, 1:] - t[:, :-1]
+        print("   mean cycles: start->first MMA issued %.0f | MMA issue span %.0f | issue-end->acc complete %.0f | epilogue %.0f | total %.0f"
+              % (d[:, 0].mean(), d[:, 1].mean(), d[:, 2].mean(), d[:, 3].mean(), (t[:, 4] - t[:, 0]).mean()))
