@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(128) conv3d_ref_kernel(const __nv_bfloat16* __
                                                          const __nv_bfloat16* __restrict__ src1, int c1, int chunks1,
                                                          const float* __restrict__ w /*[cout][c0+c1][27]*/,
                                                          __nv_bfloat16* __restrict__ out, int cout, int out_chunks,
-                                                         int D, int H, int W, int batch) {
+                                                         int D, int H, int W, int batch, int rot) {
   // cout = REAL output channels; out_chunks = chunk stride of the (padded) output tensor, padded chunks untouched
   const long long vox = (long long)D * H * W;
   const int och = (cout + 7) / 8;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(128) conv3d_ref_kernel(const __nv_bfloat16* __
                 for (int j = 0; j < 8; ++j) {
                   if (oc * 8 + j >= cout) continue;
                   const float wv =
-                      __bfloat162float(__float2bfloat16_rn(w[((long long)(oc * 8 + j) * cin + ci + k) * 27 + tap]));
+                      __bfloat162float(__float2bfloat16_rn(w[((long long)(oc * 8 + j) * cin + (rot ? (ci + k + 1) % c0 : ci + k)) * 27 + tap]));
                   acc[j] = fmaf(xi[k], wv, acc[j]);
                 }
               }

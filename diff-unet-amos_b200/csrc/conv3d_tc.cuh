@@ -55,7 +55,7 @@ struct ConvTc {
   static constexpr int B_LBO = N_TILE * 16;
   static constexpr int B_SBO = 128;
   static constexpr int PLANES = ZT + 2 * HALO;
-  static constexpr int A_SLOTS = 8;
+  static constexpr int A_SLOTS = MODE == MODE_CONV3 ? 8 : 2 * PLANES;  // transposed conv: small ring -> 2 CTAs per SM
   static constexpr int W_SLOTS = (32768 / W_UNIT_BYTES) < 2 ? 2 : ((32768 / W_UNIT_BYTES) > 8 ? 8 : (32768 / W_UNIT_BYTES));
   static constexpr int TMEM_COLS = (ZT * N_TILE <= 32) ? 32 : (ZT * N_TILE <= 64) ? 64 : (ZT * N_TILE <= 128) ? 128
                                    : (ZT * N_TILE <= 256) ? 256 : 512;

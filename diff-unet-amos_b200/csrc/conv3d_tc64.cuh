@@ -44,7 +44,7 @@ struct ConvTc64 {
 struct ConvTc64Args {
   const __nv_bfloat16* w;  // packed [cin_block][ty*3+tx][KCH][192][8]
   __nv_bfloat16* out;      // raw conv output, C8-planar, 64 channels
-  float* stats;            // [n*8 + chunk][tiles per sample][16] or nullptr
+  float* stats;            // [n*8 + chunk][gridDim.x][16] (one row per CTA and sample) or nullptr
   int nb0, nb1, chunks0, chunks1;
   int D, H, W;
   int tiles_x, tiles_y, tiles_z, batch;
@@ -192,6 +192,24 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const long long vox = (long long)a.D * a.H * a.W;
+    // InstanceNorm statistics: lane l of each warp carries, per 16-column group j, the running (sum | sum of squares)
+    // of column j*16 + (l & 15) over this warp's rows of all tiles of the current sample; one row [16] per
+    // (sample, chunk, CTA) is written when the sample changes / at the end  ->  nseg = gridDim.x, fixed order.
+    float run[4] = {0.f, 0.f, 0.f, 0.f};
+    int cur_n = -1;
+    auto flush = [&](int n_flush) {
+      // combine the four warps in a fixed order and write this CTA's row for sample n_flush
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[q * 128 + j * 32 + lane] = run[j];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = r;
+      const float tot = (red[e] + red[128 + e]) + (red[256 + e] + red[384 + e]);
+      const int l = e & 31, col = (e >> 5) * 16 + (l & 15), stat = l >> 4;
+      a.stats[(((long long)n_flush * 8 + (col >> 3)) * gridDim.x + blockIdx.x) * 16 + stat * 8 + (col & 7)] = tot;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 4; ++j) run[j] = 0.f;
+    };
     int li = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
       int t = tile;
@@ -199,13 +217,18 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       const int tiy = t % a.tiles_y; t /= a.tiles_y;
       const int tiz = t % a.tiles_z; t /= a.tiles_z;
       const int n = t;
+      if (a.stats && n != cur_n) {
+        // samples this CTA skipped entirely still need a (zero) row
+        for (int m = cur_n < 0 ? 0 : cur_n; m < n; ++m) flush(m);
+        cur_n = n;
+      }
       const int x = tix * CONV_TX + (r & 7), y = tiy * CONV_TY + (r >> 3), z0 = tiz * ZT;
       const bool xy_ok = x < a.W && y < a.H;
       const int buf = li & 1, use = li >> 1;
       mbar_wait(acc_full + 8 * buf, use & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS;
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
         float st[32];
 #pragma unroll
@@ -234,21 +257,15 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             }
           }
         }
-        if (a.stats) red[q * 128 + j * 32 + lane] = warp_reduce32(st, lane);
+        if (a.stats) run[j] += warp_reduce32(st, lane);
       }
       // all TMEM reads of this accumulator set are done: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
-      if (a.stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int e = r;  // 0..127 = 4 column groups x 32 (16 sums, 16 sums of squares)
-        const float tot = (red[e] + red[128 + e]) + (red[256 + e] + red[384 + e]);
-        const int l = e & 31, col = (e >> 5) * 16 + (l & 15), stat = l >> 4;
-        const int tile_lin = tile % tiles_per_n;
-        a.stats[(((long long)n * 8 + (col >> 3)) * tiles_per_n + tile_lin) * 16 + stat * 8 + (col & 7)] = tot;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // red[] is reused by the next tile
-      }
+    }
+    if (a.stats) {
+      for (int m = cur_n < 0 ? 0 : cur_n; m < a.batch; ++m) flush(m);
     }
   }
   __syncthreads();

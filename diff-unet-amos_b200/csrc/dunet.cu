@@ -104,7 +104,7 @@ static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, in
 // ------------------------------------------------------------------------------------------------ weight packing
 // conv weights fp32 [coutr][cinr][27] -> bf16 [n_tile][cin block][tap][k chunk][N_TILE][8]   (see conv3d_tc.cuh)
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles) {
+                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles, int rot) {
   const int kch = cb_ch / 8;
   const long long total = (long long)n_tiles * ncb * 27 * kch * n_tile * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -119,7 +119,7 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict
     const int co = nt * n_tile + col;
     const int lc = cb * cb_ch + k * 8 + j;
     int ci = -1;
-    if (lc < c0p) { if (lc < c0r) ci = lc; }
+    if (lc < c0p) { if (lc < c0r) ci = rot ? (lc + 1) % c0r : lc; }  // rot: packed order is [x.., image], reference [image, x..]
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
@@ -129,7 +129,7 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict
 // conv weights for the Cout = 64 z-stacked kernel (conv3d_tc64.cuh): bf16 [cin block][ty*3+tx][k chunk][192][8] with
 // row = (2 - tz) * 64 + cout
 __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                     int c0p, int c1r, int cb_ch, int ncb) {
+                                     int c0p, int c1r, int cb_ch, int ncb, int rot) {
   const int kch = cb_ch / 8;
   const long long total = (long long)ncb * 9 * kch * 192 * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -144,7 +144,7 @@ __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restri
     const int tap = tz * 9 + tyx;
     const int lc = cb * cb_ch + k * 8 + j;
     int ci = -1;
-    if (lc < c0p) { if (lc < c0r) ci = lc; }
+    if (lc < c0p) { if (lc < c0r) ci = rot ? (lc + 1) % c0r : lc; }  // rot: packed order is [x.., image], reference [image, x..]
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
@@ -205,6 +205,7 @@ struct ConvW {
   bf16* packed64 = nullptr;  // z-stacked layout for the Cout = 64 kernel (coutp == 64 only)
   float* w32 = nullptr;  // debug copy of the original fp32 weight
   float *gamma = nullptr, *beta = nullptr;
+  int rot = 0;  // 1: packed input channel j holds reference channel (j + 1) % c0r (denoiser input [x.., image])
   bool have_w = false, have_cb = false, have_g = false, have_b = false;
   void shape(int c0r_, int c0p_, int c1r_, int c1p_, int coutr_) {
     c0r = c0r_; c0p = c0p_; c1r = c1r_; c1p = c1p_; coutr = coutr_;
@@ -295,14 +296,17 @@ static void add_twoconv_slots(dunet_plan* p, const std::string& pre, TwoConvW* t
 
 constexpr int CONV_ZT = 4;
 
-struct ConvGeom { int tiles_x, tiles_y, tiles_z, tiles, ksplit; };
+struct ConvGeom { int tiles_x, tiles_y, tiles_z, tiles, ksplit, zt; };
 
 // tiling + split-K decision for one conv layer at U-Net level `lvl` with batch B (deterministic: depends on shapes only)
 static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
   ConvGeom g;
   g.tiles_x = (p->W[lvl] + CONV_TX - 1) / CONV_TX;
   g.tiles_y = (p->H[lvl] + CONV_TY - 1) / CONV_TY;
-  g.tiles_z = (p->D[lvl] + CONV_ZT - 1) / CONV_ZT;
+  // small volumes (deep U-Net levels) are latency bound: thinner z-tiles give more, shorter CTAs.  The Cout = 64
+  // z-stacked kernel always uses ZT = 4.
+  g.zt = (p->D[lvl] <= 24 && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
+  g.tiles_z = (p->D[lvl] + g.zt - 1) / g.zt;
   g.tiles = g.tiles_x * g.tiles_y * g.tiles_z;
   // the split factor must not depend on the batch: a window's result is bit-identical whatever it is batched with
   (void)B;
@@ -386,7 +390,8 @@ static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const Co
 static int g_num_sms = 0;
 
 template <int CB_CH>
-static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTc64Args& a, cudaStream_t st) {
+static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTc64Args& a, unsigned* grid_out,
+                            cudaStream_t st) {
   using Cfg = ConvTc64<CB_CH, CONV_ZT>;
   static bool attr_set = false;
   auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT>;
@@ -401,6 +406,7 @@ static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const 
   }
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.batch;
   const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
+  *grid_out = grid;
   if (g_prof_on) {
     if (g_prof_used == g_prof.size()) {
       ProfRec rec;
@@ -429,7 +435,7 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
     // the debug kernel writes only the chunks holding real output channels; padded chunks must still be zero
     CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * c.coutp * p->V[lvl] * sizeof(bf16), st));
     conv3d_ref_kernel<<<grid_for((long long)B * ((c.coutr + 7) / 8) * p->V[lvl], 128, 148 * 64), 128, 0, st>>>(
-        src0, c.c0r, c.c0p / 8, src1, c.c1r, c.c1p / 8, c.w32, out, c.coutr, c.coutp / 8, D, H, W, B);
+        src0, c.c0r, c.c0p / 8, src1, c.c1r, c.c1p / 8, c.w32, out, c.coutr, c.coutp / 8, D, H, W, B, c.rot);
     LAUNCH_CHECK();
     if (partial) {
       const int nseg = stats_nseg(p->V[lvl]);
@@ -446,13 +452,14 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
   else t1 = t0;
   const ConvGeom g = conv_geom(p, c, lvl, B);
   const int want_split = (splitk && partial) ? g.ksplit : 1;
-  if (c.packed64 && want_split == 1 && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {
+  if (c.packed64 && want_split == 1 && g.zt == CONV_ZT && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {
     ConvTc64Args b;
     memset(&b, 0, sizeof b);
     b.w = c.packed64; b.out = out; b.stats = partial; b.nb0 = c.nb0; b.nb1 = c.nb1; b.chunks0 = c.c0p / 8; b.chunks1 = c.c1p / 8;
     b.D = D; b.H = H; b.W = W; b.tiles_x = g.tiles_x; b.tiles_y = g.tiles_y; b.tiles_z = g.tiles_z; b.batch = B;
-    TRY(c.cb_ch == 32 ? launch_conv_tc64<32>(t0, t1, b, st) : launch_conv_tc64<64>(t0, t1, b, st));
-    if (partial) *nseg_out = g.tiles;
+    unsigned grid = 0;
+    TRY(c.cb_ch == 32 ? launch_conv_tc64<32>(t0, t1, b, &grid, st) : launch_conv_tc64<64>(t0, t1, b, &grid, st));
+    if (partial) *nseg_out = (int)grid;  // one statistics row per persistent CTA and sample
     return 0;
   }
   ConvTcArgs a;
@@ -467,6 +474,8 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
   int rc;
   if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
   else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 64 && g.zt == 2) rc = launch_conv_tc<64, 64, 2, MODE_CONV3>(t0, t1, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 128 && g.zt == 2) rc = launch_conv_tc<64, 128, 2, MODE_CONV3>(t0, t1, a, st);
   else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
   else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
   else return fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
@@ -483,39 +492,46 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
   return 0;
 }
 
-// statistics -> affine map -> fused normalise/activation(/bias/add/pool)
-static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, const float* partial, int nseg, float* ss,
+// statistics (reduced in the kernel prologue) -> fused normalise/activation(/bias/add/pool)
+static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, const float* partial, int nseg,
                     const float* bias, const bf16* add, bf16* out, bf16* pooled, int lvl, int B, cudaStream_t st) {
   const int planes = B * (c.coutp / 8);
-  stats_finalize_kernel<<<planes, 256, 0, st>>>(partial, nseg, c.gamma, c.beta, c.coutp / 8, (double)p->V[lvl], 1e-5f, ss);
-  LAUNCH_CHECK();
   NormActArgs a;
-  a.raw = raw; a.ss = ss; a.bias = bias; a.add = add;
+  a.raw = raw; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias; a.add = add;
   a.out = out; a.pooled = pooled; a.chunks = c.coutp / 8; a.D = p->D[lvl]; a.H = p->H[lvl]; a.W = p->W[lvl];
-  a.slope = 0.1f;
+  a.eps = 1e-5f; a.slope = 0.1f;
+  // ~4 resident blocks per SM in total, each streaming a long contiguous range of one 8-channel plane (the
+  // statistics prologue is paid once per block)
+  const int per_plane = std::max(1, (148 * 4 + planes - 1) / planes);
   if (pooled) {
     const long long work = p->V[lvl] / 8;
-    norm_act_kernel<true><<<dim3(grid_for(work, NORM_THREADS, 512), planes), NORM_THREADS, 0, st>>>(a);
+    norm_act_kernel<true><<<dim3(grid_for(work, NORM_THREADS, per_plane), planes), NORM_THREADS, 0, st>>>(a);
   } else {
-    norm_act_kernel<false><<<dim3(grid_for(p->V[lvl], NORM_THREADS * 4, 512), planes), NORM_THREADS, 0, st>>>(a);
+    norm_act_kernel<false><<<dim3(grid_for(p->V[lvl], NORM_THREADS * 4, per_plane), planes), NORM_THREADS, 0, st>>>(a);
   }
   LAUNCH_CHECK();
   return 0;
 }
 
+// conv -> IN -> LReLU (+temb bias) -> conv -> IN -> LReLU (+add, +pool).  With `defer_last_norm` the second normalise
+// pass is left to the consumer (the final 1x1 conv kernel applies it on the fly): the raw output stays in ws.raw and
+// *nseg_out describes its statistics rows in ws.partial.
 static int run_twoconv(const dunet_plan* p, const TwoConvW& t, const bf16* src0, const bf16* src1, const float* temb_bias,
                        const bf16* add, bf16* out, bf16* pooled, int lvl, int B, uint8_t* ws, const WsLayout& L,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool defer_last_norm = false, int* nseg_out = nullptr) {
   bf16* raw = reinterpret_cast<bf16*>(ws + L.raw);
   bf16* mid = reinterpret_cast<bf16*>(ws + L.mid);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
-  float* ss = reinterpret_cast<float*>(ws + L.ss);
   float* splitk = reinterpret_cast<float*>(ws + L.splitk);
   int nseg = 0;
   TRY(run_conv(p, t.a, src0, src1, raw, partial, splitk, &nseg, lvl, B, st));
-  TRY(run_norm(p, t.a, raw, partial, nseg, ss, temb_bias, nullptr, mid, nullptr, lvl, B, st));
+  TRY(run_norm(p, t.a, raw, partial, nseg, temb_bias, nullptr, mid, nullptr, lvl, B, st));
   TRY(run_conv(p, t.b, mid, nullptr, raw, partial, splitk, &nseg, lvl, B, st));
-  TRY(run_norm(p, t.b, raw, partial, nseg, ss, nullptr, add, out, pooled, lvl, B, st));
+  if (defer_last_norm) {
+    *nseg_out = nseg;
+    return 0;
+  }
+  TRY(run_norm(p, t.b, raw, partial, nseg, nullptr, add, out, pooled, lvl, B, st));
   return 0;
 }
 
@@ -534,9 +550,9 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf1
   memset(&a, 0, sizeof a);
   a.w = d.packed_tc; a.out = out; a.bias = d.bias; a.nb0 = d.cinp / 64; a.nb1 = 0; a.chunks0 = d.cinp / 8; a.chunks1 = 0;
   a.cout = d.coutp; a.D = D; a.H = H; a.W = W;
-  a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + CONV_ZT - 1) / CONV_ZT;
+  a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + 1) / 2;
   a.n_tiles = 8 * d.coutp / 128; a.ksplit = 1; a.batch = B; a.dbg = nullptr;
-  return launch_conv_tc<64, 128, CONV_ZT, MODE_DECONV2>(t0, t0, a, st);
+  return launch_conv_tc<64, 128, 2, MODE_DECONV2>(t0, t0, a, st);
 }
 
 static int check_call(const dunet_plan* p, int B, const void* ws) {
@@ -562,7 +578,8 @@ static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, co
 }
 
 // U-Net body given in_pack = cat([image, x_t]); leaves u1 in ws.u[1]
-static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
+static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
+                     int* last_nseg) {
   bf16* in_pack = reinterpret_cast<bf16*>(ws + L.in_pack);
   for (int l = 0; l < 5; ++l) {
     const bf16* src = l ? reinterpret_cast<bf16*>(ws + L.dpool[l]) : in_pack;
@@ -575,7 +592,7 @@ static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, c
     bf16* up = reinterpret_cast<bf16*>(ws + L.up[l]);
     TRY(run_deconv(p, p->dec[l], prev, up, l, B, st));
     TRY(run_twoconv(p, p->upc[l], reinterpret_cast<bf16*>(ws + L.x[l - 1]), up, temb_row + p->temb_off[5 + (4 - l)], nullptr,
-                    reinterpret_cast<bf16*>(ws + L.u[l]), nullptr, l - 1, B, ws, L, st));
+                    reinterpret_cast<bf16*>(ws + L.u[l]), nullptr, l - 1, B, ws, L, st, /*defer_last_norm=*/l == 1, last_nseg));
     prev = reinterpret_cast<bf16*>(ws + L.u[l]);
   }
   return 0;
@@ -595,12 +612,26 @@ static int launch_temb(dunet_plan* p, const int* d_t, int rows, float* table, cu
   return 0;
 }
 
+// fills the part of FinalDdimArgs that folds upcat_1.conv_1's InstanceNorm + LeakyReLU into the final 1x1 conv
+static void final_args_common(dunet_plan* p, FinalDdimArgs& a, uint8_t* ws, const WsLayout& L, int nseg, int B) {
+  memset(&a, 0, sizeof a);
+  a.feat = reinterpret_cast<bf16*>(ws + L.raw); a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
+  a.partial = reinterpret_cast<float*>(ws + L.partial); a.nseg = nseg; a.gamma = p->upc[1].b.gamma; a.beta = p->upc[1].b.beta;
+  a.eps = 1e-5f; a.slope = 0.1f; a.in_pad = p->in_pad; a.vox = p->V[0]; a.batch = B;
+}
+
 static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) {
-  const int grid = grid_for((long long)a.batch * a.vox, 256, 148 * 8);
-  if (a.C <= 4) final_ddim_kernel<4><<<grid, 256, 0, st>>>(a);
-  else if (a.C <= 8) final_ddim_kernel<8><<<grid, 256, 0, st>>>(a);
-  else if (a.C <= 16) final_ddim_kernel<16><<<grid, 256, 0, st>>>(a);
-  else final_ddim_kernel<32><<<grid, 256, 0, st>>>(a);
+  const dim3 grid(grid_for((a.vox + 15) / 16 * 32, FINAL_THREADS, std::max(1, 148 * 3 / a.batch)), a.batch);
+  if (a.F != 64 && a.F != 128) return fail(DUNET_E_UNSUPPORTED, "final conv: padded features[5] must be 64 or 128");
+#define DUNET_FINAL(NT)                                                                   \
+  do {                                                                                    \
+    if (a.F == 64) final_ddim_kernel<NT, 4><<<grid, FINAL_THREADS, 0, st>>>(a);           \
+    else final_ddim_kernel<NT, 8><<<grid, FINAL_THREADS, 0, st>>>(a);                     \
+  } while (0)
+  if (a.C <= 8) DUNET_FINAL(1);
+  else if (a.C <= 16) DUNET_FINAL(2);
+  else DUNET_FINAL(4);
+#undef DUNET_FINAL
   LAUNCH_CHECK();
   return 0;
 }
@@ -682,7 +713,7 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
     e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l]);
     TwoConvW& d = p->den[l];
     d.has_temb = true;
-    if (l == 0) d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0]);
+    if (l == 0) { d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0]); d.a.rot = 1; }
     else d.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l]);
     d.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l]);
   }
@@ -746,13 +777,13 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       if (!c->packed) TRY(dev_alloc(p, (void**)&c->packed, c->packed_elems() * sizeof(bf16)));
       const int cinr = c->c0r + c->c1r;
       pack_conv_w_kernel<<<grid_for((long long)c->packed_elems(), 256), 256, 0, st>>>(
-          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->nb0 + c->nb1, c->n_tiles);
+          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->nb0 + c->nb1, c->n_tiles, c->rot);
       LAUNCH_CHECK();
       if (c->coutp == 64) {
         const size_t n64 = (size_t)(c->nb0 + c->nb1) * 9 * c->cb_ch * 192;
         if (!c->packed64) TRY(dev_alloc(p, (void**)&c->packed64, n64 * sizeof(bf16)));
         pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(src, c->packed64, c->coutr, cinr, c->c0r, c->c0p,
-                                                                             c->c1r, c->cb_ch, c->nb0 + c->nb1);
+                                                                             c->c1r, c->cb_ch, c->nb0 + c->nb1, c->rot);
         LAUNCH_CHECK();
       }
       if (p->cfg.flags & DUNET_FLAG_KEEP_FP32_WEIGHTS) {
@@ -907,13 +938,13 @@ int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int3
     TRY(launch_temb(p, p->d_tmap + row, 1, p->temb_table + (size_t)row * p->temb_row, st));
   }
   pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
-      image, p->cfg.in_channels, x_t, p->C, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
+      x_t, p->C, image, p->cfg.in_channels, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
   LAUNCH_CHECK();
-  TRY(unet_body(p, p->temb_table + (size_t)row * p->temb_row, B, ws, L, st));
+  int nseg = 0;
+  TRY(unet_body(p, p->temb_table + (size_t)row * p->temb_row, B, ws, L, st, &nseg));
   FinalDdimArgs a;
-  memset(&a, 0, sizeof a);
-  a.feat = reinterpret_cast<bf16*>(ws + L.u[1]); a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
-  a.image = image; a.logits_out = logits_out; a.in_pad = p->in_pad; a.vox = p->V[0]; a.batch = B;
+  final_args_common(p, a, ws, L, nseg, B);
+  a.image = image; a.logits_out = logits_out;
   a.r = 1.f; a.m = 1.f; a.abp = 1.f;
   return launch_final(p, a, st);
 }
@@ -932,17 +963,16 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   CUDA_TRY(cudaMemcpyAsync(x_t, noise, state_bytes, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemsetAsync(acc_out, 0, state_bytes, st));
   pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
-      image, p->cfg.in_channels, x_t, p->C, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
+      x_t, p->C, image, p->cfg.in_channels, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
   LAUNCH_CHECK();
   for (int i = p->n_steps - 1, k = 0; i >= 0; --i, ++k) {  // gaussian_diffusion.py:694 indices high -> low
-    TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st));
+    int nseg = 0;
+    TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st, &nseg));
     FinalDdimArgs a;
-    memset(&a, 0, sizeof a);
-    a.feat = reinterpret_cast<bf16*>(ws + L.u[1]); a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
+    final_args_common(p, a, ws, L, nseg, B);
     a.image = image; a.x_t = x_t; a.acc = acc_out;
     a.logits_out = per_step_logits ? per_step_logits + (size_t)k * B * p->C * p->V[0] : nullptr;
     a.next_in = i > 0 ? reinterpret_cast<bf16*>(ws + L.in_pack) : nullptr;
-    a.in_pad = p->in_pad; a.vox = p->V[0]; a.batch = B;
     a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
     TRY(launch_final(p, a, st));
   }
@@ -1016,13 +1046,13 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   } else {
     CUDA_TRY(cudaMallocAsync((void**)&c.packed, c.packed_elems() * sizeof(bf16), st));
     pack_conv_w_kernel<<<grid_for((long long)c.packed_elems(), 256), 256, 0, st>>>(
-        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.nb0 + c.nb1, c.n_tiles);
+        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.nb0 + c.nb1, c.n_tiles, 0);
     LAUNCH_CHECK();
     if (c.coutp == 64 && use_ref != 2) {
       const size_t n64 = (size_t)(c.nb0 + c.nb1) * 9 * c.cb_ch * 192;
       CUDA_TRY(cudaMallocAsync((void**)&c.packed64, n64 * sizeof(bf16), st));
       pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(weight, c.packed64, c.coutr, c0 + c1, c.c0r, c.c0p,
-                                                                           c.c1r, c.cb_ch, c.nb0 + c.nb1);
+                                                                           c.c1r, c.cb_ch, c.nb0 + c.nb1, 0);
       LAUNCH_CHECK();
     }
   }

@@ -188,35 +188,41 @@ __global__ void __launch_bounds__(STATS_THREADS) splitk_reduce_stats_kernel(cons
 // ---------------------------------------------------------------------------------------------------------------
 struct NormActArgs {
   const __nv_bfloat16* raw;
-  const float* ss;         // from stats_finalize_kernel: [plane][16] = 8 scales (rstd*gamma), 8 shifts (beta - mean*scale)
+  const float* partial;    // InstanceNorm partial statistics [plane][nseg][16] (8 sums, 8 sums of squares per row)
+  int nseg;
+  const float* gamma;      // [C]
+  const float* beta;       // [C]
   const float* bias;       // [C] additive after activation (temb projection) or nullptr
   const __nv_bfloat16* add;  // C8-planar tensor added after activation (encoder feature) or nullptr
   __nv_bfloat16* out;
   __nv_bfloat16* pooled;   // POOL only
   int chunks;              // C/8
   int D, H, W;
-  float slope;
+  float eps, slope;
 };
 
 constexpr int NORM_THREADS = 256;
 
-// Second stage of the InstanceNorm statistics: fixed-order fp64 reduction of the per-CTA / per-segment partial rows
-// [plane][nseg][16] into the affine map of the normalisation (biased variance, eps inside the sqrt, as F.instance_norm).
-__global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __restrict__ partial, int nseg,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, int chunks, double count,
-                                                             float eps, float* __restrict__ ss) {
-  __shared__ double red[16][16];
-  const int plane = blockIdx.x, e = threadIdx.x & 15, g0 = threadIdx.x >> 4;
-  double acc = 0.0;
-  for (int g = g0; g < nseg; g += 16) acc += (double)partial[((long long)plane * nseg + g) * 16 + e];
-  red[g0][e] = acc;
+// Second stage of the InstanceNorm statistics, done by every consumer block for its own 8 channels: fixed-order fp64
+// reduction of the partial rows into the affine map of the normalisation (biased variance, eps inside the sqrt, as
+// F.instance_norm).  nseg <= a few hundred rows (one per conv CTA / reduction segment), so this is ~10 KB from L2.
+// sc/sh: 8 floats each; scratch: 16*16 doubles.  Needs >= 256 threads; ends with __syncthreads().
+__device__ __forceinline__ void stats_to_affine(const float* __restrict__ partial, int nseg, int plane,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                int chunks, double count, float eps, float* sc, float* sh,
+                                                double* scratch) {
+  if (threadIdx.x < 256) {
+    const int e = threadIdx.x & 15, g0 = threadIdx.x >> 4;
+    double acc = 0.0;
+    for (int g = g0; g < nseg; g += 16) acc += (double)partial[((long long)plane * nseg + g) * 16 + e];
+    scratch[g0 * 16 + e] = acc;
+  }
   __syncthreads();
   if (threadIdx.x < 8) {
     double s = 0.0, q = 0.0;
     for (int g = 0; g < 16; ++g) {
-      s += red[g][threadIdx.x];
-      q += red[g][8 + threadIdx.x];
+      s += scratch[g * 16 + threadIdx.x];
+      q += scratch[g * 16 + 8 + threadIdx.x];
     }
     const int c = (plane % chunks) * 8 + threadIdx.x;
     const double mean = s / count;
@@ -224,19 +230,16 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __rest
     if (var < 0.0) var = 0.0;
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float scale = rstd * gamma[c];
-    ss[plane * 16 + threadIdx.x] = scale;
-    ss[plane * 16 + 8 + threadIdx.x] = beta[c] - (float)mean * scale;
-  }
-}
-
-__device__ __forceinline__ void norm_prologue(const NormActArgs& a, int plane, float* sc, float* sh, float* bi) {
-  if (threadIdx.x < 8) {
-    const int c = (plane % a.chunks) * 8 + threadIdx.x;
-    sc[threadIdx.x] = a.ss[plane * 16 + threadIdx.x];
-    sh[threadIdx.x] = a.ss[plane * 16 + 8 + threadIdx.x];
-    bi[threadIdx.x] = a.bias ? a.bias[c] : 0.f;
+    sc[threadIdx.x] = scale;
+    sh[threadIdx.x] = beta[c] - (float)mean * scale;
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void norm_prologue(const NormActArgs& a, int plane, float* sc, float* sh, float* bi,
+                                              double* scratch) {
+  if (threadIdx.x < 8) bi[threadIdx.x] = a.bias ? a.bias[(plane % a.chunks) * 8 + threadIdx.x] : 0.f;
+  stats_to_affine(a.partial, a.nseg, plane, a.gamma, a.beta, a.chunks, (double)a.D * a.H * a.W, a.eps, sc, sh, scratch);
 }
 
 __device__ __forceinline__ void norm_apply(float (&f)[8], const float* sc, const float* sh, const float* bi,
@@ -252,8 +255,9 @@ __device__ __forceinline__ void norm_apply(float (&f)[8], const float* sc, const
 template <bool POOL>
 __global__ void __launch_bounds__(NORM_THREADS) norm_act_kernel(NormActArgs a) {
   __shared__ float sc[8], sh[8], bi[8];
+  __shared__ double scratch[256];
   const int plane = blockIdx.y;  // n*chunks + chunk
-  norm_prologue(a, plane, sc, sh, bi);
+  norm_prologue(a, plane, sc, sh, bi, scratch);
   const long long vox = (long long)a.D * a.H * a.W;
   const BF8* in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
   const BF8* add = a.add ? reinterpret_cast<const BF8*>(a.add) + plane * vox : nullptr;
@@ -368,13 +372,27 @@ __global__ void __launch_bounds__(256) deconv2_kernel(const __nv_bfloat16* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// final 1x1x1 conv (denoiser.py:282,311) fused with the DDIM update (gaussian_diffusion.py:292-297 clamp,
-// :345-349 eps, :566-584 eta=0 step), the ensemble accumulation (models/diffusion/diffusion.py:94-98) and the
-// re-pack of cat([image, x_{t-1}]) as the next step's bf16 conv input.   thread = voxel.
+// final 1x1x1 conv (denoiser.py:282,311) fused with
+//   * the InstanceNorm + LeakyReLU of its input (the last TwoConv's normalise pass: u1 never goes to HBM),
+//   * the DDIM update (gaussian_diffusion.py:292-297 clamp, :345-349 eps, :566-584 eta = 0 step),
+//   * the ensemble accumulation (models/diffusion/diffusion.py:94-98),
+//   * the re-pack of the next step's bf16 conv input.
+// The [voxels x F] x [F x C] product runs on warp-level bf16 MMAs (m16n8k16) with the fp32 weights split into
+// hi + lo bf16 parts (two MMAs) so the weights keep ~16 mantissa bits; everything else is plain fp32.
+// The kernel is HBM-bound (reads the 64-channel feature map once, reads/writes the fp32 state once).
+//
+// Packed denoiser-input channel order: [x_0 .. x_{C-1}, image, 0 ...]  (the reference's cat([image, x]) order is
+// restored by permuting the first conv's input channels when its weights are packed), so a thread's two adjacent
+// classes form one aligned 4-byte store.
 // ---------------------------------------------------------------------------------------------------------------
 struct FinalDdimArgs {
-  const __nv_bfloat16* feat;  // u1, C8-planar, F channels
-  int F;
+  const __nv_bfloat16* feat;  // RAW output of the last conv (or, with partial == nullptr, the activated u1), C8-planar
+  int F;                      // feature channels (multiple of 16, <= 128)
+  const float* partial;       // InstanceNorm partial statistics of `feat` [n*F/8 + chunk][nseg][16] or nullptr
+  int nseg;
+  const float* gamma;
+  const float* beta;
+  float eps, slope;
   const float* w;             // [C][F] fp32
   const float* b;             // [C]
   int C;
@@ -382,7 +400,7 @@ struct FinalDdimArgs {
   float* x_t;                 // [B][C][vox] fp32, updated in place (nullptr: logits only)
   float* acc;                 // [B][C][vox] fp32, += clamp(logits)
   float* logits_out;          // optional [B][C][vox]
-  __nv_bfloat16* next_in;     // optional packed cat([image, x_prev]) with in_pad channels
+  __nv_bfloat16* next_in;     // optional packed [x_prev, image, 0..] with in_pad channels
   int in_pad;
   long long vox;
   int batch;
@@ -391,93 +409,151 @@ struct FinalDdimArgs {
 
 constexpr int FINAL_MAX_C = 32;
 constexpr int FINAL_MAX_F = 128;
+constexpr int FINAL_THREADS = 256;
 
-// CP = classes padded to a multiple of 4 (template: 4, 8, 16, 32).  Weights sit transposed in shared memory as
-// [F][CP] so one 16-byte LDS feeds 4 class accumulators.
-template <int CP>
-__global__ void __launch_bounds__(256) final_ddim_kernel(FinalDdimArgs a) {
-  __shared__ __align__(16) float sw[FINAL_MAX_F * CP];
-  __shared__ float sb[CP];
-  for (int i = threadIdx.x; i < a.F * CP; i += blockDim.x) {
-    const int c = i % CP, k = i / CP;
-    sw[i] = c < a.C ? a.w[c * a.F + k] : 0.f;
-  }
-  for (int i = threadIdx.x; i < CP; i += blockDim.x) sb[i] = i < a.C ? a.b[i] : 0.f;
-  __syncthreads();
-  const float s_abp = sqrtf(a.abp), s_1mabp = sqrtf(1.f - a.abp - 0.f);
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// NT = number of 8-class column tiles (C <= 8 * NT); NKS = F / 16 k-steps
+template <int NT, int NKS>
+__global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs a) {
+  // B fragments of the weights: [k-step][n-tile][hi|lo][b0|b1][lane]
+  __shared__ uint32_t wfrag[(FINAL_MAX_F / 16) * NT * 2 * 2 * 32];
+  __shared__ float sbias[NT * 8];
+  __shared__ float nsc[FINAL_MAX_F], nsh[FINAL_MAX_F];
+  __shared__ double scratch[256];
+  constexpr int nks = NKS;
   const int fch = a.F / 8;
-  const long long total = (long long)a.batch * a.vox;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long v = i % a.vox;
-    const int n = (int)(i / a.vox);
-    float lg[CP];
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  if (a.partial) {
+    for (int k = 0; k < fch; ++k)
+      stats_to_affine(a.partial, a.nseg, n * fch + k, a.gamma, a.beta, fch, (double)a.vox, a.eps, nsc + k * 8, nsh + k * 8, scratch);
+  }
+  for (int i = threadIdx.x; i < nks * NT * 32; i += FINAL_THREADS) {
+    const int l = i & 31, nt = (i >> 5) % NT, ks = i / (32 * NT);
+    const int cls = nt * 8 + (l >> 2), k0 = ks * 16 + 2 * (l & 3);
+    float wv[4];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) lg[c] = sb[c];
-    const BF8* fp = reinterpret_cast<const BF8*>(a.feat) + (long long)n * fch * a.vox + v;
-    for (int k = 0; k < fch; ++k) {
-      float f[8];
-      bf8_to_float(fp[(long long)k * a.vox], f);
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + (j & 1) + (j >> 1) * 8;
+      wv[j] = cls < a.C ? a.w[cls * a.F + k] : 0.f;
+    }
+    float hi[4], lo[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4* wr = reinterpret_cast<const float4*>(sw + (k * 8 + j) * CP);
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __bfloat162float(__float2bfloat16_rn(wv[j]));
+      lo[j] = wv[j] - hi[j];
+    }
+    uint32_t* dst = wfrag + ((ks * NT + nt) * 4) * 32 + l;
+    dst[0] = pack_bf16x2(hi[0], hi[1]);
+    dst[32] = pack_bf16x2(hi[2], hi[3]);
+    dst[64] = pack_bf16x2(lo[0], lo[1]);
+    dst[96] = pack_bf16x2(lo[2], lo[3]);
+  }
+  for (int i = threadIdx.x; i < NT * 8; i += FINAL_THREADS) sbias[i] = i < a.C ? a.b[i] : 0.f;
+  __syncthreads();
+
+  const float s_abp = sqrtf(a.abp), s_1mabp = sqrtf(1.f - a.abp - 0.f);
+  const uint32_t* fw = reinterpret_cast<const uint32_t*>(a.feat) + (long long)n * fch * a.vox * 4;  // 4 words per 16 B
+  const int warps = gridDim.x * (FINAL_THREADS / 32);
+  const int warp_id = blockIdx.x * (FINAL_THREADS / 32) + (threadIdx.x >> 5);
+  const long long ngroups = (a.vox + 15) / 16;
+  for (long long grp = warp_id; grp < ngroups; grp += warps) {
+    const long long v0 = grp * 16 + g, v1 = v0 + 8;
+    const bool ok0 = v0 < a.vox, ok1 = v1 < a.vox;
+    float d[NT][4];
 #pragma unroll
-        for (int c4 = 0; c4 < CP / 4; ++c4) {
-          const float4 w4 = wr[c4];
-          lg[c4 * 4 + 0] = fmaf(f[j], w4.x, lg[c4 * 4 + 0]);
-          lg[c4 * 4 + 1] = fmaf(f[j], w4.y, lg[c4 * 4 + 1]);
-          lg[c4 * 4 + 2] = fmaf(f[j], w4.z, lg[c4 * 4 + 2]);
-          lg[c4 * 4 + 3] = fmaf(f[j], w4.w, lg[c4 * 4 + 3]);
+    for (int nt = 0; nt < NT; ++nt) {
+      d[nt][0] = d[nt][2] = sbias[nt * 8 + 2 * t];
+      d[nt][1] = d[nt][3] = sbias[nt * 8 + 2 * t + 1];
+    }
+    // A fragments: rows (voxels) v0 / v1, channel pairs (2t, 2t+1) of chunk 2ks and of chunk 2ks+1.  All 4*NKS loads
+    // are issued before the first use so they overlap.
+    uint32_t af[NKS][4];
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const uint32_t* p0 = fw + ((long long)(2 * ks) * a.vox) * 4 + t;
+      const uint32_t* p1 = p0 + a.vox * 4;
+      af[ks][0] = ok0 ? __ldg(p0 + v0 * 4) : 0u;
+      af[ks][1] = ok1 ? __ldg(p0 + v1 * 4) : 0u;
+      af[ks][2] = ok0 ? __ldg(p1 + v0 * 4) : 0u;
+      af[ks][3] = ok1 ? __ldg(p1 + v1 * 4) : 0u;
+    }
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      if (a.partial) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = ks * 16 + (j >> 1) * 8 + 2 * t;
+          const float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&af[ks][j]));
+          float y0 = fmaf(x.x, nsc[c], nsh[c]), y1 = fmaf(x.y, nsc[c + 1], nsh[c + 1]);
+          y0 = y0 > 0.f ? y0 : y0 * a.slope;
+          y1 = y1 > 0.f ? y1 : y1 * a.slope;
+          af[ks][j] = pack_bf16x2(y0, y1);
         }
       }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t* wf = wfrag + ((ks * NT + nt) * 4) * 32 + lane;
+        mma_bf16_16816(d[nt], af[ks], wf[0], wf[32]);
+        mma_bf16_16816(d[nt], af[ks], wf[64], wf[96]);
+      }
     }
-    // DDIM update (x_t given) or plain logits; lg[] is overwritten with x_{t-1} for the re-pack below.
-    // All loads are issued before any store so the 2*C independent 4-byte loads overlap (the state tensors are planar).
-    const long long o0 = (long long)n * a.C * a.vox + v;
+    // d[nt][0..1]: voxel v0, classes nt*8 + 2t, +1 ; d[nt][2..3]: voxel v1, same classes
+    const float img0 = (a.next_in && ok0) ? a.image[(long long)n * a.vox + v0] : 0.f;
+    const float img1 = (a.next_in && ok1) ? a.image[(long long)n * a.vox + v1] : 0.f;
+    float xt[NT][4], ac[NT][4];
     if (a.x_t) {
-      float xt[CP], ac[CP];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) {
-        if (c < a.C) {
-          xt[c] = a.x_t[o0 + c * a.vox];
-          ac[c] = a.acc[o0 + c * a.vox];
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cls = nt * 8 + 2 * t + (j & 1);
+          const long long v = (j >> 1) ? v1 : v0;
+          const bool ok = cls < a.C && ((j >> 1) ? ok1 : ok0);
+          const long long o = ((long long)n * a.C + cls) * a.vox + v;
+          xt[nt][j] = ok ? a.x_t[o] : 0.f;
+          ac[nt][j] = ok ? a.acc[o] : 0.f;
         }
-      }
-#pragma unroll
-      for (int c = 0; c < CP; ++c) {
-        if (c < a.C) {
-          if (a.logits_out) a.logits_out[o0 + c * a.vox] = lg[c];
-          const float x0 = fminf(fmaxf(lg[c], -1.f), 1.f);
-          const float eps = (a.r * xt[c] - x0) / a.m;
-          const float xp = x0 * s_abp + s_1mabp * eps;
-          a.x_t[o0 + c * a.vox] = xp;
-          a.acc[o0 + c * a.vox] = ac[c] + x0;
-          lg[c] = xp;
-        } else {
-          lg[c] = 0.f;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < CP; ++c)
-        if (c < a.C && a.logits_out) a.logits_out[o0 + c * a.vox] = lg[c];
     }
-    if (a.next_in) {
-      // channel order cat([image, x]) (denoiser.py:298): packed channel 0 = image, 1..C = x_{t-1}, rest zero
-      const float img = a.image[(long long)n * a.vox + v];
-      const int chunks = a.in_pad / 8;
-      BF8* np = reinterpret_cast<BF8*>(a.next_in) + (long long)n * chunks * a.vox + v;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < chunks) {
-          float f[8];
+    for (int nt = 0; nt < NT; ++nt) {
+      float nxt[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int ch = k * 8 + j;
-            f[j] = ch == 0 ? img : ((ch - 1) < CP ? lg[(ch - 1) < CP ? (ch - 1) : 0] : 0.f);
+      for (int j = 0; j < 4; ++j) {
+        const int cls = nt * 8 + 2 * t + (j & 1);
+        const long long v = (j >> 1) ? v1 : v0;
+        const bool okv = (j >> 1) ? ok1 : ok0;
+        const long long o = ((long long)n * a.C + cls) * a.vox + v;
+        float val = 0.f;
+        if (cls < a.C && okv) {
+          const float lg = d[nt][j];
+          if (a.logits_out) a.logits_out[o] = lg;
+          if (a.x_t) {
+            const float x0 = fminf(fmaxf(lg, -1.f), 1.f);
+            const float eps = (a.r * xt[nt][j] - x0) / a.m;
+            const float xp = x0 * s_abp + s_1mabp * eps;
+            a.x_t[o] = xp;
+            a.acc[o] = ac[nt][j] + x0;
+            val = xp;
           }
-          np[(long long)k * a.vox] = float_to_bf8(f);
+        } else if (cls == a.C) {
+          val = (j >> 1) ? img1 : img0;
         }
+        nxt[j] = val;
+      }
+      if (a.next_in && nt * 8 < a.in_pad) {
+        uint32_t* np = reinterpret_cast<uint32_t*>(a.next_in) + ((long long)n * (a.in_pad / 8) + nt) * a.vox * 4 + t;
+        if (ok0) np[v0 * 4] = pack_bf16x2(nxt[0], nxt[1]);
+        if (ok1) np[v1 * 4] = pack_bf16x2(nxt[2], nxt[3]);
       }
     }
   }
