@@ -1,5 +1,6 @@
 """Public surface of the B200 Diff-UNet inference package."""
 from ._lib import DunetError, load as load_library
+from .dist import infer_volume_distributed, my_window_range, reduce_partial_volume
 from .inference import StitchBuffers, infer_volume, sliding_window_inference
 from .model import DEFAULT_FEATURES, DiffUNetB200
 from .schedule import DdimSchedule
@@ -15,5 +16,5 @@ def model_hub(model_name: str, **kwargs):
 
 
 __all__ = ["DiffUNetB200", "DEFAULT_FEATURES", "DdimSchedule", "DunetError", "StitchBuffers", "axis_counts",
-           "infer_volume", "load_library", "model_hub", "scan_intervals", "shard_range", "sliding_window_inference",
+           "infer_volume", "infer_volume_distributed", "load_library", "my_window_range", "reduce_partial_volume", "model_hub", "scan_intervals", "shard_range", "sliding_window_inference",
            "window_starts"]

@@ -71,7 +71,7 @@ def crop_windows(volume: torch.Tensor, starts, roi) -> torch.Tensor:
 
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable[..., torch.Tensor],
                              overlap: float = 0.25, mode: str = "constant", window_range: Optional[Tuple[int, int]] = None,
-                             finalize: bool = True, **kwargs):
+                             finalize: bool = True, out_channels: Optional[int] = None, **kwargs):
     """Constant-blend sliding window on the GPU.  ``predictor(window_batch, **kwargs)`` -> [b, C, *roi].
 
     ``window_range=(lo, hi)`` restricts the run to a contiguous shard of the window list (multi-GPU); with
@@ -106,6 +106,10 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
                     buf = StitchBuffers(pred.shape[1], vol, roi, overlap, inputs.device)
                 for j, s in enumerate(grp):
                     buf.add(pred[j], s)
+            if buf is None:  # empty shard (more ranks than windows): contribute zeros to the reduction
+                if out_channels is None:
+                    raise ValueError("empty window range: pass out_channels")
+                buf = StitchBuffers(out_channels, vol, roi, overlap, inputs.device)
             outs.append(buf)
     if not finalize:
         return outs
