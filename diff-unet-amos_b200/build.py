@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdunet_b200.so")
 STAMP = os.path.join(HERE, ".libdunet_b200.stamp")
 SOURCES = ["dunet.cu"]
-HEADERS = ["ptx.cuh", "elementwise.cuh", "conv3d_tc.cuh", "conv3d_ref.cuh", os.path.join("..", "..", "include", "dunet.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "dunet.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

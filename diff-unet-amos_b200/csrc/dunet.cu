@@ -17,6 +17,7 @@
 #include "conv3d_ref.cuh"
 #include "conv3d_tc.cuh"
 #include "conv3d_tc64.cuh"
+#include "deconv2_tc.cuh"
 #include "elementwise.cuh"
 
 using namespace dunet;
@@ -55,11 +56,31 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // ---- optional live profiling of the conv launches (bench.py roofline) ----
-struct ProfRec { cudaEvent_t a, b; };
+struct ProfRec { cudaEvent_t a, b; int tag; };
+enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_TAGS = 8 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;       // event pool, reused across enable() calls
 static size_t g_prof_used = 0;
 static double g_prof_flops = 0.0;
+
+static int prof_begin(int tag, cudaStream_t st) {
+  if (!g_prof_on) return 0;
+  if (g_prof_used == g_prof.size()) {
+    ProfRec rec;
+    CUDA_TRY(cudaEventCreate(&rec.a));
+    CUDA_TRY(cudaEventCreate(&rec.b));
+    g_prof.push_back(rec);
+  }
+  g_prof[g_prof_used].tag = tag;
+  CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].a, st));
+  return 0;
+}
+static int prof_end(cudaStream_t st) {
+  if (!g_prof_on) return 0;
+  CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].b, st));
+  ++g_prof_used;
+  return 0;
+}
 
 static inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 static inline int grid_for(long long total, int threads, int cap = 148 * 16) {
@@ -240,7 +261,7 @@ struct Slot {
 };
 
 struct WsLayout {
-  size_t in_pack, raw, mid, partial, ss, splitk, x_t, total;
+  size_t in_pack, raw, mid, partial, ss, splitk, x_t, acc, total;
   size_t emb[5], epool[5], x[5], dpool[5], up[5], u[5];
 };
 
@@ -343,7 +364,9 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
   L.partial = take(part_max);
   L.ss = take(ss_max);
   L.splitk = take(split_max);
-  L.x_t = take((size_t)B * p->C * p->V[0] * sizeof(float));
+  const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);  // voxel-major DDIM state, classes padded to the MMA column tiles
+  L.x_t = take((size_t)B * CP * p->V[0] * sizeof(float));
+  L.acc = take((size_t)B * CP * p->V[0] * sizeof(float));
   for (int l = 0; l < 5; ++l) {
     L.emb[l] = take(act(p->fp[l], l));
     L.x[l] = take(act(p->fp[l], l));
@@ -369,21 +392,10 @@ static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const Co
     attr_set = true;
   }
   const long long grid = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
-  if (g_prof_on) {
-    if (g_prof_used == g_prof.size()) {
-      ProfRec rec;
-      CUDA_TRY(cudaEventCreate(&rec.a));
-      CUDA_TRY(cudaEventCreate(&rec.b));
-      g_prof.push_back(rec);
-    }
-    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].a, st));
-  }
+  TRY(prof_begin(MODE == MODE_CONV3 ? PROF_CONV : PROF_DECONV, st));
   kern<<<(unsigned)grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, a);
   LAUNCH_CHECK();
-  if (g_prof_on) {
-    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].b, st));
-    ++g_prof_used;
-  }
+  TRY(prof_end(st));
   return 0;
 }
 
@@ -407,21 +419,10 @@ static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const 
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.batch;
   const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
   *grid_out = grid;
-  if (g_prof_on) {
-    if (g_prof_used == g_prof.size()) {
-      ProfRec rec;
-      CUDA_TRY(cudaEventCreate(&rec.a));
-      CUDA_TRY(cudaEventCreate(&rec.b));
-      g_prof.push_back(rec);
-    }
-    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].a, st));
-  }
+  TRY(prof_begin(PROF_CONV, st));
   kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, a);
   LAUNCH_CHECK();
-  if (g_prof_on) {
-    CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].b, st));
-    ++g_prof_used;
-  }
+  TRY(prof_end(st));
   return 0;
 }
 
@@ -482,9 +483,11 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
   TRY(rc);
   if (a.ksplit > 1) {
     const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
+    TRY(prof_begin(PROF_SPLITK, st));
     splitk_reduce_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(
         splitk, a.ksplit, (long long)B * c.coutp * p->V[lvl], out, partial, p->V[lvl], nseg);
     LAUNCH_CHECK();
+    TRY(prof_end(st));
     *nseg_out = nseg;
   } else if (partial) {
     *nseg_out = g.tiles;
@@ -502,14 +505,19 @@ static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, const 
   a.eps = 1e-5f; a.slope = 0.1f;
   // ~4 resident blocks per SM in total, each streaming a long contiguous range of one 8-channel plane (the
   // statistics prologue is paid once per block)
-  const int per_plane = std::max(1, (148 * 4 + planes - 1) / planes);
+  const int per_plane = std::max(1, (148 * 8 + planes - 1) / planes);
+  TRY(prof_begin(PROF_NORM, st));
   if (pooled) {
-    const long long work = p->V[lvl] / 8;
-    norm_act_kernel<true><<<dim3(grid_for(work, NORM_THREADS, per_plane), planes), NORM_THREADS, 0, st>>>(a);
+    const dim3 grid(grid_for(p->V[lvl] / 4, NORM_THREADS, per_plane), planes);
+    if (add) norm_act_pool_kernel<true><<<grid, NORM_THREADS, 0, st>>>(a);
+    else norm_act_pool_kernel<false><<<grid, NORM_THREADS, 0, st>>>(a);
   } else {
-    norm_act_kernel<false><<<dim3(grid_for(p->V[lvl], NORM_THREADS * 4, per_plane), planes), NORM_THREADS, 0, st>>>(a);
+    const dim3 grid(grid_for(p->V[lvl], NORM_THREADS * 4, per_plane), planes);
+    if (add) norm_act_kernel<true><<<grid, NORM_THREADS, 0, st>>>(a);
+    else norm_act_kernel<false><<<grid, NORM_THREADS, 0, st>>>(a);
   }
   LAUNCH_CHECK();
+  TRY(prof_end(st));
   return 0;
 }
 
@@ -546,6 +554,32 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf1
   const int D = p->D[lvl_in], H = p->H[lvl_in], W = p->W[lvl_in];
   CUtensorMap t0;
   TRY(make_act_tmap(&t0, in, B * (d.cinp / 8), D, H, W, 8, 0));
+  if (d.cinp <= 128 && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {  // persistent, HBM-write-bound variant
+    DeconvTcArgs b;
+    memset(&b, 0, sizeof b);
+    b.w = d.packed_tc; b.out = out; b.bias = d.bias; b.chunks_in = d.cinp / 8; b.cout = d.coutp; b.D = D; b.H = H; b.W = W;
+    b.tiles_x = (W + CONV_TX - 1) / CONV_TX; b.tiles_y = (H + CONV_TY - 1) / CONV_TY; b.tiles_z = (D + 1) / 2;
+    b.n_tiles = 8 * d.coutp / 128; b.batch = B; b.dbg = g_conv_dbg;
+    if (!g_num_sms) {
+      int dev = 0;
+      CUDA_TRY(cudaGetDevice(&dev));
+      CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long tiles = (long long)b.tiles_x * b.tiles_y * b.tiles_z * B;
+    const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
+    static bool attr1 = false, attr2 = false;
+    TRY(prof_begin(PROF_DECONV, st));
+    if (d.cinp == 64) {
+      if (!attr1) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<1, 2>::SMEM_BYTES)); attr1 = true; }
+      deconv2_tc_kernel<1, 2><<<grid, CONV_THREADS, DeconvTc<1, 2>::SMEM_BYTES, st>>>(t0, b);
+    } else {
+      if (!attr2) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<2, 2>::SMEM_BYTES)); attr2 = true; }
+      deconv2_tc_kernel<2, 2><<<grid, CONV_THREADS, DeconvTc<2, 2>::SMEM_BYTES, st>>>(t0, b);
+    }
+    LAUNCH_CHECK();
+    TRY(prof_end(st));
+    return 0;
+  }
   ConvTcArgs a;
   memset(&a, 0, sizeof a);
   a.w = d.packed_tc; a.out = out; a.bias = d.bias; a.nb0 = d.cinp / 64; a.nb1 = 0; a.chunks0 = d.cinp / 8; a.chunks1 = 0;
@@ -628,11 +662,13 @@ static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) 
     if (a.F == 64) final_ddim_kernel<NT, 4><<<grid, FINAL_THREADS, 0, st>>>(a);           \
     else final_ddim_kernel<NT, 8><<<grid, FINAL_THREADS, 0, st>>>(a);                     \
   } while (0)
+  TRY(prof_begin(PROF_FINAL, st));
   if (a.C <= 8) DUNET_FINAL(1);
   else if (a.C <= 16) DUNET_FINAL(2);
   else DUNET_FINAL(4);
 #undef DUNET_FINAL
   LAUNCH_CHECK();
+  TRY(prof_end(st));
   return 0;
 }
 
@@ -653,13 +689,29 @@ int dunet_profile_enable(int32_t on) {
 int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_flops) {
   if (!conv_ms || !conv_launches || !conv_flops) return fail(DUNET_E_INVALID, "NULL argument");
   double total = 0.0;
+  uint64_t n = 0;
   for (size_t i = 0; i < g_prof_used; ++i) {
+    if (g_prof[i].tag != PROF_CONV) continue;
     CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
     total += ms;
+    ++n;
   }
-  *conv_ms = total; *conv_launches = g_prof_used; *conv_flops = g_prof_flops;
+  *conv_ms = total; *conv_launches = n; *conv_flops = g_prof_flops;
+  return 0;
+}
+
+int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag) {
+  if (!ms_by_tag || !launches_by_tag) return fail(DUNET_E_INVALID, "NULL argument");
+  for (int i = 0; i < PROF_TAGS; ++i) { ms_by_tag[i] = 0.0; launches_by_tag[i] = 0; }
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
+    ms_by_tag[g_prof[i].tag] += ms;
+    launches_by_tag[g_prof[i].tag] += 1;
+  }
   return 0;
 }
 
@@ -957,26 +1009,36 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const WsLayout L = ws_layout(p, B);
-  const size_t state_bytes = (size_t)B * p->C * p->V[0] * sizeof(float);
-  float* x_t = reinterpret_cast<float*>(ws + L.x_t);
+  const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);
+  float* x_t = reinterpret_cast<float*>(ws + L.x_t);   // voxel-major [B][vox][CP]
+  float* acc = reinterpret_cast<float*>(ws + L.acc);
   if (run_encoder) TRY(encode_impl(p, image, B, ws, L, st));
-  CUDA_TRY(cudaMemcpyAsync(x_t, noise, state_bytes, cudaMemcpyDeviceToDevice, st));
-  CUDA_TRY(cudaMemsetAsync(acc_out, 0, state_bytes, st));
+  const int sgrid = grid_for((long long)B * p->V[0] * (CP / 4), 256, 148 * 8);
+  state_to_vm_kernel<<<sgrid, 256, 0, st>>>(noise, x_t, p->C, CP, p->V[0], B);
+  LAUNCH_CHECK();
+  state_to_vm_kernel<<<sgrid, 256, 0, st>>>(nullptr, acc, p->C, CP, p->V[0], B);
+  LAUNCH_CHECK();
   pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
-      x_t, p->C, image, p->cfg.in_channels, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
+      noise, p->C, image, p->cfg.in_channels, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
   LAUNCH_CHECK();
   for (int i = p->n_steps - 1, k = 0; i >= 0; --i, ++k) {  // gaussian_diffusion.py:694 indices high -> low
     int nseg = 0;
     TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st, &nseg));
     FinalDdimArgs a;
     final_args_common(p, a, ws, L, nseg, B);
-    a.image = image; a.x_t = x_t; a.acc = acc_out;
+    a.image = image; a.x_t = x_t; a.acc = acc;
     a.logits_out = per_step_logits ? per_step_logits + (size_t)k * B * p->C * p->V[0] : nullptr;
     a.next_in = i > 0 ? reinterpret_cast<bf16*>(ws + L.in_pack) : nullptr;
     a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
     TRY(launch_final(p, a, st));
   }
-  if (final_x) CUDA_TRY(cudaMemcpyAsync(final_x, x_t, state_bytes, cudaMemcpyDeviceToDevice, st));
+  const int egrid = sgrid;
+  state_from_vm_kernel<<<egrid, 256, 0, st>>>(acc, acc_out, p->C, CP, p->V[0], B);
+  LAUNCH_CHECK();
+  if (final_x) {
+    state_from_vm_kernel<<<egrid, 256, 0, st>>>(x_t, final_x, p->C, CP, p->V[0], B);
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -1077,7 +1139,7 @@ int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dunet_plan tmp;
   memset(&tmp.cfg, 0, sizeof tmp.cfg);
-  tmp.cfg.flags = use_ref ? DUNET_FLAG_REF_CONV : 0;
+  tmp.cfg.flags = use_ref == 1 ? DUNET_FLAG_REF_CONV : (use_ref == 2 ? DUNET_FLAG_GENERIC_CONV : 0);
   tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
   tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
   DeconvW d;

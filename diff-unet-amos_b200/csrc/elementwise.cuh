@@ -252,82 +252,107 @@ __device__ __forceinline__ void norm_apply(float (&f)[8], const float* sc, const
   }
 }
 
-template <bool POOL>
-__global__ void __launch_bounds__(NORM_THREADS) norm_act_kernel(NormActArgs a) {
+// ADD: the encoder-feature residual is present.  Both variants keep 4 independent 16-byte loads per tensor in flight per
+// thread; __launch_bounds__ asks for 3-4 resident blocks per SM so ~64 KB of loads are outstanding per SM.
+template <bool ADD>
+__global__ void __launch_bounds__(NORM_THREADS, ADD ? 3 : 4) norm_act_kernel(NormActArgs a) {
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;  // n*chunks + chunk
   norm_prologue(a, plane, sc, sh, bi, scratch);
   const long long vox = (long long)a.D * a.H * a.W;
-  const BF8* in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
-  const BF8* add = a.add ? reinterpret_cast<const BF8*>(a.add) + plane * vox : nullptr;
-  BF8* out = reinterpret_cast<BF8*>(a.out) + plane * vox;
-  if constexpr (!POOL) {
-    constexpr int U = 4;  // independent 16-byte loads in flight per thread
-    const long long stride = (long long)gridDim.x * NORM_THREADS;
-    for (long long v0 = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; v0 < vox; v0 += stride * U) {
-      BF8 xin[U], ain[U];
+  const BF8* __restrict__ in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
+  const BF8* __restrict__ add = reinterpret_cast<const BF8*>(a.add) + plane * vox;
+  BF8* __restrict__ out = reinterpret_cast<BF8*>(a.out) + plane * vox;
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * NORM_THREADS;
+  for (long long v0 = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; v0 < vox; v0 += stride * U) {
+    BF8 xin[U], ain[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long v = v0 + u * stride;
-        if (v < vox) {
-          xin[u] = in[v];
-          if (add) ain[u] = add[v];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long v = v0 + u * stride;
-        if (v < vox) {
-          float f[8];
-          bf8_to_float(xin[u], f);
-          norm_apply(f, sc, sh, bi, a.slope);
-          if (add) {
-            float g[8];
-            bf8_to_float(ain[u], g);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += g[j];
-          }
-          out[v] = float_to_bf8(f);
-        }
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < vox) {
+        xin[u] = in[v];
+        if constexpr (ADD) ain[u] = add[v];
       }
     }
-  } else {
-    const int D2 = a.D / 2, H2 = a.H / 2, W2 = a.W / 2;
-    const long long vox2 = (long long)D2 * H2 * W2;
-    BF8* pooled = reinterpret_cast<BF8*>(a.pooled) + plane * vox2;
-    for (long long p = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; p < vox2;
-         p += (long long)gridDim.x * NORM_THREADS) {
-      const int x2 = (int)(p % W2), y2 = (int)((p / W2) % H2), z2 = (int)(p / ((long long)W2 * H2));
-      float m[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < vox) {
+        float f[8];
+        bf8_to_float(xin[u], f);
+        norm_apply(f, sc, sh, bi, a.slope);
+        if constexpr (ADD) {
+          float g[8];
+          bf8_to_float(ain[u], g);
 #pragma unroll
-      for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 2; ++dx) {
-            const long long v = ((long long)(2 * z2 + dz) * a.H + (2 * y2 + dy)) * a.W + (2 * x2 + dx);
-            float f[8];
-            bf8_to_float(in[v], f);
-            norm_apply(f, sc, sh, bi, a.slope);
-            if (add) {
-              float g[8];
-              bf8_to_float(add[v], g);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += g[j];
-            }
-            BF8 o = float_to_bf8(f);
-            out[v] = o;
-            // pool the ROUNDED values so that pooled == maxpool(out) exactly
-            float r[8];
-            bf8_to_float(o, r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], r[j]);
-          }
-      pooled[p] = float_to_bf8(m);
+          for (int j = 0; j < 8; ++j) f[j] += g[j];
+        }
+        out[v] = float_to_bf8(f);
+      }
     }
+  }
+}
+
+// Same pass + the 2x2x2 max-pool of the result (Down, denoiser.py:105-108).  thread = (x, y/2, z/2): it handles the four
+// (dz, dy) voxels at its x (lanes run along x: every load/store instruction covers 512 contiguous bytes) and completes
+// the pool with its x^1 neighbour through a shuffle; the pooled tensor is built from the ROUNDED outputs so that
+// pooled == maxpool(out) exactly.
+template <bool ADD>
+__global__ void __launch_bounds__(NORM_THREADS, 3) norm_act_pool_kernel(NormActArgs a) {
+  __shared__ float sc[8], sh[8], bi[8];
+  __shared__ double scratch[256];
+  const int plane = blockIdx.y;
+  norm_prologue(a, plane, sc, sh, bi, scratch);
+  const long long vox = (long long)a.D * a.H * a.W;
+  const BF8* __restrict__ in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
+  const BF8* __restrict__ add = reinterpret_cast<const BF8*>(a.add) + plane * vox;
+  BF8* __restrict__ out = reinterpret_cast<BF8*>(a.out) + plane * vox;
+  const int D2 = a.D / 2, H2 = a.H / 2, W2 = a.W / 2;
+  BF8* __restrict__ pooled = reinterpret_cast<BF8*>(a.pooled) + plane * ((long long)D2 * H2 * W2);
+  const long long total = (long long)D2 * H2 * a.W;  // even: W is even
+  const int lane = threadIdx.x & 31;
+  for (long long p = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; p - lane < total;
+       p += (long long)gridDim.x * NORM_THREADS) {
+    const bool valid = p < total;
+    const int x = (int)(p % a.W), y2 = (int)((p / a.W) % H2), z2 = (int)(p / ((long long)a.W * H2));
+    BF8 xin[4], ain[4];
+    long long vv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      vv[k] = ((long long)(2 * z2 + (k >> 1)) * a.H + (2 * y2 + (k & 1))) * a.W + x;
+      if (valid) {
+        xin[k] = in[vv[k]];
+        if constexpr (ADD) ain[k] = add[vv[k]];
+      }
+    }
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        bf8_to_float(xin[k], f);
+        norm_apply(f, sc, sh, bi, a.slope);
+        if constexpr (ADD) {
+          float g[8];
+          bf8_to_float(ain[k], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += g[j];
+        }
+        const BF8 o = float_to_bf8(f);
+        out[vv[k]] = o;
+        float r[8];
+        bf8_to_float(o, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], r[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], 1));
+    if (valid && !(x & 1)) pooled[((long long)z2 * H2 + y2) * W2 + (x >> 1)] = float_to_bf8(m);
   }
 }
 
@@ -397,8 +422,8 @@ struct FinalDdimArgs {
   const float* b;             // [C]
   int C;
   const float* image;         // [B][1][vox] fp32 (in_channels = 1)
-  float* x_t;                 // [B][C][vox] fp32, updated in place (nullptr: logits only)
-  float* acc;                 // [B][C][vox] fp32, += clamp(logits)
+  float* x_t;                 // DDIM state, VOXEL-MAJOR fp32 [B][vox][8*NT], updated in place (nullptr: logits only)
+  float* acc;                 // sum of clamped x0, same voxel-major layout, += clamp(logits)
   float* logits_out;          // optional [B][C][vox]
   __nv_bfloat16* next_in;     // optional packed [x_prev, image, 0..] with in_pad channels
   int in_pad;
@@ -427,7 +452,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
   // B fragments of the weights: [k-step][n-tile][hi|lo][b0|b1][lane]
   __shared__ uint32_t wfrag[(FINAL_MAX_F / 16) * NT * 2 * 2 * 32];
   __shared__ float sbias[NT * 8];
-  __shared__ float nsc[FINAL_MAX_F], nsh[FINAL_MAX_F];
+  __shared__ __align__(8) float nsc[FINAL_MAX_F], nsh[FINAL_MAX_F];
   __shared__ double scratch[256];
   constexpr int nks = NKS;
   const int fch = a.F / 8;
@@ -462,30 +487,62 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
   __syncthreads();
 
   const float s_abp = sqrtf(a.abp), s_1mabp = sqrtf(1.f - a.abp - 0.f);
-  const uint32_t* fw = reinterpret_cast<const uint32_t*>(a.feat) + (long long)n * fch * a.vox * 4;  // 4 words per 16 B
-  const int warps = gridDim.x * (FINAL_THREADS / 32);
-  const int warp_id = blockIdx.x * (FINAL_THREADS / 32) + (threadIdx.x >> 5);
-  const long long ngroups = (a.vox + 15) / 16;
-  for (long long grp = warp_id; grp < ngroups; grp += warps) {
-    const long long v0 = grp * 16 + g, v1 = v0 + 8;
-    const bool ok0 = v0 < a.vox, ok1 = v1 < a.vox;
+  // All per-sample bases are formed once (64-bit); inside the loop only 32-bit element offsets are computed.
+  // (voxels per window < 2^26 and every per-sample tensor < 2^31 elements: checked on the host.)
+  const unsigned vox = (unsigned)a.vox;
+  const uint32_t* __restrict__ fw = reinterpret_cast<const uint32_t*>(a.feat) + (size_t)n * fch * vox * 4 + t;
+  const float* __restrict__ img_n = a.image ? a.image + (size_t)n * vox : nullptr;
+  // voxel-major state: a quad of lanes (t = 0..3) covers 8 consecutive classes of one voxel with float2 accesses, so
+  // the 8 voxels x NT*8 classes a warp touches per access form one contiguous run
+  float2* xt_n = a.x_t ? reinterpret_cast<float2*>(a.x_t) + (size_t)n * vox * (NT * 4) + t : nullptr;
+  float2* acc_n = a.acc ? reinterpret_cast<float2*>(a.acc) + (size_t)n * vox * (NT * 4) + t : nullptr;
+  float* lg_n = a.logits_out ? a.logits_out + (size_t)n * a.C * vox : nullptr;
+  uint32_t* np_n = a.next_in ? reinterpret_cast<uint32_t*>(a.next_in) + (size_t)n * (a.in_pad / 8) * vox * 4 + t : nullptr;
+  unsigned cls_off[NT][2];
+  bool cls_ok[NT][2], cls_img[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int cls = nt * 8 + 2 * t + b;
+      cls_ok[nt][b] = cls < a.C;
+      cls_img[nt][b] = cls == a.C;
+      cls_off[nt][b] = (unsigned)cls * vox;
+    }
+  const unsigned warps = gridDim.x * (FINAL_THREADS / 32);
+  const unsigned warp_id = blockIdx.x * (FINAL_THREADS / 32) + (threadIdx.x >> 5);
+  const unsigned ngroups = (vox + 15) / 16;
+  for (unsigned grp = warp_id; grp < ngroups; grp += warps) {
+    const unsigned v0 = grp * 16 + g, v1 = v0 + 8;
+    const bool ok0 = v0 < vox, ok1 = v1 < vox;
+    // ---- issue every load of this group up front: state (independent of the MMAs), image, features
+    float2 xt[NT][2], ac[NT][2];  // [class tile][voxel v0 | v1] = classes (2t, 2t+1)
+    if (xt_n) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        xt[nt][0] = ok0 ? xt_n[v0 * (NT * 4) + nt * 4] : make_float2(0.f, 0.f);
+        xt[nt][1] = ok1 ? xt_n[v1 * (NT * 4) + nt * 4] : make_float2(0.f, 0.f);
+        ac[nt][0] = ok0 ? acc_n[v0 * (NT * 4) + nt * 4] : make_float2(0.f, 0.f);
+        ac[nt][1] = ok1 ? acc_n[v1 * (NT * 4) + nt * 4] : make_float2(0.f, 0.f);
+      }
+    }
+    const float img0 = (np_n && ok0) ? img_n[v0] : 0.f;
+    const float img1 = (np_n && ok1) ? img_n[v1] : 0.f;
+    // A fragments: rows (voxels) v0 / v1, channel pairs (2t, 2t+1) of chunk 2ks and of chunk 2ks+1
+    uint32_t af[NKS][4];
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const unsigned c0 = (2 * ks) * vox, c1 = c0 + vox;
+      af[ks][0] = ok0 ? __ldg(fw + (c0 + v0) * 4) : 0u;
+      af[ks][1] = ok1 ? __ldg(fw + (c0 + v1) * 4) : 0u;
+      af[ks][2] = ok0 ? __ldg(fw + (c1 + v0) * 4) : 0u;
+      af[ks][3] = ok1 ? __ldg(fw + (c1 + v1) * 4) : 0u;
+    }
     float d[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       d[nt][0] = d[nt][2] = sbias[nt * 8 + 2 * t];
       d[nt][1] = d[nt][3] = sbias[nt * 8 + 2 * t + 1];
-    }
-    // A fragments: rows (voxels) v0 / v1, channel pairs (2t, 2t+1) of chunk 2ks and of chunk 2ks+1.  All 4*NKS loads
-    // are issued before the first use so they overlap.
-    uint32_t af[NKS][4];
-#pragma unroll
-    for (int ks = 0; ks < NKS; ++ks) {
-      const uint32_t* p0 = fw + ((long long)(2 * ks) * a.vox) * 4 + t;
-      const uint32_t* p1 = p0 + a.vox * 4;
-      af[ks][0] = ok0 ? __ldg(p0 + v0 * 4) : 0u;
-      af[ks][1] = ok1 ? __ldg(p0 + v1 * 4) : 0u;
-      af[ks][2] = ok0 ? __ldg(p1 + v0 * 4) : 0u;
-      af[ks][3] = ok1 ? __ldg(p1 + v1 * 4) : 0u;
     }
 #pragma unroll
     for (int ks = 0; ks < NKS; ++ks) {
@@ -494,9 +551,10 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
         for (int j = 0; j < 4; ++j) {
           const int c = ks * 16 + (j >> 1) * 8 + 2 * t;
           const float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&af[ks][j]));
-          float y0 = fmaf(x.x, nsc[c], nsh[c]), y1 = fmaf(x.y, nsc[c + 1], nsh[c + 1]);
-          y0 = y0 > 0.f ? y0 : y0 * a.slope;
-          y1 = y1 > 0.f ? y1 : y1 * a.slope;
+          const float2 sc2 = *reinterpret_cast<const float2*>(nsc + c), sh2 = *reinterpret_cast<const float2*>(nsh + c);
+          float y0 = fmaf(x.x, sc2.x, sh2.x), y1 = fmaf(x.y, sc2.y, sh2.y);
+          y0 = fmaxf(y0, y0 * a.slope);  // LeakyReLU with 0 < slope < 1
+          y1 = fmaxf(y1, y1 * a.slope);
           af[ks][j] = pack_bf16x2(y0, y1);
         }
       }
@@ -508,53 +566,77 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
       }
     }
     // d[nt][0..1]: voxel v0, classes nt*8 + 2t, +1 ; d[nt][2..3]: voxel v1, same classes
-    const float img0 = (a.next_in && ok0) ? a.image[(long long)n * a.vox + v0] : 0.f;
-    const float img1 = (a.next_in && ok1) ? a.image[(long long)n * a.vox + v1] : 0.f;
-    float xt[NT][4], ac[NT][4];
-    if (a.x_t) {
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cls = nt * 8 + 2 * t + (j & 1);
-          const long long v = (j >> 1) ? v1 : v0;
-          const bool ok = cls < a.C && ((j >> 1) ? ok1 : ok0);
-          const long long o = ((long long)n * a.C + cls) * a.vox + v;
-          xt[nt][j] = ok ? a.x_t[o] : 0.f;
-          ac[nt][j] = ok ? a.acc[o] : 0.f;
-        }
-    }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       float nxt[4];
+      float xp4[4], ac4[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int cls = nt * 8 + 2 * t + (j & 1);
-        const long long v = (j >> 1) ? v1 : v0;
         const bool okv = (j >> 1) ? ok1 : ok0;
-        const long long o = ((long long)n * a.C + cls) * a.vox + v;
-        float val = 0.f;
-        if (cls < a.C && okv) {
+        const float xin = (j & 1) ? xt[nt][j >> 1].y : xt[nt][j >> 1].x;
+        const float ain = (j & 1) ? ac[nt][j >> 1].y : ac[nt][j >> 1].x;
+        float val = cls_img[nt][j & 1] ? ((j >> 1) ? img1 : img0) : 0.f;
+        xp4[j] = 0.f;
+        ac4[j] = 0.f;
+        if (cls_ok[nt][j & 1] && okv) {
           const float lg = d[nt][j];
-          if (a.logits_out) a.logits_out[o] = lg;
-          if (a.x_t) {
+          if (lg_n) lg_n[cls_off[nt][j & 1] + ((j >> 1) ? v1 : v0)] = lg;
+          if (xt_n) {
             const float x0 = fminf(fmaxf(lg, -1.f), 1.f);
-            const float eps = (a.r * xt[nt][j] - x0) / a.m;
+            const float eps = (a.r * xin - x0) / a.m;
             const float xp = x0 * s_abp + s_1mabp * eps;
-            a.x_t[o] = xp;
-            a.acc[o] = ac[nt][j] + x0;
+            xp4[j] = xp;
+            ac4[j] = ain + x0;
             val = xp;
           }
-        } else if (cls == a.C) {
-          val = (j >> 1) ? img1 : img0;
         }
         nxt[j] = val;
       }
-      if (a.next_in && nt * 8 < a.in_pad) {
-        uint32_t* np = reinterpret_cast<uint32_t*>(a.next_in) + ((long long)n * (a.in_pad / 8) + nt) * a.vox * 4 + t;
-        if (ok0) np[v0 * 4] = pack_bf16x2(nxt[0], nxt[1]);
-        if (ok1) np[v1 * 4] = pack_bf16x2(nxt[2], nxt[3]);
+      if (xt_n) {
+        if (ok0) { xt_n[v0 * (NT * 4) + nt * 4] = make_float2(xp4[0], xp4[1]); acc_n[v0 * (NT * 4) + nt * 4] = make_float2(ac4[0], ac4[1]); }
+        if (ok1) { xt_n[v1 * (NT * 4) + nt * 4] = make_float2(xp4[2], xp4[3]); acc_n[v1 * (NT * 4) + nt * 4] = make_float2(ac4[2], ac4[3]); }
       }
+      if (np_n && nt * 8 < a.in_pad) {
+        if (ok0) np_n[(nt * vox + v0) * 4] = pack_bf16x2(nxt[0], nxt[1]);
+        if (ok1) np_n[(nt * vox + v1) * 4] = pack_bf16x2(nxt[2], nxt[3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// DDIM state layout conversion: planar fp32 [B][C][vox] (the reference's NCDHW) <-> voxel-major fp32 [B][vox][CP].
+// to_vm: dst_vm = src (or 0 when src == nullptr);  from_vm: dst planar = src_vm.   thread = (voxel, 4 classes)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void state_to_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch) {
+  const int q4 = CP / 4;
+  const long long total = (long long)batch * vox * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int qd = (int)(i % q4);
+    const long long v = (i / q4) % vox;
+    const int n = (int)(i / (q4 * vox));
+    float f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = qd * 4 + j;
+      f[j] = (src && c < C) ? src[((long long)n * C + c) * vox + v] : 0.f;
+    }
+    reinterpret_cast<float4*>(dst)[i] = make_float4(f[0], f[1], f[2], f[3]);
+  }
+}
+__global__ void state_from_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch) {
+  const int q4 = CP / 4;
+  const long long total = (long long)batch * vox * q4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int qd = (int)(i % q4);
+    const long long v = (i / q4) % vox;
+    const int n = (int)(i / (q4 * vox));
+    const float4 f4 = reinterpret_cast<const float4*>(src)[i];
+    const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = qd * 4 + j;
+      if (c < C) dst[((long long)n * C + c) * vox + v] = f[j];
     }
   }
 }

@@ -67,7 +67,8 @@ def test_conv_zero_padding_is_exact():
 
 
 @pytest.mark.parametrize("cin,cout,B,dims", [(64, 64, 1, (8, 16, 8)), (128, 64, 2, (6, 6, 6)), (512, 256, 1, (2, 2, 2)),
-                                             (256, 128, 1, (12, 12, 12)), (16, 8, 1, (8, 8, 8))])
+                                             (256, 128, 1, (12, 12, 12)), (16, 8, 1, (8, 8, 8)), (64, 64, 3, (24, 40, 24)),
+                                             (128, 128, 1, (7, 9, 5))])
 def test_deconv2x2x2_tensor_core_vs_fp64(cin, cout, B, dims):
     """tcgen05 transposed conv (GEMM + scatter epilogue + bias) == conv_transpose3d of the bf16-rounded operands."""
     torch.manual_seed(cin + cout)
@@ -75,11 +76,12 @@ def test_deconv2x2x2_tensor_core_vs_fp64(cin, cout, B, dims):
     w = torch.randn(cin, cout, 2, 2, 2, device="cuda") / cin ** 0.5
     b = torch.randn(cout, device="cuda")
     exp = F.conv_transpose3d(_bf(x).double(), _bf(w).double(), b.double(), stride=2).float()
-    out = torch.empty_like(exp)
-    _lib.check(_lib.load().dunet_op_deconv2x2x2(_p(x), cin, _p(w), _p(b), cout, _p(out), B, _lib.i32x3(dims), 0,
-                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-    torch.cuda.synchronize()
-    assert rel_l2(out, exp) < 4e-3
+    for kernel in (0, 2):  # 0: production dispatch (persistent kernel for Cin <= 128), 2: generic tcgen05 kernel
+        out = torch.zeros_like(exp)
+        _lib.check(_lib.load().dunet_op_deconv2x2x2(_p(x), cin, _p(w), _p(b), cout, _p(out), B, _lib.i32x3(dims), kernel,
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        assert rel_l2(out, exp) < 4e-3
 
 
 def _build(cout, S, feats, **kw):

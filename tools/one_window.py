@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--S", type=int, default=96)
 ap.add_argument("--C", type=int, default=16)
 ap.add_argument("--ddim", type=int, default=10)
+ap.add_argument("--prof", action="store_true")
 a = ap.parse_args()
 torch.manual_seed(0)
 m = pkg.DiffUNetB200(in_channels=1, out_channels=a.C, image_size=a.S, spatial_size=a.S, batch_max=a.batch, num_steps=a.ddim).cuda().eval()
@@ -33,5 +34,22 @@ with torch.no_grad():
     torch.cuda.synchronize()
     t1 = time.perf_counter()
 ms = e0.elapsed_time(e1) / a.reps
+if a.prof:
+    import ctypes
+    from diff_unet_amos_b200 import _lib
+    lib = _lib.load()
+    lib.dunet_profile_enable(1)
+    with torch.no_grad():
+        m(image=image, pred_type="ddim_sample", noise=noise)
+    torch.cuda.synchronize()
+    msb = (ctypes.c_double * 8)(); cnt = (ctypes.c_uint64 * 8)()
+    _lib.check(lib.dunet_profile_read_all(msb, cnt))
+    lib.dunet_profile_enable(0)
+    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "other"]
+    tot = sum(msb)
+    print("in-situ CUDA-event time per kernel family (one call, batch %d):" % a.batch)
+    for i, nme in enumerate(names):
+        print(f"  {nme:14s} {msb[i]:8.3f} ms  {100 * msb[i] / tot:5.1f}%  launches {cnt[i]}")
+    print(f"  sum {tot:.3f} ms")
 print(f"window batch {a.batch}: {ms:.2f} ms per call ({ms / a.batch:.2f} ms/window, {1e3 * a.batch / ms:.1f} patches/s), "
       f"host wall {1e3 * (t1 - t0) / a.reps:.2f} ms, out range [{out.min().item():.2f}, {out.max().item():.2f}]")
