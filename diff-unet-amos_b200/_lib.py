@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(HERE, "libdunet_b200.so")
 
 DUNET_FLAG_REF_CONV = 1
 DUNET_FLAG_KEEP_FP32_WEIGHTS = 2
+DUNET_FLAG_GENERIC_CONV = 4
+DUNET_FLAG_DUAL_STREAM = 8
 
 
 class DunetCfg(ctypes.Structure):

@@ -50,6 +50,19 @@ struct ConvTc64Args {
   int tiles_x, tiles_y, tiles_z, batch;
 };
 
+// Static tile schedule.  Within EACH sample the tiles are dealt round-robin over the CTAs, so the set of tiles whose
+// InstanceNorm partial sums share a row is a residue class modulo gridDim.x -- independent of how many samples are
+// batched (a window's result is bit-identical whatever it is batched with).  The residue a CTA serves is rotated from
+// sample to sample so the CTAs with one tile more are different ones each time.
+template <class F>
+__device__ __forceinline__ void for_each_tile(int tiles_per_n, int batch, F&& f) {
+  const int G = gridDim.x, shift = tiles_per_n % G;
+  for (int n = 0; n < batch; ++n) {
+    const int r = (int)((blockIdx.x + (long long)G * batch - (long long)n * shift) % G);
+    for (int lin = r; lin < tiles_per_n; lin += G) f(n, lin);
+  }
+}
+
 template <int CB_CH, int ZT>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, ConvTc64Args a) {
@@ -70,7 +83,6 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncb = a.nb0 + a.nb1;
   const int tiles_per_n = a.tiles_x * a.tiles_y * a.tiles_z;
-  const int total_tiles = tiles_per_n * a.batch;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
@@ -96,12 +108,11 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     // =============================== halo-plane producer (TMA), runs ahead across tiles ===============================
     if (elect_one_sync()) {
       int u = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
+      for_each_tile(tiles_per_n, a.batch, [&](int n, int lin) {
+        int t = lin;
         const int tix = t % a.tiles_x; t /= a.tiles_x;
         const int tiy = t % a.tiles_y; t /= a.tiles_y;
-        const int tiz = t % a.tiles_z; t /= a.tiles_z;
-        const int n = t;
+        const int tiz = t;
         const int x0 = tix * CONV_TX, y0 = tiy * CONV_TY, z0 = tiz * ZT;
         for (int cb = 0; cb < ncb; ++cb) {
           const bool second = cb >= a.nb0;
@@ -114,13 +125,13 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             tma_load_4d(a_smem + slot * Cfg::PLANE_BYTES, tm, a_full + 8 * slot, (x0 - 1) * 8, y0 - 1, z0 + p - 1, c3);
           }
         }
-      }
+      });
     }
   } else if (warp == 1) {
     // =============================== weight-tile producer (bulk copy) ===============================
     if (elect_one_sync()) {
       int w = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for_each_tile(tiles_per_n, a.batch, [&](int, int) {
         for (int i = 0; i < ncb * 9; ++i, ++w) {
           const int slot = w % Cfg::W_SLOTS, it = w / Cfg::W_SLOTS;
           if (it > 0) mbar_wait(w_empty + 8 * slot, (it - 1) & 1);
@@ -129,7 +140,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                        reinterpret_cast<const uint8_t*>(a.w) + (size_t)i * Cfg::W_UNIT_BYTES, Cfg::W_UNIT_BYTES,
                        w_full + 8 * slot);
         }
-      }
+      });
     }
   } else if (warp == 2) {
     // =============================== MMA issuer (one thread) ===============================
@@ -137,7 +148,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       const uint64_t a_desc0 = make_smem_desc(a_smem, Cfg::A_LBO, Cfg::A_SBO);
       const uint64_t b_desc0 = make_smem_desc(w_smem, Cfg::B_LBO, Cfg::B_SBO);
       int u0 = 0, w = 0, li = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
+      for_each_tile(tiles_per_n, a.batch, [&](int, int) {
         const int buf = li & 1, use = li >> 1;
         if (use > 0) { mbar_wait(acc_empty + 8 * buf, (use - 1) & 1); tc_fence_after(); }
         const uint32_t acc = tmem_base + buf * Cfg::ACC_COLS;
@@ -185,7 +196,8 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
           }
         }
         umma_commit(acc_full + 8 * buf);
-      }
+        ++li;
+      });
     }
   } else {
     // =============================== epilogue: TMEM -> bf16 -> HBM (+ IN statistics) ===============================
@@ -196,7 +208,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     // of column j*16 + (l & 15) over this warp's rows of all tiles of the current sample; one row [16] per
     // (sample, chunk, CTA) is written when the sample changes / at the end  ->  nseg = gridDim.x, fixed order.
     float run[4] = {0.f, 0.f, 0.f, 0.f};
-    int cur_n = -1;
+    int cur_n = 0;
     auto flush = [&](int n_flush) {
       // combine the four warps in a fixed order and write this CTA's row for sample n_flush
 #pragma unroll
@@ -211,16 +223,13 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       for (int j = 0; j < 4; ++j) run[j] = 0.f;
     };
     int li = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++li) {
-      int t = tile;
+    for_each_tile(tiles_per_n, a.batch, [&](int n, int lin) {
+      int t = lin;
       const int tix = t % a.tiles_x; t /= a.tiles_x;
       const int tiy = t % a.tiles_y; t /= a.tiles_y;
-      const int tiz = t % a.tiles_z; t /= a.tiles_z;
-      const int n = t;
-      if (a.stats && n != cur_n) {
-        // samples this CTA skipped entirely still need a (zero) row
-        for (int m = cur_n < 0 ? 0 : cur_n; m < n; ++m) flush(m);
-        cur_n = n;
+      const int tiz = t;
+      if (a.stats) {
+        for (; cur_n < n; ++cur_n) flush(cur_n);  // rows of finished (or skipped) samples
       }
       const int x = tix * CONV_TX + (r & 7), y = tiy * CONV_TY + (r >> 3), z0 = tiz * ZT;
       const bool xy_ok = x < a.W && y < a.H;
@@ -263,9 +272,10 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
-    }
+      ++li;
+    });
     if (a.stats) {
-      for (int m = cur_n < 0 ? 0 : cur_n; m < a.batch; ++m) flush(m);
+      for (; cur_n < a.batch; ++cur_n) flush(cur_n);
     }
   }
   __syncthreads();

@@ -288,6 +288,10 @@ struct dunet_plan {
   int temb_row = 0, temb_off[9];
   bool committed = false;
   std::vector<void*> owned;
+  // two internal streams: the two halves of a window batch run out of phase so that the HBM-bound kernels of one half
+  // (normalise, final/DDIM, transposed conv) overlap the tensor-core-bound convolutions of the other
+  cudaStream_t half_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 static int dev_alloc(dunet_plan* p, void** out, size_t bytes) {
@@ -353,7 +357,7 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
     raw_max = std::max(raw_max, act(c.coutp, lvl));
     const ConvGeom g = conv_geom(p, c, lvl, B);
     const size_t planes = (size_t)B * (c.coutp / 8);
-    part_max = std::max(part_max, planes * std::max(g.tiles, 128) * 16 * sizeof(float));
+    part_max = std::max(part_max, planes * std::max(g.tiles, 160) * 16 * sizeof(float));  // rows: tiles, reduction segments (<= 128) or persistent CTAs (<= #SMs)
     ss_max = std::max(ss_max, planes * 16 * sizeof(float));
     if (g.ksplit > 1) split_max = std::max(split_max, (size_t)g.ksplit * B * c.coutp * (size_t)p->V[lvl] * sizeof(float));
   };
@@ -809,6 +813,11 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
 void dunet_plan_destroy(dunet_plan* p) {
   if (!p) return;
   for (void* q : p->owned) cudaFree(q);
+  for (int i = 0; i < 2; ++i) {
+    if (p->half_stream[i]) cudaStreamDestroy(p->half_stream[i]);
+    if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   delete p;
 }
 
@@ -943,7 +952,9 @@ int dunet_plan_commit(dunet_plan* p, void* stream) {
 int dunet_workspace_bytes(const dunet_plan* p, int32_t batch, size_t* out) {
   if (!p || !out) return fail(DUNET_E_INVALID, "NULL argument");
   if (batch < 1 || batch > p->cfg.batch_max) return fail(DUNET_E_INVALID, "batch %d outside [1, %d]", batch, p->cfg.batch_max);
-  *out = ws_layout(p, batch).total;
+  const size_t single = ws_layout(p, batch).total;
+  const size_t halves = batch >= 2 ? 2 * ws_layout(p, (batch + 1) / 2).total : 0;
+  *out = std::max(single, halves);
   return 0;
 }
 
@@ -1001,13 +1012,10 @@ int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int3
   return launch_final(p, a, st);
 }
 
-int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
-                      float* final_x, int32_t B, int32_t run_encoder, void* workspace, void* stream) {
-  TRY(check_call(p, B, workspace));
-  if (!image || !noise || !acc_out) return fail(DUNET_E_INVALID, "NULL tensor argument");
-  if (!aligned16(image) || !aligned16(noise) || !aligned16(acc_out)) return fail(DUNET_E_INVALID, "tensors must be 16-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
+// one batch (or half batch) of windows on one stream, workspace laid out for exactly B windows.
+// per_step_stride = elements between consecutive steps in per_step_logits (the FULL batch size when halves are used).
+static int ddim_sample_impl(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
+                            size_t per_step_stride, float* final_x, int B, int run_encoder, uint8_t* ws, cudaStream_t st) {
   const WsLayout L = ws_layout(p, B);
   const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);
   float* x_t = reinterpret_cast<float*>(ws + L.x_t);   // voxel-major [B][vox][CP]
@@ -1027,18 +1035,52 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
     FinalDdimArgs a;
     final_args_common(p, a, ws, L, nseg, B);
     a.image = image; a.x_t = x_t; a.acc = acc;
-    a.logits_out = per_step_logits ? per_step_logits + (size_t)k * B * p->C * p->V[0] : nullptr;
+    a.logits_out = per_step_logits ? per_step_logits + (size_t)k * per_step_stride : nullptr;
     a.next_in = i > 0 ? reinterpret_cast<bf16*>(ws + L.in_pack) : nullptr;
     a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
     TRY(launch_final(p, a, st));
   }
-  const int egrid = sgrid;
-  state_from_vm_kernel<<<egrid, 256, 0, st>>>(acc, acc_out, p->C, CP, p->V[0], B);
+  state_from_vm_kernel<<<sgrid, 256, 0, st>>>(acc, acc_out, p->C, CP, p->V[0], B);
   LAUNCH_CHECK();
   if (final_x) {
-    state_from_vm_kernel<<<egrid, 256, 0, st>>>(x_t, final_x, p->C, CP, p->V[0], B);
+    state_from_vm_kernel<<<sgrid, 256, 0, st>>>(x_t, final_x, p->C, CP, p->V[0], B);
     LAUNCH_CHECK();
   }
+  return 0;
+}
+
+int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
+                      float* final_x, int32_t B, int32_t run_encoder, void* workspace, void* stream) {
+  TRY(check_call(p, B, workspace));
+  if (!image || !noise || !acc_out) return fail(DUNET_E_INVALID, "NULL tensor argument");
+  if (!aligned16(image) || !aligned16(noise) || !aligned16(acc_out)) return fail(DUNET_E_INVALID, "tensors must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const size_t per_step_stride = (size_t)B * p->C * p->V[0];
+  const bool dual = B >= 2 && run_encoder && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on;
+  if (!dual)
+    return ddim_sample_impl(p, image, noise, acc_out, per_step_logits, per_step_stride, final_x, B, run_encoder, ws, st);
+  // ---- two half batches on two internal streams (fork from / join into the caller's stream; no host synchronisation)
+  if (!p->half_stream[0]) {
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&p->half_stream[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  }
+  const int B0 = (B + 1) / 2;
+  const size_t half_ws = ws_layout(p, B0).total;
+  CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+  for (int h = 0; h < 2; ++h) {
+    const int b0 = h * B0, nb = h ? B - B0 : B0;
+    const size_t img_off = (size_t)b0 * p->cfg.in_channels * p->V[0], st_off = (size_t)b0 * p->C * p->V[0];
+    CUDA_TRY(cudaStreamWaitEvent(p->half_stream[h], p->ev_fork, 0));
+    TRY(ddim_sample_impl(p, image + img_off, noise + st_off, acc_out + st_off, per_step_logits ? per_step_logits + st_off : nullptr,
+                         per_step_stride, final_x ? final_x + st_off : nullptr, nb, run_encoder, ws + h * half_ws,
+                         p->half_stream[h]));
+    CUDA_TRY(cudaEventRecord(p->ev_join[h], p->half_stream[h]));
+  }
+  for (int h = 0; h < 2; ++h) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[h], 0));
   return 0;
 }
 

@@ -41,6 +41,10 @@ enum {
 
 #define DUNET_FLAG_GENERIC_CONV 4u /* debug: route Cout = 64 convs through the generic tcgen05 kernel (no z-stacking) */
 
+#define DUNET_FLAG_DUAL_STREAM 8u /* experimental: run the two halves of a window batch on two internal streams (measured:
+                                    +3 % at batch 4, large loss at batch 2 -- the persistent conv kernels use a static tile
+                                    schedule and do not share SMs gracefully; off by default) */
+
 typedef struct dunet_plan dunet_plan;
 
 /* Mirrors DiffUNet.__init__(spatial_dims=3, in_channels, out_channels, image_size, spatial_size, features, ...)

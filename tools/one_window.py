@@ -17,9 +17,10 @@ ap.add_argument("--S", type=int, default=96)
 ap.add_argument("--C", type=int, default=16)
 ap.add_argument("--ddim", type=int, default=10)
 ap.add_argument("--prof", action="store_true")
+ap.add_argument("--flags", type=int, default=0)
 a = ap.parse_args()
 torch.manual_seed(0)
-m = pkg.DiffUNetB200(in_channels=1, out_channels=a.C, image_size=a.S, spatial_size=a.S, batch_max=a.batch, num_steps=a.ddim).cuda().eval()
+m = pkg.DiffUNetB200(in_channels=1, out_channels=a.C, image_size=a.S, spatial_size=a.S, batch_max=a.batch, num_steps=a.ddim, debug_flags=a.flags).cuda().eval()
 image = torch.rand(a.batch, 1, a.S, a.S, a.S, device="cuda")
 noise = torch.randn(a.batch, a.C, a.S, a.S, a.S, device="cuda")
 with torch.no_grad():
