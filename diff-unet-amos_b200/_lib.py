@@ -50,7 +50,7 @@ SIGNATURES = {
     "dunet_get_embedding": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "dunet_set_embedding": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "dunet_denoise_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
-    "dunet_ddim_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "dunet_ddim_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32, c_void_p, c_void_p]),
     "dunet_crop_window": (c_int32, [c_void_p, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "dunet_stitch_add": (c_int32, [c_void_p, POINTER(c_int32), c_int32, c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "dunet_finalize": (c_int32, [c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -1015,7 +1015,8 @@ int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int3
 // one batch (or half batch) of windows on one stream, workspace laid out for exactly B windows.
 // per_step_stride = elements between consecutive steps in per_step_logits (the FULL batch size when halves are used).
 static int ddim_sample_impl(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
-                            size_t per_step_stride, float* final_x, int B, int run_encoder, uint8_t* ws, cudaStream_t st) {
+                            size_t per_step_stride, float* final_x, int B, int run_encoder, float out_scale, int out_accumulate,
+                            uint8_t* ws, cudaStream_t st) {
   const WsLayout L = ws_layout(p, B);
   const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);
   float* x_t = reinterpret_cast<float*>(ws + L.x_t);   // voxel-major [B][vox][CP]
@@ -1040,17 +1041,18 @@ static int ddim_sample_impl(dunet_plan* p, const float* image, const float* nois
     a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
     TRY(launch_final(p, a, st));
   }
-  state_from_vm_kernel<<<sgrid, 256, 0, st>>>(acc, acc_out, p->C, CP, p->V[0], B);
+  state_from_vm_kernel<<<sgrid, 256, 0, st>>>(acc, acc_out, p->C, CP, p->V[0], B, out_scale, out_accumulate);
   LAUNCH_CHECK();
   if (final_x) {
-    state_from_vm_kernel<<<sgrid, 256, 0, st>>>(x_t, final_x, p->C, CP, p->V[0], B);
+    state_from_vm_kernel<<<sgrid, 256, 0, st>>>(x_t, final_x, p->C, CP, p->V[0], B, 1.f, 0);
     LAUNCH_CHECK();
   }
   return 0;
 }
 
 int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
-                      float* final_x, int32_t B, int32_t run_encoder, void* workspace, void* stream) {
+                      float* final_x, int32_t B, int32_t run_encoder, float out_scale, int32_t out_accumulate, void* workspace,
+                      void* stream) {
   TRY(check_call(p, B, workspace));
   if (!image || !noise || !acc_out) return fail(DUNET_E_INVALID, "NULL tensor argument");
   if (!aligned16(image) || !aligned16(noise) || !aligned16(acc_out)) return fail(DUNET_E_INVALID, "tensors must be 16-byte aligned");
@@ -1059,7 +1061,8 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   const size_t per_step_stride = (size_t)B * p->C * p->V[0];
   const bool dual = B >= 2 && run_encoder && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on;
   if (!dual)
-    return ddim_sample_impl(p, image, noise, acc_out, per_step_logits, per_step_stride, final_x, B, run_encoder, ws, st);
+    return ddim_sample_impl(p, image, noise, acc_out, per_step_logits, per_step_stride, final_x, B, run_encoder, out_scale,
+                            out_accumulate, ws, st);
   // ---- two half batches on two internal streams (fork from / join into the caller's stream; no host synchronisation)
   if (!p->half_stream[0]) {
     for (int i = 0; i < 2; ++i) {
@@ -1076,8 +1079,8 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
     const size_t img_off = (size_t)b0 * p->cfg.in_channels * p->V[0], st_off = (size_t)b0 * p->C * p->V[0];
     CUDA_TRY(cudaStreamWaitEvent(p->half_stream[h], p->ev_fork, 0));
     TRY(ddim_sample_impl(p, image + img_off, noise + st_off, acc_out + st_off, per_step_logits ? per_step_logits + st_off : nullptr,
-                         per_step_stride, final_x ? final_x + st_off : nullptr, nb, run_encoder, ws + h * half_ws,
-                         p->half_stream[h]));
+                         per_step_stride, final_x ? final_x + st_off : nullptr, nb, run_encoder, out_scale, out_accumulate,
+                         ws + h * half_ws, p->half_stream[h]));
     CUDA_TRY(cudaEventRecord(p->ev_join[h], p->half_stream[h]));
   }
   for (int h = 0; h < 2; ++h) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[h], 0));

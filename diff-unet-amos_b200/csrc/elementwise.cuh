@@ -624,7 +624,9 @@ __global__ void state_to_vm_kernel(const float* __restrict__ src, float* __restr
     reinterpret_cast<float4*>(dst)[i] = make_float4(f[0], f[1], f[2], f[3]);
   }
 }
-__global__ void state_from_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch) {
+// dst = (accumulate ? dst : 0) + scale * src   (ensemble averaging over independent noise draws)
+__global__ void state_from_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch,
+                                     float scale, int accumulate) {
   const int q4 = CP / 4;
   const long long total = (long long)batch * vox * q4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -636,7 +638,10 @@ __global__ void state_from_vm_kernel(const float* __restrict__ src, float* __res
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = qd * 4 + j;
-      if (c < C) dst[((long long)n * C + c) * vox + v] = f[j];
+      if (c < C) {
+        float* o = dst + ((long long)n * C + c) * vox + v;
+        *o = accumulate ? fmaf(scale, f[j], *o) : scale * f[j];
+      }
     }
   }
 }

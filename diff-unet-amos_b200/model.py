@@ -384,24 +384,27 @@ class DiffUNetB200(nn.Module):
         rt.emb_token = token
         self._emb_keepalive = list(embeddings)  # ids in the token stay unique while these are alive
 
-    def _run_ddim(self, image, noise, run_encoder=True, want_steps=False, want_final=True):
+    def _run_ddim(self, image, noise, run_encoder=True, want_steps=False, want_final=True, acc=None, scale=1.0,
+                  accumulate=False):
         rt = self._rt
         B = image.shape[0]
         plan = rt.ensure(image.device)
         ws = rt.workspace(B)
-        acc = torch.empty_like(noise)
+        if acc is None:
+            acc = torch.empty_like(noise)
         per = torch.empty((self.num_steps,) + tuple(noise.shape), dtype=torch.float32, device=noise.device) if want_steps else None
         fin = torch.empty_like(noise) if want_final else None
         with torch.cuda.device(image.device):
             _lib.check(_lib.load().dunet_ddim_sample(plan, _ptr(image), _ptr(noise), _ptr(acc), _ptr(per), _ptr(fin), B,
-                                                     1 if run_encoder else 0, _ptr(ws), _stream()))
+                                                     1 if run_encoder else 0, ctypes.c_float(scale), 1 if accumulate else 0,
+                                                     _ptr(ws), _stream()))
         if run_encoder:
             rt.emb_token = None
         return {"acc": acc, "per_step": per, "final_x": fin}
 
     # ---- the reference's Diffusion.forward dispatch (models/diffusion/diffusion.py:49-63) ------------------------
     def forward(self, image: torch.Tensor = None, x: torch.Tensor = None, step: torch.Tensor = None,
-                pred_type: str = None, noise: torch.Tensor = None):
+                pred_type: str = None, noise: torch.Tensor = None, ensemble: int = 1):
         if image is not None and x is not None:
             assert image.device == x.device
         if pred_type == "q_sample":
@@ -409,7 +412,7 @@ class DiffUNetB200(nn.Module):
         elif pred_type == "denoise":
             return self.denoise(image, x, step)
         elif pred_type == "ddim_sample":
-            return self.ddim_sample(image, noise=noise)
+            return self.ddim_sample(image, noise=noise, ensemble=ensemble)
         raise NotImplementedError(f"No such prediction type : {pred_type}")
 
     def q_sample(self, x):
@@ -422,16 +425,25 @@ class DiffUNetB200(nn.Module):
         embeddings = self.embed_model(image)
         return self.model(x=x, t=step, embeddings=embeddings, image=image)
 
-    def ddim_sample(self, image: torch.Tensor, noise: torch.Tensor = None) -> torch.Tensor:
+    def ddim_sample(self, image: torch.Tensor, noise: torch.Tensor = None, ensemble: int = 1) -> torch.Tensor:
         """Sum over the N DDIM steps of the clamped x0 prediction for every window of the batch
-        (models/diffusion/diffusion.py:86-102).  ``noise`` ([B, C, *patch]) replaces the reference's internal
-        ``randn`` draws so runs can be compared on identical noise."""
+        (models/diffusion/diffusion.py:86-102).  ``noise`` ([B, C, *patch], or [R, B, C, *patch] with ``ensemble=R``)
+        replaces the reference's internal ``randn`` draws so runs can be compared on identical noise.
+        ``ensemble=R`` (BASELINE config 4; not in the reference) averages the summed outputs of R independent noise
+        draws; the encoder runs once."""
         image = _f32c(image, "image")
         self._check_image(image)
         B = image.shape[0]
+        shape = (B, self.num_classes) + self.patch
         if noise is None:
-            noise = torch.randn((B, self.num_classes) + self.patch, device=image.device)
+            noise = torch.randn((ensemble,) + shape, device=image.device)
         noise = _f32c(noise, "noise")
-        if tuple(noise.shape) != (B, self.num_classes) + self.patch:
-            raise ValueError(f"noise must be {(B, self.num_classes) + self.patch}, got {tuple(noise.shape)}")
-        return self._run_ddim(image, noise, run_encoder=True, want_final=False)["acc"]
+        if noise.dim() == 5:
+            noise = noise.unsqueeze(0)
+        if tuple(noise.shape) != (ensemble,) + shape:
+            raise ValueError(f"noise must be {(ensemble,) + shape} (or {shape} when ensemble == 1), got {tuple(noise.shape)}")
+        acc = torch.empty(shape, dtype=torch.float32, device=image.device)
+        for r in range(ensemble):
+            self._run_ddim(image, noise[r], run_encoder=(r == 0), want_final=False, acc=acc, scale=1.0 / ensemble,
+                           accumulate=(r > 0))
+        return acc

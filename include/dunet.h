@@ -106,9 +106,12 @@ int dunet_denoise_step(dunet_plan* plan, const float* x_t, const float* image, i
  * sum_k clamp(model_output_k, -1, 1); per_step_logits (nullable): [n_steps, batch, C, D, H, W] raw model outputs in
  * loop order (t high -> low); final_x (nullable): the last sample.  run_encoder == 0 skips the encoder and uses the
  * embeddings already in the workspace (the reference's ddim_sample_loop(model, shape, model_kwargs={image, embeddings})
- * seam, gaussian_diffusion.py:626-665). */
+ * seam, gaussian_diffusion.py:626-665).  Ensemble averaging over R independent noise draws (BASELINE config 4): call R times
+ * with out_scale = 1/R, out_accumulate = 0 for the first draw and 1 afterwards (acc_out = [acc_out +] out_scale * sum_k x0_k);
+ * the reference itself corresponds to out_scale = 1, out_accumulate = 0. */
 int dunet_ddim_sample(dunet_plan* plan, const float* image, const float* noise, float* acc_out, float* per_step_logits,
-                      float* final_x, int32_t batch, int32_t run_encoder, void* workspace, void* stream);
+                      float* final_x, int32_t batch, int32_t run_encoder, float out_scale, int32_t out_accumulate,
+                      void* workspace, void* stream);
 
 /* replaces: the body of monai.inferers.sliding_window_inference as called at engine.py:173-177 (constant blend):
  * window crop, `out[slices] += pred`, `out /= count`, and Engine.infer's sigmoid+threshold (engine.py:179-180). */

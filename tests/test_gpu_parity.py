@@ -203,3 +203,70 @@ def test_full_size_window_vs_oracle_on_gpu():
     am = (acc.argmax(1) == ref.argmax(1)).float().mean().item()
     print(f"96^3 window: rel-l2 {err:.4f}  sign agreement {sign:.5f}  argmax agreement {am:.5f}")
     assert err < BF16_TOL
+
+
+def _oracle_window_gpu(sd, image, noise, num_steps):
+    """oracle DDIM window evaluated with torch on the GPU in fp32 (TF32 off): checker for the BASELINE-size cases"""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sched = oracle_ddim.SpacedSchedule(num_steps)
+    e = oracle_model.encoder_forward(sd, image)
+    x, ref = noise, torch.zeros_like(noise)
+    for i in reversed(range(num_steps)):
+        t = torch.full((image.shape[0],), sched.timestep_map[i], dtype=torch.int64, device="cuda")
+        x0 = oracle_model.denoiser_forward(sd, x, t, image, e).clamp(-1, 1)
+        r = float(np.float32(sched.sqrt_recip_alphas_cumprod[i]))
+        m_ = float(np.float32(sched.sqrt_recipm1_alphas_cumprod[i]))
+        abp = torch.tensor(np.float32(sched.alphas_cumprod_prev[i]), device="cuda")
+        x = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp) * ((r * x - x0) / m_)
+        ref = ref + x0
+    return ref
+
+
+def test_config4_btcv_batch8_three_sample_ensemble():
+    """BASELINE config 4: C=14, 96^3 patches, batch 8, DDIM-10, 3-sample ensemble averaging (mean over 3 noise draws of
+    the summed x0; the encoder runs once).  Checked against the oracle for two of the eight windows."""
+    cout, S, B, R = 14, 96, 8, 3
+    m = _build(cout, S, oracle_model.DEFAULT_FEATURES, batch_max=B)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    image = seeded_image((B, 1, S, S, S)).cuda()
+    noise = seeded_noise((R, B, cout, S, S, S)).cuda()
+    with torch.no_grad():
+        out = m(image=image, pred_type="ddim_sample", noise=noise, ensemble=R)
+        for w in (0, 5):
+            ref = sum(_oracle_window_gpu(sd, image[w:w + 1], noise[r, w:w + 1], 10) for r in range(R)) / R
+            err = rel_l2(out[w:w + 1].cpu(), ref.cpu())
+            print(f"config 4 window {w}: rel-l2 {err:.4f}")
+            assert err < BF16_TOL
+    assert float(out.min()) >= -10.0 and float(out.max()) <= 10.0
+
+
+def test_config5_msd_128cube_ddim25():
+    """BASELINE config 5: C=3, 128^3 patches, batch 4, DDIM-25 (space_timesteps(1000, [25]))."""
+    cout, S, B, N = 3, 128, 4, 25
+    m = _build(cout, S, oracle_model.DEFAULT_FEATURES, batch_max=B, num_steps=N)
+    assert m.sample_diffusion.timestep_map[:4] == [0, 42, 83, 125] and m.sample_diffusion.num_timesteps == 25
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    image, noise = seeded_image((B, 1, S, S, S)).cuda(), seeded_noise((B, cout, S, S, S)).cuda()
+    with torch.no_grad():
+        out = m(image=image, pred_type="ddim_sample", noise=noise)
+        ref = _oracle_window_gpu(sd, image[1:2], noise[1:2], N)
+    err = rel_l2(out[1:2].cpu(), ref.cpu())
+    print(f"config 5 (128^3, DDIM-25): rel-l2 {err:.4f}, range [{out.min().item():.1f}, {out.max().item():.1f}]")
+    assert err < BF16_TOL
+    assert float(out.min()) >= -25.0 and float(out.max()) <= 25.0
+
+
+@pytest.mark.parametrize("cout", [15, 13, 1])
+def test_odd_class_counts(cout):
+    """include_background:false gives 15 / 13 output channels (cfg/amos/classes.yaml, engine.py:58-59): channel padding
+    of the packed input, the final conv tiles and the state layout must not leak."""
+    S = 32
+    m = _build(cout, S, SMALL)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    image, noise = seeded_image((2, 1, S, S, S)), seeded_noise((2, cout, S, S, S))
+    with torch.no_grad():
+        out = m(image=image.cuda(), pred_type="ddim_sample", noise=noise.cuda())
+        e = oracle_model.encoder_forward(sd, image[1:2])
+        ref = oracle_ddim.ddim_sample_window(lambda x, t: oracle_model.denoiser_forward(sd, x, t, image[1:2], e), noise[1:2])
+    assert rel_l2(out[1:2].cpu(), ref["sample_return"]) < BF16_TOL
