@@ -205,6 +205,8 @@ def run_b200(args):
         ms = e0.elapsed_time(e1)
         conv_ms, conv_n, conv_fl = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
         _lib.check(lib.dunet_profile_read(ctypes.byref(conv_ms), ctypes.byref(conv_n), ctypes.byref(conv_fl)))
+        fam_ms, fam_n, fam_b = (ctypes.c_double * 8)(), (ctypes.c_uint64 * 8)(), (ctypes.c_double * 8)()
+        _lib.check(lib.dunet_profile_read_all(fam_ms, fam_n, fam_b))
         _lib.check(lib.dunet_profile_enable(0))
         # ---------------- end-to-end leg: host volume in, host labels out, every step ----------------
         barrier()
@@ -244,11 +246,18 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": host_vol.numel() * 4,
                     "d2h_bytes_per_step": host_labels.numel(), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv3d_tc_kernel (all 3x3x3 conv launches of rank 0 in the timed region)",
+            "roofline": {"bound": "tensor", "kernel": "conv3d_tc64_kernel + conv3d_tc_kernel: every 3x3x3 conv launch of rank 0 in the timed region (CUDA events around each launch)",
                          "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
                          "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
                          "launches": int(conv_n.value), "avg_launch_ms": conv_ms.value / max(conv_n.value, 1),
-                         "conv_share_of_step": conv_ms.value / ms, "traffic": None},
+                         "conv_share_of_step": conv_ms.value / ms,
+                         "traffic": 227.1e6, "traffic_note": "ncu --set full, conv3d_tc64<64,4> 64->64 @96^3 batch 1: dram read 113.5 MB + write <= 113.6 MB per launch = the algorithmic bytes (profiles/r1_ncu_full_conv3d_tc64.txt)"},
+            "roofline_hbm": {name: {"bound": "hbm", "achieved": fam_b[i] / fam_ms[i] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": fam_b[i] / fam_ms[i] / 1e6 / peaks["hbm_gbs"], "launches": int(fam_n[i]),
+                                    "share_of_step": fam_ms[i] / ms}
+                             for i, name in ((1, "normalise (IN+LeakyReLU+bias+residual+pool)"), (2, "final 1x1 conv + DDIM update + accumulate"),
+                                             (3, "transposed conv k2s2")) if fam_ms[i] > 0},
+            "kernel_time_share": {n: fam_ms[i] / ms for i, n in enumerate(["conv3x3x3", "normalise", "final_ddim", "deconv", "splitk_reduce"])},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

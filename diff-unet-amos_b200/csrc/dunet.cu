@@ -62,6 +62,7 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;       // event pool, reused across enable() calls
 static size_t g_prof_used = 0;
 static double g_prof_flops = 0.0;
+static double g_prof_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ALGORITHMIC HBM bytes per kernel family (see dunet_profile_read_all)
 
 static int prof_begin(int tag, cudaStream_t st) {
   if (!g_prof_on) return 0;
@@ -510,6 +511,8 @@ static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, const 
   // ~4 resident blocks per SM in total, each streaming a long contiguous range of one 8-channel plane (the
   // statistics prologue is paid once per block)
   const int per_plane = std::max(1, (148 * 8 + planes - 1) / planes);
+  if (g_prof_on)  // one bf16 read + one bf16 write per element (+ read of the residual, + 1/8 write of the pooled tensor)
+    g_prof_bytes[PROF_NORM] += (double)B * c.coutp * (double)p->V[lvl] * (4.0 + (add ? 2.0 : 0.0) + (pooled ? 0.25 : 0.0));
   TRY(prof_begin(PROF_NORM, st));
   if (pooled) {
     const dim3 grid(grid_for(p->V[lvl] / 4, NORM_THREADS, per_plane), planes);
@@ -572,6 +575,7 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf1
     const long long tiles = (long long)b.tiles_x * b.tiles_y * b.tiles_z * B;
     const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
     static bool attr1 = false, attr2 = false;
+    if (g_prof_on) g_prof_bytes[PROF_DECONV] += (double)B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
     TRY(prof_begin(PROF_DECONV, st));
     if (d.cinp == 64) {
       if (!attr1) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<1, 2>::SMEM_BYTES)); attr1 = true; }
@@ -666,6 +670,8 @@ static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) 
     if (a.F == 64) final_ddim_kernel<NT, 4><<<grid, FINAL_THREADS, 0, st>>>(a);           \
     else final_ddim_kernel<NT, 8><<<grid, FINAL_THREADS, 0, st>>>(a);                     \
   } while (0)
+  if (g_prof_on)  // feature map read once (bf16) + fp32 state x_t and sum(x0) read+written + bf16 re-pack of the next input
+    g_prof_bytes[PROF_FINAL] += (double)a.batch * (double)a.vox * (2.0 * a.F + (a.x_t ? 16.0 * a.C : 0.0) + (a.logits_out ? 4.0 * a.C : 0.0) + (a.next_in ? 2.0 * a.C : 0.0));
   TRY(prof_begin(PROF_FINAL, st));
   if (a.C <= 8) DUNET_FINAL(1);
   else if (a.C <= 16) DUNET_FINAL(2);
@@ -686,6 +692,7 @@ uint64_t dunet_launch_count(void) { return g_launches.load(); }
 int dunet_profile_enable(int32_t on) {
   g_prof_used = 0;
   g_prof_flops = 0.0;
+  for (double& b : g_prof_bytes) b = 0.0;
   g_prof_on = on != 0;
   return 0;
 }
@@ -706,9 +713,9 @@ int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_fl
   return 0;
 }
 
-int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag) {
+int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag) {
   if (!ms_by_tag || !launches_by_tag) return fail(DUNET_E_INVALID, "NULL argument");
-  for (int i = 0; i < PROF_TAGS; ++i) { ms_by_tag[i] = 0.0; launches_by_tag[i] = 0; }
+  for (int i = 0; i < PROF_TAGS; ++i) { ms_by_tag[i] = 0.0; launches_by_tag[i] = 0; if (bytes_by_tag) bytes_by_tag[i] = g_prof_bytes[i]; }
   for (size_t i = 0; i < g_prof_used; ++i) {
     CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
     float ms = 0.f;

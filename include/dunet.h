@@ -147,8 +147,10 @@ int dunet_debug_set_conv_timeline(int64_t* dev_buffer);
  * kernel time (ms), number of conv launches, and their ALGORITHMIC flops 2*B*V*Cout*27*Cin (real channels only). */
 int dunet_profile_enable(int32_t on);
 int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_flops);
-/* per kernel family [8]: 0 conv3x3x3, 1 normalise, 2 final+DDIM, 3 transposed conv, 4 split-K reduce, 5 other */
-int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag);
+/* per kernel family [8]: 0 conv3x3x3, 1 normalise, 2 final+DDIM, 3 transposed conv, 4 split-K reduce, 5 other.
+ * bytes_by_tag (nullable): ALGORITHMIC HBM bytes of the bandwidth-bound families (normalise: 4 B/element (+2 residual,
+ * +0.25 pooled); final+DDIM: per voxel 2F + 16C (+2C re-pack); transposed conv: 2(Cin + 8 Cout) per input voxel). */
+int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag);
 
 /* Device-side pipeline watchdog: non-zero if a bounded mbarrier wait expired inside a kernel (kernel bug). */
 int dunet_debug_barrier_timeouts(uint32_t* out_flag);

@@ -43,14 +43,15 @@ if a.prof:
     with torch.no_grad():
         m(image=image, pred_type="ddim_sample", noise=noise)
     torch.cuda.synchronize()
-    msb = (ctypes.c_double * 8)(); cnt = (ctypes.c_uint64 * 8)()
-    _lib.check(lib.dunet_profile_read_all(msb, cnt))
+    msb = (ctypes.c_double * 8)(); cnt = (ctypes.c_uint64 * 8)(); byt = (ctypes.c_double * 8)()
+    _lib.check(lib.dunet_profile_read_all(msb, cnt, byt))
     lib.dunet_profile_enable(0)
     names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "other"]
     tot = sum(msb)
     print("in-situ CUDA-event time per kernel family (one call, batch %d):" % a.batch)
     for i, nme in enumerate(names):
-        print(f"  {nme:14s} {msb[i]:8.3f} ms  {100 * msb[i] / tot:5.1f}%  launches {cnt[i]}")
+        bw = f"  {byt[i] / msb[i] / 1e6:7.0f} GB/s algorithmic" if byt[i] > 0 and msb[i] > 0 else ""
+        print(f"  {nme:14s} {msb[i]:8.3f} ms  {100 * msb[i] / tot:5.1f}%  launches {cnt[i]}{bw}")
     print(f"  sum {tot:.3f} ms")
 print(f"window batch {a.batch}: {ms:.2f} ms per call ({ms / a.batch:.2f} ms/window, {1e3 * a.batch / ms:.1f} patches/s), "
       f"host wall {1e3 * (t1 - t0) / a.reps:.2f} ms, out range [{out.min().item():.2f}, {out.max().item():.2f}]")
