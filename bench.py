@@ -122,14 +122,14 @@ def run_reference(args):
     elapsed = time.perf_counter() - t_all
     v = sum(vals) / len(vals)
     sample = "per step: encoder + 1 of 10 DDIM steps of one 96^3 window (C=16, fp32 torch CPU); patches/s = 1/(t_enc + 10*t_step)"
-    print(json.dumps({
+    print_json({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "reference CPU path (oracle port of the reference's PyTorch code; the reference is pure Python and cannot travel to the GPU box)"},
         "cpu_baseline": {"value": v, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -264,12 +264,26 @@ def run_b200(args):
             te, ts = cpu_window_sample(threads)
             out["cpu_baseline"] = {"value": 1.0 / (te + STEPS_DDIM * ts), "unit": "patches/s", "cores": threads, "kind": "port",
                                    "sample": "encoder + 1 of 10 DDIM steps of one 96^3 window, fp32 torch CPU oracle port; patches/s = 1/(t_enc + 10*t_step)"}
-        print(json.dumps(out))
+        print_json(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.  Route fd 1 to
+    stderr for the duration of the run and return a writer bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out_stream = _claim_stdout()
+    global print_json
+    def print_json(obj):
+        out_stream.write(json.dumps(obj) + "\n")
+        out_stream.flush()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
