@@ -60,6 +60,7 @@ SIGNATURES = {
     "dunet_profile_enable": (c_int32, [c_int32]),
     "dunet_profile_read": (c_int32, [POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double)]),
     "dunet_profile_read_all": (c_int32, [POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double)]),
+    "dunet_profile_dump": (c_int32, [POINTER(ctypes.c_double), POINTER(c_int32), c_int32, POINTER(c_int32)]),
     "dunet_debug_barrier_timeouts": (c_int32, [POINTER(c_uint32)]),
     "dunet_launch_count": (c_uint64, []),
 }

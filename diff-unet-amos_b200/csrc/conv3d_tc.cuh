@@ -114,10 +114,36 @@ __device__ __forceinline__ float warp_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// decoded work item of the generic kernel: (sample, K split, cout tile, spatial tile), spatial tile fastest so that
+// CTAs running side by side share weight tiles and halos in L2
+struct ConvItem {
+  int n, ks, ntile, tix, tiy, tiz, cb_lo, cb_hi;
+};
+__device__ __forceinline__ ConvItem conv_item(const ConvTcArgs& a, int item) {
+  ConvItem it;
+  int t = item;
+  it.tix = t % a.tiles_x; t /= a.tiles_x;
+  it.tiy = t % a.tiles_y; t /= a.tiles_y;
+  it.tiz = t % a.tiles_z; t /= a.tiles_z;
+  it.ntile = t % a.n_tiles; t /= a.n_tiles;
+  it.ks = t % a.ksplit; t /= a.ksplit;
+  it.n = t;
+  const int ncb = a.nb0 + a.nb1;
+  it.cb_lo = (int)((long long)it.ks * ncb / a.ksplit);
+  it.cb_hi = (int)((long long)(it.ks + 1) * ncb / a.ksplit);
+  return it;
+}
+
+// PERSISTENT: gridDim.x <= #SMs CTAs walk the work items round-robin; the plane / weight rings run ahead across items
+// and, when 2 * ZT * N_TILE <= 512, the accumulators are double-buffered in TMEM so the epilogue of one item overlaps
+// the MMAs of the next.  Statistics rows are per spatial tile, so results do not depend on the item -> CTA assignment.
 template <int CB_CH, int N_TILE, int ZT, int MODE>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, ConvTcArgs a) {
   using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
+  constexpr int NBUF = (2 * ZT * N_TILE <= 512) ? 2 : 1;
+  constexpr int ACC_COLS = ZT * N_TILE;
+  constexpr int TMEM_COLS = NBUF == 2 ? 512 : Cfg::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem_base;
@@ -126,33 +152,24 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   const uint32_t bars = red_smem + Cfg::RED_BYTES;
   const uint32_t a_full = bars, a_empty = bars + 8 * Cfg::A_SLOTS;
   const uint32_t w_full = bars + 16 * Cfg::A_SLOTS, w_empty = w_full + 8 * Cfg::W_SLOTS;
-  const uint32_t acc_full = w_empty + 8 * Cfg::W_SLOTS;
-  const uint32_t tmem_slot = acc_full + 8;
+  const uint32_t acc_full = w_empty + 8 * Cfg::W_SLOTS;  // [2]
+  const uint32_t acc_empty = acc_full + 16;              // [2]
+  const uint32_t tmem_slot = acc_empty + 16;
   float* red = reinterpret_cast<float*>(smem_raw + (red_smem - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile coordinates (x fastest so that co-resident CTAs share halos and the same weight tile in L2)
-  int t = blockIdx.x;
-  const int tix = t % a.tiles_x; t /= a.tiles_x;
-  const int tiy = t % a.tiles_y; t /= a.tiles_y;
-  const int tiz = t % a.tiles_z; t /= a.tiles_z;
-  const int ntile = t % a.n_tiles; t /= a.n_tiles;
-  const int ks = t % a.ksplit; t /= a.ksplit;
-  const int n = t;
-  const int x0 = tix * CONV_TX, y0 = tiy * CONV_TY, z0 = tiz * ZT;
   const int ncb = a.nb0 + a.nb1;
-  const int cb_lo = (int)((long long)ks * ncb / a.ksplit), cb_hi = (int)((long long)(ks + 1) * ncb / a.ksplit);
+  const int total_items = a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
 
   if (threadIdx.x == 0) {
     if (a.dbg) a.dbg[blockIdx.x * 8 + 0] = clock64();
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   if (warp == 0 && lane == 0) {
@@ -168,173 +185,193 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   if (warp == 0) {
     // =============================== input-plane producer (TMA) ===============================
     if (elect_one_sync()) {
-      for (int cb = cb_lo; cb < cb_hi; ++cb) {
-        const bool second = cb >= a.nb0;
-        const CUtensorMap* tm = second ? &tmap1 : &tmap0;
-        const int c3 = second ? n * a.chunks1 + (cb - a.nb0) * Cfg::KCH : n * a.chunks0 + cb * Cfg::KCH;
-        for (int p = 0; p < Cfg::PLANES; ++p) {
-          const int u = (cb - cb_lo) * Cfg::PLANES + p;
-          const int slot = u % Cfg::A_SLOTS, it = u / Cfg::A_SLOTS;
-          if (it > 0) mbar_wait(a_empty + 8 * slot, (it - 1) & 1);
-          mbar_arrive_expect_tx(a_full + 8 * slot, Cfg::PLANE_BYTES);
-          tma_load_4d(a_smem + slot * Cfg::PLANE_BYTES, tm, a_full + 8 * slot, (x0 - Cfg::HALO) * 8, y0 - Cfg::HALO,
-                      z0 + p - Cfg::HALO, c3);
+      int u = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const ConvItem it = conv_item(a, item);
+        const int x0 = it.tix * CONV_TX, y0 = it.tiy * CONV_TY, z0 = it.tiz * ZT;
+        for (int cb = it.cb_lo; cb < it.cb_hi; ++cb) {
+          const bool second = cb >= a.nb0;
+          const CUtensorMap* tm = second ? &tmap1 : &tmap0;
+          const int c3 = second ? it.n * a.chunks1 + (cb - a.nb0) * Cfg::KCH : it.n * a.chunks0 + cb * Cfg::KCH;
+          for (int p = 0; p < Cfg::PLANES; ++p, ++u) {
+            const int slot = u % Cfg::A_SLOTS, rnd = u / Cfg::A_SLOTS;
+            if (rnd > 0) mbar_wait(a_empty + 8 * slot, (rnd - 1) & 1);
+            mbar_arrive_expect_tx(a_full + 8 * slot, Cfg::PLANE_BYTES);
+            tma_load_4d(a_smem + slot * Cfg::PLANE_BYTES, tm, a_full + 8 * slot, (x0 - Cfg::HALO) * 8, y0 - Cfg::HALO,
+                        z0 + p - Cfg::HALO, c3);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== weight-tile producer (bulk copy) ===============================
     if (elect_one_sync()) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) +
-                            ((size_t)ntile * ncb + cb_lo) * Cfg::TAPS * Cfg::W_UNIT_BYTES;
-      const int nw = (cb_hi - cb_lo) * Cfg::TAPS;
-      for (int w = 0; w < nw; ++w) {
-        const int slot = w % Cfg::W_SLOTS, it = w / Cfg::W_SLOTS;
-        if (it > 0) mbar_wait(w_empty + 8 * slot, (it - 1) & 1);
-        mbar_arrive_expect_tx(w_full + 8 * slot, Cfg::W_UNIT_BYTES);
-        bulk_load_1d(w_smem + slot * Cfg::W_UNIT_BYTES, wsrc + (size_t)w * Cfg::W_UNIT_BYTES, Cfg::W_UNIT_BYTES,
-                     w_full + 8 * slot);
+      int w = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const ConvItem it = conv_item(a, item);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) +
+                              ((size_t)it.ntile * ncb + it.cb_lo) * Cfg::TAPS * Cfg::W_UNIT_BYTES;
+        const int nw = (it.cb_hi - it.cb_lo) * Cfg::TAPS;
+        for (int i = 0; i < nw; ++i, ++w) {
+          const int slot = w % Cfg::W_SLOTS, rnd = w / Cfg::W_SLOTS;
+          if (rnd > 0) mbar_wait(w_empty + 8 * slot, (rnd - 1) & 1);
+          mbar_arrive_expect_tx(w_full + 8 * slot, Cfg::W_UNIT_BYTES);
+          bulk_load_1d(w_smem + slot * Cfg::W_UNIT_BYTES, wsrc + (size_t)i * Cfg::W_UNIT_BYTES, Cfg::W_UNIT_BYTES,
+                       w_full + 8 * slot);
+        }
       }
     }
   } else if (warp == 2) {
     // =============================== MMA issuer (one thread) ===============================
     if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE);
-      for (int cb = cb_lo; cb < cb_hi; ++cb) {
-        const int ubase = (cb - cb_lo) * Cfg::PLANES;
-        int waited = 0;
+      int ubase = 0, w = 0, li = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+        const ConvItem it = conv_item(a, item);
+        const int buf = li % NBUF, use = li / NBUF;
+        if (use > 0) { mbar_wait(acc_empty + 8 * buf, (use - 1) & 1); tc_fence_after(); }
+        const uint32_t acc = tmem_base + buf * ACC_COLS;
+        for (int cb = it.cb_lo; cb < it.cb_hi; ++cb, ubase += Cfg::PLANES) {
+          int waited = 0;
 #pragma unroll 1
-        for (int tz = 0; tz < Cfg::TZ; ++tz) {
+          for (int tz = 0; tz < Cfg::TZ; ++tz) {
 #pragma unroll 1
-          for (int tyx = 0; tyx < Cfg::TYX; ++tyx) {
-            const int w = (cb - cb_lo) * Cfg::TAPS + tz * Cfg::TYX + tyx;
-            const int ws = w % Cfg::W_SLOTS;
-            mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
-            tc_fence_after();
-            const uint32_t tap_off = ((tyx / 3) * Cfg::HX + (tyx % 3)) * 16;
-            const uint32_t wb = w_smem + ws * Cfg::W_UNIT_BYTES;
+            for (int tyx = 0; tyx < Cfg::TYX; ++tyx, ++w) {
+              const int ws = w % Cfg::W_SLOTS;
+              mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
+              tc_fence_after();
+              const uint32_t tap_off = ((tyx / 3) * Cfg::HX + (tyx % 3)) * 16;
+              const uint32_t wb = w_smem + ws * Cfg::W_UNIT_BYTES;
 #pragma unroll
-            for (int s = 0; s < ZT; ++s) {
-              const int p = s + tz;
-              while (waited <= p) {
-                const int u = ubase + waited;
-                mbar_wait(a_full + 8 * (u % Cfg::A_SLOTS), (u / Cfg::A_SLOTS) & 1);
-                tc_fence_after();
-                ++waited;
-              }
-              const int u = ubase + p;
-              const uint32_t ab = a_smem + (u % Cfg::A_SLOTS) * Cfg::PLANE_BYTES + tap_off;
+              for (int s = 0; s < ZT; ++s) {
+                const int p = s + tz;
+                while (waited <= p) {
+                  const int u = ubase + waited;
+                  mbar_wait(a_full + 8 * (u % Cfg::A_SLOTS), (u / Cfg::A_SLOTS) & 1);
+                  tc_fence_after();
+                  ++waited;
+                }
+                const int u = ubase + p;
+                const uint32_t ab = a_smem + (u % Cfg::A_SLOTS) * Cfg::PLANE_BYTES + tap_off;
 #pragma unroll
-              for (int k = 0; k < CB_CH / 16; ++k) {
-                const uint64_t ad = make_smem_desc(ab + k * 2 * Cfg::A_LBO, Cfg::A_LBO, Cfg::A_SBO);
-                const uint64_t bd = make_smem_desc(wb + k * 2 * Cfg::B_LBO, Cfg::B_LBO, Cfg::B_SBO);
-                umma_bf16(tmem_base + s * N_TILE, ad, bd, idesc, ((cb - cb_lo) | tz | tyx | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < CB_CH / 16; ++k) {
+                  const uint64_t ad = make_smem_desc(ab + k * 2 * Cfg::A_LBO, Cfg::A_LBO, Cfg::A_SBO);
+                  const uint64_t bd = make_smem_desc(wb + k * 2 * Cfg::B_LBO, Cfg::B_LBO, Cfg::B_SBO);
+                  umma_bf16(acc + s * N_TILE, ad, bd, idesc, ((cb - it.cb_lo) | tz | tyx | k) != 0 ? 1u : 0u);
+                }
               }
+              umma_commit(w_empty + 8 * ws);  // weight slot free once these MMAs retire
             }
-            umma_commit(w_empty + 8 * ws);  // weight slot free once these MMAs retire
-            if (a.dbg && w == 0) a.dbg[blockIdx.x * 8 + 1] = clock64();
-          }
-          // planes whose last reader was this tz phase go back to the producer
-          if (tz < Cfg::TZ - 1) {
-            umma_commit(a_empty + 8 * ((ubase + tz) % Cfg::A_SLOTS));
-          } else {
-            for (int p = tz; p < Cfg::PLANES; ++p) umma_commit(a_empty + 8 * ((ubase + p) % Cfg::A_SLOTS));
+            // planes whose last reader was this tz phase go back to the producer
+            if (tz < Cfg::TZ - 1) {
+              umma_commit(a_empty + 8 * ((ubase + tz) % Cfg::A_SLOTS));
+            } else {
+              for (int p = tz; p < Cfg::PLANES; ++p) umma_commit(a_empty + 8 * ((ubase + p) % Cfg::A_SLOTS));
+            }
           }
         }
+        umma_commit(acc_full + 8 * buf);
       }
-      umma_commit(acc_full);
       if (a.dbg) a.dbg[blockIdx.x * 8 + 2] = clock64();
     }
   } else {
     // =============================== epilogue: TMEM -> registers -> HBM ===============================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    if (a.dbg && warp == 3 && lane == 0) a.dbg[blockIdx.x * 8 + 3] = clock64();
     const int r = q * 32 + lane;  // GEMM row = voxel (y = r / 8, x = r % 8)
-    const int x = x0 + (r & 7), y = y0 + (r >> 3);
-    const bool xy_ok = x < a.W && y < a.H;
     const int out_chunks = a.cout / 8;
     const long long in_vox = (long long)a.D * a.H * a.W;
     const bool do_stats = (MODE == MODE_CONV3) && a.stats != nullptr;
+    int li = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+      const ConvItem it = conv_item(a, item);
+      const int n = it.n, ks = it.ks, ntile = it.ntile;
+      const int x = it.tix * CONV_TX + (r & 7), y = it.tiy * CONV_TY + (r >> 3), z0 = it.tiz * ZT;
+      const bool xy_ok = x < a.W && y < a.H;
+      const int buf = li % NBUF, use = li / NBUF;
+      mbar_wait(acc_full + 8 * buf, use & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
 #pragma unroll 1
-    for (int j = 0; j < N_TILE / 16; ++j) {
-      float st[32];
+      for (int j = 0; j < N_TILE / 16; ++j) {
+        float st[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) st[i] = 0.f;
-      const int gcol = ntile * N_TILE + j * 16;
+        for (int i = 0; i < 32; ++i) st[i] = 0.f;
+        const int gcol = ntile * N_TILE + j * 16;
 #pragma unroll 1
-      for (int s = 0; s < ZT; ++s) {
-        const int z = z0 + s;
-        const bool ok = xy_ok && z < a.D;
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + s * N_TILE + j * 16, v);
-        if constexpr (MODE == MODE_CONV3) {
-          const long long vofs = ((long long)z * a.H + y) * a.W + x;
-          if (a.out_partial) {
-            if (ok) {
-              float4* dst = reinterpret_cast<float4*>(a.out_partial) +
-                            ((((long long)ks * a.batch + n) * out_chunks + gcol / 8) * in_vox + vofs) * 2;
-              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-              dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-              dst[in_vox * 2] = make_float4(v[8], v[9], v[10], v[11]);
-              dst[in_vox * 2 + 1] = make_float4(v[12], v[13], v[14], v[15]);
+        for (int s = 0; s < ZT; ++s) {
+          const int z = z0 + s;
+          const bool ok = xy_ok && z < a.D;
+          float v[16];
+          tmem_ld16(acc + s * N_TILE + j * 16, v);
+          if constexpr (MODE == MODE_CONV3) {
+            const long long vofs = ((long long)z * a.H + y) * a.W + x;
+            if (a.out_partial) {
+              if (ok) {
+                float4* dst = reinterpret_cast<float4*>(a.out_partial) +
+                              ((((long long)ks * a.batch + n) * out_chunks + gcol / 8) * in_vox + vofs) * 2;
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                dst[in_vox * 2] = make_float4(v[8], v[9], v[10], v[11]);
+                dst[in_vox * 2 + 1] = make_float4(v[12], v[13], v[14], v[15]);
+              }
+            } else {
+              if (ok) {
+                BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + gcol / 8) * in_vox + vofs;
+                float lo[8], hi[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+                dst[0] = float_to_bf8(lo);
+                dst[in_vox] = float_to_bf8(hi);
+              }
+              if (do_stats) {
+                const float m = ok ? 1.f : 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float xv = v[i] * m;
+                  st[i] += xv;
+                  st[16 + i] = fmaf(xv, xv, st[16 + i]);
+                }
+              }
             }
           } else {
             if (ok) {
-              BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + gcol / 8) * in_vox + vofs;
+              const int tap = gcol / a.cout, co = gcol % a.cout;
+              const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
+              const long long ovox = in_vox * 8;
+              BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + co / 8) * ovox +
+                         ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;
               float lo[8], hi[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+              for (int i = 0; i < 8; ++i) { lo[i] = v[i] + a.bias[co + i]; hi[i] = v[8 + i] + a.bias[co + 8 + i]; }
               dst[0] = float_to_bf8(lo);
-              dst[in_vox] = float_to_bf8(hi);
+              dst[ovox] = float_to_bf8(hi);
             }
-            if (do_stats) {
-              const float m = ok ? 1.f : 0.f;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float xv = v[i] * m;
-                st[i] += xv;
-                st[16 + i] = fmaf(xv, xv, st[16 + i]);
-              }
-            }
-          }
-        } else {
-          if (ok) {
-            const int tap = gcol / a.cout, co = gcol % a.cout;
-            const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
-            const long long ovox = in_vox * 8;
-            BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + co / 8) * ovox +
-                       ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;
-            float lo[8], hi[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { lo[i] = v[i] + a.bias[co + i]; hi[i] = v[8 + i] + a.bias[co + 8 + i]; }
-            dst[0] = float_to_bf8(lo);
-            dst[ovox] = float_to_bf8(hi);
           }
         }
+        if (do_stats) red[q * (N_TILE * 2) + j * 32 + lane] = warp_reduce32(st, lane);
       }
-      if (do_stats) red[q * (N_TILE * 2) + j * 32 + lane] = warp_reduce32(st, lane);
-    }
-    if (do_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      const int i = q * 32 + lane;                     // 0..127
-      const int nseg = a.tiles_x * a.tiles_y * a.tiles_z;
-      const int tile_lin = (tiz * a.tiles_y + tiy) * a.tiles_x + tix;
-      for (int e = i; e < N_TILE * 2; e += 128) {
-        const float tot = (red[e] + red[N_TILE * 2 + e]) + (red[2 * N_TILE * 2 + e] + red[3 * N_TILE * 2 + e]);
-        const int l = e & 31, col = (e >> 5) * 16 + (l & 15), stat = l >> 4;
-        const int chunk = (ntile * N_TILE + col) >> 3;
-        a.stats[(((long long)n * out_chunks + chunk) * nseg + tile_lin) * 16 + stat * 8 + (col & 7)] = tot;
+      // all TMEM reads of this accumulator set are done: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+      if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const int nseg = a.tiles_x * a.tiles_y * a.tiles_z;
+        const int tile_lin = (it.tiz * a.tiles_y + it.tiy) * a.tiles_x + it.tix;
+        for (int e = r; e < N_TILE * 2; e += 128) {
+          const float tot = (red[e] + red[N_TILE * 2 + e]) + (red[2 * N_TILE * 2 + e] + red[3 * N_TILE * 2 + e]);
+          const int l = e & 31, col = (e >> 5) * 16 + (l & 15), stat = l >> 4;
+          const int chunk = (ntile * N_TILE + col) >> 3;
+          a.stats[(((long long)n * out_chunks + chunk) * nseg + tile_lin) * 16 + stat * 8 + (col & 7)] = tot;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // red[] is reused by the next item
       }
     }
-    if (a.dbg && warp == 3 && lane == 0) a.dbg[blockIdx.x * 8 + 4] = clock64();
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -329,9 +329,15 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
   ConvGeom g;
   g.tiles_x = (p->W[lvl] + CONV_TX - 1) / CONV_TX;
   g.tiles_y = (p->H[lvl] + CONV_TY - 1) / CONV_TY;
-  // small volumes (deep U-Net levels) are latency bound: thinner z-tiles give more, shorter CTAs.  The Cout = 64
-  // z-stacked kernel always uses ZT = 4.
-  g.zt = (p->D[lvl] <= 24 && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
+  // ZT (z-slabs per work item) trades weight re-use (each streamed weight tile feeds ZT slabs) against parallelism.
+  // Small volumes (deep U-Net levels) get thinner items when a single sample would otherwise give fewer than ~half a
+  // wave of work items.  Decided from per-sample shapes only (batch-invariant results).  The Cout = 64 z-stacked
+  // kernel always uses ZT = 4.
+  {
+    const int tz4 = (p->D[lvl] + CONV_ZT - 1) / CONV_ZT;
+    const int items4 = g.tiles_x * g.tiles_y * tz4 * c.n_tiles * std::max(1, std::min(c.nb0 + c.nb1, 4));
+    g.zt = (items4 < 64 && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
+  }
   g.tiles_z = (p->D[lvl] + g.zt - 1) / g.zt;
   g.tiles = g.tiles_x * g.tiles_y * g.tiles_z;
   // the split factor must not depend on the batch: a window's result is bit-identical whatever it is batched with
@@ -386,6 +392,7 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
 
 // ------------------------------------------------------------------------------------------------ layer launchers
 static long long* g_conv_dbg = nullptr;  // optional per-CTA timeline buffer (tools only)
+static int g_num_sms = 0;
 
 template <int CB_CH, int N_TILE, int ZT, int MODE>
 static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTcArgs& a, cudaStream_t st) {
@@ -396,15 +403,20 @@ static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const Co
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const long long grid = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
+  const long long items = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
+  if (!g_num_sms) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // persistent: one CTA per SM (each may own all 512 TMEM columns) walking the work items round-robin
+  const long long grid = std::min<long long>(items, (long long)g_num_sms);
   TRY(prof_begin(MODE == MODE_CONV3 ? PROF_CONV : PROF_DECONV, st));
   kern<<<(unsigned)grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
   return 0;
 }
-
-static int g_num_sms = 0;
 
 template <int CB_CH>
 static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTc64Args& a, unsigned* grid_out,
@@ -723,6 +735,19 @@ int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag, double*
     ms_by_tag[g_prof[i].tag] += ms;
     launches_by_tag[g_prof[i].tag] += 1;
   }
+  return 0;
+}
+
+int dunet_profile_dump(double* ms, int32_t* tags, int32_t capacity, int32_t* count) {
+  if (!ms || !tags || !count) return fail(DUNET_E_INVALID, "NULL argument");
+  int n = 0;
+  for (size_t i = 0; i < g_prof_used && n < capacity; ++i, ++n) {
+    CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
+    ms[n] = t; tags[n] = g_prof[i].tag;
+  }
+  *count = n;
   return 0;
 }
 

@@ -151,6 +151,8 @@ int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_fl
  * bytes_by_tag (nullable): ALGORITHMIC HBM bytes of the bandwidth-bound families (normalise: 4 B/element (+2 residual,
  * +0.25 pooled); final+DDIM: per voxel 2F + 16C (+2C re-pack); transposed conv: 2(Cin + 8 Cout) per input voxel). */
 int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag);
+/* every profiled launch in issue order: duration (ms) and kernel family tag */
+int dunet_profile_dump(double* ms, int32_t* tags, int32_t capacity, int32_t* count);
 
 /* Device-side pipeline watchdog: non-zero if a bounded mbarrier wait expired inside a kernel (kernel bug). */
 int dunet_debug_barrier_timeouts(uint32_t* out_flag);

@@ -18,6 +18,7 @@ ap.add_argument("--C", type=int, default=16)
 ap.add_argument("--ddim", type=int, default=10)
 ap.add_argument("--prof", action="store_true")
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--dump", action="store_true")
 a = ap.parse_args()
 torch.manual_seed(0)
 m = pkg.DiffUNetB200(in_channels=1, out_channels=a.C, image_size=a.S, spatial_size=a.S, batch_max=a.batch, num_steps=a.ddim, debug_flags=a.flags).cuda().eval()
@@ -53,5 +54,20 @@ if a.prof:
         bw = f"  {byt[i] / msb[i] / 1e6:7.0f} GB/s algorithmic" if byt[i] > 0 and msb[i] > 0 else ""
         print(f"  {nme:14s} {msb[i]:8.3f} ms  {100 * msb[i] / tot:5.1f}%  launches {cnt[i]}{bw}")
     print(f"  sum {tot:.3f} ms")
+    if a.dump:
+        cap = 4096
+        dms = (ctypes.c_double * cap)(); dtg = (ctypes.c_int32 * cap)(); dn = ctypes.c_int32()
+        lib.dunet_profile_enable(1)
+        with torch.no_grad():
+            m(image=image, pred_type="ddim_sample", noise=noise)
+        torch.cuda.synchronize()
+        _lib.check(lib.dunet_profile_dump(dms, dtg, cap, ctypes.byref(dn)))
+        lib.dunet_profile_enable(0)
+        seq = [(dtg[i], dms[i] * 1e3) for i in range(dn.value)]
+        # one denoiser step = the launches between the 2nd and 3rd final kernel
+        fin = [i for i, (tg, _) in enumerate(seq) if tg == 2]
+        print("one DDIM step, in issue order (us):")
+        for tg, us in seq[fin[1] + 1:fin[2] + 1]:
+            print(f"   {names[tg]:14s} {us:8.1f}")
 print(f"window batch {a.batch}: {ms:.2f} ms per call ({ms / a.batch:.2f} ms/window, {1e3 * a.batch / ms:.1f} patches/s), "
       f"host wall {1e3 * (t1 - t0) / a.reps:.2f} ms, out range [{out.min().item():.2f}, {out.max().item():.2f}]")
