@@ -16,6 +16,7 @@ DUNET_FLAG_REF_CONV = 1
 DUNET_FLAG_KEEP_FP32_WEIGHTS = 2
 DUNET_FLAG_GENERIC_CONV = 4
 DUNET_FLAG_DUAL_STREAM = 8
+DUNET_FLAG_FP32X3 = 16
 
 
 class DunetCfg(ctypes.Structure):

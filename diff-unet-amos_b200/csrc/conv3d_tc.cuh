@@ -66,14 +66,39 @@ struct ConvTc {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
+// Input-channel blocks are described by up to 6 SEGMENTS, each a run of `nblocks` consecutive blocks of one source
+// tensor (tensor map `tmap` of the kernel's four).  bf16 mode: [skip] or [skip, upsampled] (the UpCat concat).
+// fp32x3 mode (split-bf16: every activation and weight is a hi + lo bf16 pair, product = hi*hi + lo*hi + hi*lo):
+// [S0.hi, S1.hi | S0.lo, S1.lo | S0.hi, S1.hi] against weight blocks [W.hi | W.hi | W.lo].
+struct ConvSeg {
+  int tmap, nblocks, chunks;  // chunks = C/8 of the source (stride of the batch index in the folded 4th tensor-map dim)
+};
+constexpr int CONV_MAX_SEGS = 6;
+struct ConvSegs {
+  int n, ncb;
+  ConvSeg s[CONV_MAX_SEGS];
+};
+// global input-channel block index -> (tensor map, first 16-byte chunk of the block inside one sample of that source)
+__device__ __forceinline__ void conv_seg_lookup(const ConvSegs& sg, int cb, int kch, int& tmap, int& chunk0, int& chunks) {
+  int base = 0;
+#pragma unroll 1
+  for (int i = 0; i < sg.n; ++i) {
+    if (cb < base + sg.s[i].nblocks || i == sg.n - 1) {
+      tmap = sg.s[i].tmap; chunk0 = (cb - base) * kch; chunks = sg.s[i].chunks;
+      return;
+    }
+    base += sg.s[i].nblocks;
+  }
+}
+
 struct ConvTcArgs {
   const __nv_bfloat16* w;  // packed [n_tile][cin_block][tap][KCH][N_TILE][8]
   __nv_bfloat16* out;      // bf16 C8-planar output (raw conv output / transposed-conv result), `cout` channels
+  __nv_bfloat16* out_lo;   // fp32x3 mode: low part of the output (out + out_lo ~ the fp32 accumulator) or nullptr
   float* out_partial;      // split-K only: fp32 partial tiles [ks][n][cout/8][voxels][8]
   float* stats;            // fused IN statistics [n*cout/8 + chunk][tiles per sample][16] (conv, ksplit == 1) or nullptr
   const float* bias;       // transposed conv: bias[cout]
-  int nb0, nb1;            // input-channel blocks taken from tensor map 0 / 1
-  int chunks0, chunks1;    // C/8 of source 0 / 1 (stride of the batch index in the folded 4th tensor-map dim)
+  ConvSegs segs;           // input-channel block list
   int cout;                // channels of the output tensor (padded)
   int D, H, W;             // INPUT spatial size (the transposed conv writes a 2D x 2H x 2W volume)
   int tiles_x, tiles_y, tiles_z, n_tiles, ksplit, batch;
@@ -128,7 +153,7 @@ __device__ __forceinline__ ConvItem conv_item(const ConvTcArgs& a, int item) {
   it.ntile = t % a.n_tiles; t /= a.n_tiles;
   it.ks = t % a.ksplit; t /= a.ksplit;
   it.n = t;
-  const int ncb = a.nb0 + a.nb1;
+  const int ncb = a.segs.ncb;
   it.cb_lo = (int)((long long)it.ks * ncb / a.ksplit);
   it.cb_hi = (int)((long long)(it.ks + 1) * ncb / a.ksplit);
   return it;
@@ -139,7 +164,8 @@ __device__ __forceinline__ ConvItem conv_item(const ConvTcArgs& a, int item) {
 // the MMAs of the next.  Statistics rows are per spatial tile, so results do not depend on the item -> CTA assignment.
 template <int CB_CH, int N_TILE, int ZT, int MODE>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, ConvTcArgs a) {
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                 const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, ConvTcArgs a) {
   using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
   constexpr int NBUF = (2 * ZT * N_TILE <= 512) ? 2 : 1;
   constexpr int ACC_COLS = ZT * N_TILE;
@@ -158,7 +184,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   float* red = reinterpret_cast<float*>(smem_raw + (red_smem - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ncb = a.nb0 + a.nb1;
+  const int ncb = a.segs.ncb;
   const int total_items = a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
 
   if (threadIdx.x == 0) {
@@ -174,7 +200,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap0);
-    if (a.nb1 > 0) tma_prefetch_desc(&tmap1);
+    if (a.segs.n > 1) tma_prefetch_desc(&tmap1);
+    if (a.segs.n > 2) { tma_prefetch_desc(&tmap2); tma_prefetch_desc(&tmap3); }
   }
   tc_fence_before();
   __syncthreads();
@@ -185,14 +212,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   if (warp == 0) {
     // =============================== input-plane producer (TMA) ===============================
     if (elect_one_sync()) {
+      const CUtensorMap* const tms[4] = {&tmap0, &tmap1, &tmap2, &tmap3};
       int u = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const ConvItem it = conv_item(a, item);
         const int x0 = it.tix * CONV_TX, y0 = it.tiy * CONV_TY, z0 = it.tiz * ZT;
         for (int cb = it.cb_lo; cb < it.cb_hi; ++cb) {
-          const bool second = cb >= a.nb0;
-          const CUtensorMap* tm = second ? &tmap1 : &tmap0;
-          const int c3 = second ? it.n * a.chunks1 + (cb - a.nb0) * Cfg::KCH : it.n * a.chunks0 + cb * Cfg::KCH;
+          int ti, chunk0, chunks;
+          conv_seg_lookup(a.segs, cb, Cfg::KCH, ti, chunk0, chunks);
+          const CUtensorMap* tm = tms[ti];
+          const int c3 = it.n * chunks + chunk0;
           for (int p = 0; p < Cfg::PLANES; ++p, ++u) {
             const int slot = u % Cfg::A_SLOTS, rnd = u / Cfg::A_SLOTS;
             if (rnd > 0) mbar_wait(a_empty + 8 * slot, (rnd - 1) & 1);
@@ -316,12 +345,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
               }
             } else {
               if (ok) {
-                BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + gcol / 8) * in_vox + vofs;
-                float lo[8], hi[8];
+                const long long o = ((long long)n * out_chunks + gcol / 8) * in_vox + vofs;
+                float c0[8], c1[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
-                dst[0] = float_to_bf8(lo);
-                dst[in_vox] = float_to_bf8(hi);
+                for (int i = 0; i < 8; ++i) { c0[i] = v[i]; c1[i] = v[8 + i]; }
+                store_split(a.out, a.out_lo, o, c0);
+                store_split(a.out, a.out_lo, o + in_vox, c1);
               }
               if (do_stats) {
                 const float m = ok ? 1.f : 0.f;
@@ -338,13 +367,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
               const int tap = gcol / a.cout, co = gcol % a.cout;
               const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
               const long long ovox = in_vox * 8;
-              BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + co / 8) * ovox +
-                         ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;
-              float lo[8], hi[8];
+              const long long o = ((long long)n * out_chunks + co / 8) * ovox + ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;
+              float c0[8], c1[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { lo[i] = v[i] + a.bias[co + i]; hi[i] = v[8 + i] + a.bias[co + 8 + i]; }
-              dst[0] = float_to_bf8(lo);
-              dst[ovox] = float_to_bf8(hi);
+              for (int i = 0; i < 8; ++i) { c0[i] = v[i] + a.bias[co + i]; c1[i] = v[8 + i] + a.bias[co + 8 + i]; }
+              store_split(a.out, a.out_lo, o, c0);
+              store_split(a.out, a.out_lo, o + ovox, c1);
             }
           }
         }

@@ -44,8 +44,9 @@ struct ConvTc64 {
 struct ConvTc64Args {
   const __nv_bfloat16* w;  // packed [cin_block][ty*3+tx][KCH][192][8]
   __nv_bfloat16* out;      // raw conv output, C8-planar, 64 channels
+  __nv_bfloat16* out_lo;   // fp32x3 mode: low part of the output, or nullptr
   float* stats;            // [n*8 + chunk][gridDim.x][16] (one row per CTA and sample) or nullptr
-  int nb0, nb1, chunks0, chunks1;
+  ConvSegs segs;           // input-channel block list (conv3d_tc.cuh)
   int D, H, W;
   int tiles_x, tiles_y, tiles_z, batch;
 };
@@ -65,7 +66,8 @@ __device__ __forceinline__ void for_each_tile(int tiles_per_n, int batch, F&& f)
 
 template <int CB_CH, int ZT>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, ConvTc64Args a) {
+conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
+                   const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, ConvTc64Args a) {
   using Cfg = ConvTc64<CB_CH, ZT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -81,7 +83,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   float* red = reinterpret_cast<float*>(smem_raw + (red_smem - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ncb = a.nb0 + a.nb1;
+  const int ncb = a.segs.ncb;
   const int tiles_per_n = a.tiles_x * a.tiles_y * a.tiles_z;
 
   if (threadIdx.x == 0) {
@@ -96,7 +98,8 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap0);
-    if (a.nb1 > 0) tma_prefetch_desc(&tmap1);
+    if (a.segs.n > 1) tma_prefetch_desc(&tmap1);
+    if (a.segs.n > 2) { tma_prefetch_desc(&tmap2); tma_prefetch_desc(&tmap3); }
   }
   tc_fence_before();
   __syncthreads();
@@ -107,6 +110,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   if (warp == 0) {
     // =============================== halo-plane producer (TMA), runs ahead across tiles ===============================
     if (elect_one_sync()) {
+      const CUtensorMap* const tms[4] = {&tmap0, &tmap1, &tmap2, &tmap3};
       int u = 0;
       for_each_tile(tiles_per_n, a.batch, [&](int n, int lin) {
         int t = lin;
@@ -115,9 +119,10 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         const int tiz = t;
         const int x0 = tix * CONV_TX, y0 = tiy * CONV_TY, z0 = tiz * ZT;
         for (int cb = 0; cb < ncb; ++cb) {
-          const bool second = cb >= a.nb0;
-          const CUtensorMap* tm = second ? &tmap1 : &tmap0;
-          const int c3 = second ? n * a.chunks1 + (cb - a.nb0) * Cfg::KCH : n * a.chunks0 + cb * Cfg::KCH;
+          int ti, chunk0, chunks;
+          conv_seg_lookup(a.segs, cb, Cfg::KCH, ti, chunk0, chunks);
+          const CUtensorMap* tm = tms[ti];
+          const int c3 = n * chunks + chunk0;
           for (int p = 0; p < Cfg::PLANES; ++p, ++u) {
             const int slot = u % Cfg::A_SLOTS, it = u / Cfg::A_SLOTS;
             if (it > 0) mbar_wait(a_empty + 8 * slot, (it - 1) & 1);
@@ -249,12 +254,12 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
           float v[16];
           tmem_ld16(acc + s * 64 + j * 16, v);
           if (ok) {
-            BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * 8 + j * 2) * vox + ((long long)z * a.H + y) * a.W + x;
-            float lo[8], hi[8];
+            const long long o = ((long long)n * 8 + j * 2) * vox + ((long long)z * a.H + y) * a.W + x;
+            float c0[8], c1[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
-            dst[0] = float_to_bf8(lo);
-            dst[vox] = float_to_bf8(hi);
+            for (int i = 0; i < 8; ++i) { c0[i] = v[i]; c1[i] = v[8 + i]; }
+            store_split(a.out, a.out_lo, o, c0);
+            store_split(a.out, a.out_lo, o + vox, c1);
           }
           if (a.stats) {
             const float m = ok ? 1.f : 0.f;

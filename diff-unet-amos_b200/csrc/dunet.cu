@@ -125,9 +125,16 @@ static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, in
 
 // ------------------------------------------------------------------------------------------------ weight packing
 // conv weights fp32 [coutr][cinr][27] -> bf16 [n_tile][cin block][tap][k chunk][N_TILE][8]   (see conv3d_tc.cuh)
+// fp32x3 mode (parts == 3): the block list is [W.hi | W.hi | W.lo] (ncb = 3 x the logical blocks), matching the activation
+// segments [A.hi | A.lo | A.hi] of ConvSegs.
+__device__ __forceinline__ bf16 weight_part(float v, int part) {
+  const bf16 hi = __float2bfloat16_rn(v);
+  return part < 2 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+}
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles, int rot) {
+                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles, int rot, int parts) {
   const int kch = cb_ch / 8;
+  const int ncb1 = ncb / parts;
   const long long total = (long long)n_tiles * ncb * 27 * kch * n_tile * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -136,23 +143,25 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict
     const int col = (int)(t % n_tile); t /= n_tile;
     const int k = (int)(t % kch); t /= kch;
     const int tap = (int)(t % 27); t /= 27;
-    const int cb = (int)(t % ncb); t /= ncb;
+    const int cbg = (int)(t % ncb); t /= ncb;
     const int nt = (int)t;
     const int co = nt * n_tile + col;
+    const int cb = cbg % ncb1, part = parts == 1 ? 0 : cbg / ncb1;
     const int lc = cb * cb_ch + k * 8 + j;
     int ci = -1;
     if (lc < c0p) { if (lc < c0r) ci = rot ? (lc + 1) % c0r : lc; }  // rot: packed order is [x.., image], reference [image, x..]
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = weight_part(v, part);
   }
 }
 // conv weights for the Cout = 64 z-stacked kernel (conv3d_tc64.cuh): bf16 [cin block][ty*3+tx][k chunk][192][8] with
 // row = (2 - tz) * 64 + cout
 __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                     int c0p, int c1r, int cb_ch, int ncb, int rot) {
+                                     int c0p, int c1r, int cb_ch, int ncb, int rot, int parts) {
   const int kch = cb_ch / 8;
+  const int ncb1 = ncb / parts;
   const long long total = (long long)ncb * 9 * kch * 192 * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -161,7 +170,8 @@ __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restri
     const int row = (int)(t % 192); t /= 192;
     const int k = (int)(t % kch); t /= kch;
     const int tyx = (int)(t % 9); t /= 9;
-    const int cb = (int)t;
+    const int cbg = (int)t;
+    const int cb = cbg % ncb1, part = parts == 1 ? 0 : cbg / ncb1;
     const int tz = 2 - row / 64, co = row % 64;
     const int tap = tz * 9 + tyx;
     const int lc = cb * cb_ch + k * 8 + j;
@@ -170,7 +180,7 @@ __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restri
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = weight_part(v, part);
   }
 }
 // transposed-conv weights fp32 [cinr][coutr][8] -> bf16 [tap][cinp][coutp]
@@ -190,8 +200,8 @@ __global__ void pack_deconv_w_kernel(const float* __restrict__ w, bf16* __restri
 // transposed-conv weights fp32 [cinr][coutr][8] -> tensor-core B operand bf16 [n_tile][cin block][k chunk][128][8] where
 // GEMM column = tap * coutp + cout  (tap = dz*4 + dy*2 + dx)
 __global__ void pack_deconv_tc_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cinr, int coutr, int cinp,
-                                        int coutp) {
-  const int n_tile = 128, kch = 8, ncb = cinp / 64, n_tiles = 8 * coutp / n_tile;
+                                        int coutp, int parts) {
+  const int n_tile = 128, kch = 8, ncb1 = cinp / 64, ncb = ncb1 * parts, n_tiles = 8 * coutp / n_tile;
   const long long total = (long long)n_tiles * ncb * kch * n_tile * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -199,13 +209,14 @@ __global__ void pack_deconv_tc_w_kernel(const float* __restrict__ w, bf16* __res
     const int j = (int)(t % 8); t /= 8;
     const int col = (int)(t % n_tile); t /= n_tile;
     const int k = (int)(t % kch); t /= kch;
-    const int cb = (int)(t % ncb); t /= ncb;
+    const int cbg = (int)(t % ncb); t /= ncb;
     const int nt = (int)t;
+    const int cb = cbg % ncb1, part = parts == 1 ? 0 : cbg / ncb1;
     const int gcol = nt * n_tile + col, tap = gcol / coutp, co = gcol % coutp;
     const int ci = cb * 64 + k * 8 + j;
     float v = 0.f;
     if (ci < cinr && co < coutr) v = w[((long long)ci * coutr + co) * 8 + tap];
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = weight_part(v, part);
   }
 }
 // copy `n` floats into a zero-padded buffer of n_pad floats, optionally strided rows: dst[r][0..cols_pad) <- src[r][0..cols)
@@ -223,21 +234,28 @@ __global__ void copy_pad_rows_kernel(const float* __restrict__ src, float* __res
 struct ConvW {
   int c0r = 0, c1r = 0, c0p = 0, c1p = 0, coutr = 0, coutp = 0;
   int cb_ch = 64, n_tile = 64, nb0 = 0, nb1 = 0, n_tiles = 1;
+  int parts = 1;  // 3 in fp32x3 mode: weight block list [W.hi | W.hi | W.lo]
   bf16* packed = nullptr;
   bf16* packed64 = nullptr;  // z-stacked layout for the Cout = 64 kernel (coutp == 64 only)
   float* w32 = nullptr;  // debug copy of the original fp32 weight
   float *gamma = nullptr, *beta = nullptr;
   int rot = 0;  // 1: packed input channel j holds reference channel (j + 1) % c0r (denoiser input [x.., image])
   bool have_w = false, have_cb = false, have_g = false, have_b = false;
-  void shape(int c0r_, int c0p_, int c1r_, int c1p_, int coutr_) {
-    c0r = c0r_; c0p = c0p_; c1r = c1r_; c1p = c1p_; coutr = coutr_;
+  void shape(int c0r_, int c0p_, int c1r_, int c1p_, int coutr_, int parts_ = 1) {
+    c0r = c0r_; c0p = c0p_; c1r = c1r_; c1p = c1p_; coutr = coutr_; parts = parts_;
     coutp = pad_to(coutr, 64);
     cb_ch = (c1p == 0 && c0p == 32) ? 32 : 64;
     n_tile = (coutp % 128 == 0) ? 128 : 64;
     n_tiles = coutp / n_tile;
     nb0 = c0p / cb_ch; nb1 = c1p / cb_ch;
   }
-  size_t packed_elems() const { return (size_t)n_tiles * (nb0 + nb1) * 27 * cb_ch * n_tile; }
+  int ncb() const { return (nb0 + nb1) * parts; }  // input-channel blocks the kernels walk
+  size_t packed_elems() const { return (size_t)n_tiles * ncb() * 27 * cb_ch * n_tile; }
+  size_t packed64_elems() const { return (size_t)ncb() * 9 * cb_ch * 192; }
+};
+struct Act {  // an activation tensor: C8-planar bf16, plus its low part in fp32x3 mode
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
 };
 struct TwoConvW {
   ConvW a, b;
@@ -245,7 +263,7 @@ struct TwoConvW {
   bool has_temb = false, have_tpw = false, have_tpb = false;
 };
 struct DeconvW {
-  int cinr = 0, cinp = 0, coutr = 0, coutp = 0;
+  int cinr = 0, cinp = 0, coutr = 0, coutp = 0, parts = 1;
   bf16* packed = nullptr;     // CUDA-core debug kernel layout [tap][cinp][coutp]
   bf16* packed_tc = nullptr;  // tensor-core layout, see pack_deconv_tc_w_kernel
   float* bias = nullptr;
@@ -335,14 +353,14 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
   // kernel always uses ZT = 4.
   {
     const int tz4 = (p->D[lvl] + CONV_ZT - 1) / CONV_ZT;
-    const int items4 = g.tiles_x * g.tiles_y * tz4 * c.n_tiles * std::max(1, std::min(c.nb0 + c.nb1, 4));
+    const int items4 = g.tiles_x * g.tiles_y * tz4 * c.n_tiles * std::max(1, std::min(c.ncb(), 4));
     g.zt = (items4 < 64 && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
   }
   g.tiles_z = (p->D[lvl] + g.zt - 1) / g.zt;
   g.tiles = g.tiles_x * g.tiles_y * g.tiles_z;
   // the split factor must not depend on the batch: a window's result is bit-identical whatever it is batched with
   (void)B;
-  const int ctas = g.tiles * c.n_tiles, ncb = c.nb0 + c.nb1;
+  const int ctas = g.tiles * c.n_tiles, ncb = c.ncb();
   g.ksplit = 1;
   if (ncb >= 2 && ctas < 96) g.ksplit = std::max(1, std::min(ncb, 148 / ctas));
   return g;
@@ -353,11 +371,22 @@ static int stats_nseg(long long vox) {
   return (int)std::min<long long>(std::max<long long>(n, 1), 128);
 }
 
+static inline bool is_prec(const dunet_plan* p) { return (p->cfg.flags & DUNET_FLAG_FP32X3) != 0; }
+// activation of `ch` (padded) channels at U-Net level `lvl`, batch B, stored at workspace offset `off`: in fp32x3 mode the
+// low part follows the high part
+static inline Act ws_act(const dunet_plan* p, uint8_t* ws, size_t off, int ch, int lvl, int B) {
+  Act a;
+  a.hi = reinterpret_cast<bf16*>(ws + off);
+  a.lo = is_prec(p) ? a.hi + (size_t)B * ch * (size_t)p->V[lvl] : nullptr;
+  return a;
+}
+
 static WsLayout ws_layout(const dunet_plan* p, int B) {
   WsLayout L;
   size_t off = 0;
+  const size_t pm = is_prec(p) ? 2 : 1;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  auto act = [&](int ch, int lvl) -> size_t { return (size_t)((size_t)B * ch * (size_t)p->V[lvl] * sizeof(bf16)); };
+  auto act = [&](int ch, int lvl) -> size_t { return (size_t)(pm * (size_t)B * ch * (size_t)p->V[lvl] * sizeof(bf16)); };
   L.in_pack = take(act(p->in_pad, 0));
   size_t raw_max = 0, part_max = 0, ss_max = 0, split_max = 0;
   auto upd = [&](const ConvW& c, int lvl) {
@@ -394,8 +423,17 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
 static long long* g_conv_dbg = nullptr;  // optional per-CTA timeline buffer (tools only)
 static int g_num_sms = 0;
 
+static int ensure_num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return 0;
+}
+
 template <int CB_CH, int N_TILE, int ZT, int MODE>
-static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTcArgs& a, cudaStream_t st) {
+static int launch_conv_tc(const CUtensorMap (&t)[4], const ConvTcArgs& a, cudaStream_t st) {
   using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
   static bool attr_set = false;
   auto kern = conv3d_tc_kernel<CB_CH, N_TILE, ZT, MODE>;
@@ -404,23 +442,18 @@ static int launch_conv_tc(const CUtensorMap& t0, const CUtensorMap& t1, const Co
     attr_set = true;
   }
   const long long items = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
-  if (!g_num_sms) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  TRY(ensure_num_sms());
   // persistent: one CTA per SM (each may own all 512 TMEM columns) walking the work items round-robin
   const long long grid = std::min<long long>(items, (long long)g_num_sms);
   TRY(prof_begin(MODE == MODE_CONV3 ? PROF_CONV : PROF_DECONV, st));
-  kern<<<(unsigned)grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, a);
+  kern<<<(unsigned)grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
   return 0;
 }
 
 template <int CB_CH>
-static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const ConvTc64Args& a, unsigned* grid_out,
-                            cudaStream_t st) {
+static int launch_conv_tc64(const CUtensorMap (&t)[4], const ConvTc64Args& a, unsigned* grid_out, cudaStream_t st) {
   using Cfg = ConvTc64<CB_CH, CONV_ZT>;
   static bool attr_set = false;
   auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT>;
@@ -428,61 +461,78 @@ static int launch_conv_tc64(const CUtensorMap& t0, const CUtensorMap& t1, const 
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  if (!g_num_sms) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  TRY(ensure_num_sms());
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.batch;
   const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
   *grid_out = grid;
   TRY(prof_begin(PROF_CONV, st));
-  kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t0, t1, a);
+  kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
   return 0;
 }
 
-// 3x3x3 conv -> raw bf16 output + InstanceNorm partial statistics [plane][*nseg_out][16] in `partial`
-static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const bf16* src1, bf16* out, float* partial,
-                    float* splitk, int* nseg_out, int lvl, int B, cudaStream_t st) {
+// block list of a conv: bf16 mode [S0, S1]; fp32x3 mode [S0.hi, S1.hi | S0.lo, S1.lo | S0.hi, S1.hi] (tensor maps 0..3 =
+// S0.hi, S1.hi, S0.lo, S1.lo), matching the packed weight blocks [W.hi | W.hi | W.lo]
+static ConvSegs make_segs(int nb0, int chunks0, int nb1, int chunks1, bool prec) {
+  ConvSegs sg;
+  memset(&sg, 0, sizeof sg);
+  auto add = [&](int tm, int nb, int chunks) {
+    if (nb > 0) { sg.s[sg.n].tmap = tm; sg.s[sg.n].nblocks = nb; sg.s[sg.n].chunks = chunks; ++sg.n; sg.ncb += nb; }
+  };
+  add(0, nb0, chunks0); add(1, nb1, chunks1);
+  if (prec) { add(2, nb0, chunks0); add(3, nb1, chunks1); add(0, nb0, chunks0); add(1, nb1, chunks1); }
+  return sg;
+}
+
+// 3x3x3 conv -> raw output (bf16, or hi + lo in fp32x3 mode) + InstanceNorm partial statistics [plane][*nseg_out][16]
+static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act out, float* partial, float* splitk,
+                    int* nseg_out, int lvl, int B, cudaStream_t st) {
   const int D = p->D[lvl], H = p->H[lvl], W = p->W[lvl];
   const int planes = B * (c.coutp / 8);
+  const bool prec = c.parts == 3;
+  if (prec && (!src0.lo || !out.lo || (c.nb1 > 0 && !src1.lo))) return fail(DUNET_E_STATE, "fp32x3 conv needs hi + lo tensors");
   if (p->cfg.flags & DUNET_FLAG_REF_CONV) {
+    if (prec) return fail(DUNET_E_UNSUPPORTED, "DUNET_FLAG_REF_CONV and DUNET_FLAG_FP32X3 are mutually exclusive");
     if (!c.w32) return fail(DUNET_E_STATE, "DUNET_FLAG_REF_CONV needs DUNET_FLAG_KEEP_FP32_WEIGHTS");
     // the debug kernel writes only the chunks holding real output channels; padded chunks must still be zero
-    CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)B * c.coutp * p->V[lvl] * sizeof(bf16), st));
+    CUDA_TRY(cudaMemsetAsync(out.hi, 0, (size_t)B * c.coutp * p->V[lvl] * sizeof(bf16), st));
     conv3d_ref_kernel<<<grid_for((long long)B * ((c.coutr + 7) / 8) * p->V[lvl], 128, 148 * 64), 128, 0, st>>>(
-        src0, c.c0r, c.c0p / 8, src1, c.c1r, c.c1p / 8, c.w32, out, c.coutr, c.coutp / 8, D, H, W, B, c.rot);
+        src0.hi, c.c0r, c.c0p / 8, src1.hi, c.c1r, c.c1p / 8, c.w32, out.hi, c.coutr, c.coutp / 8, D, H, W, B, c.rot);
     LAUNCH_CHECK();
     if (partial) {
       const int nseg = stats_nseg(p->V[lvl]);
-      in_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(out, partial, p->V[lvl], nseg);
+      in_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(out.hi, partial, p->V[lvl], nseg);
       LAUNCH_CHECK();
       *nseg_out = nseg;
     }
     return 0;
   }
   if (g_prof_on) g_prof_flops += 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
-  CUtensorMap t0, t1;
-  TRY(make_act_tmap(&t0, src0, B * (c.c0p / 8), D, H, W, c.cb_ch / 8, 1));
-  if (c.nb1 > 0) TRY(make_act_tmap(&t1, src1, B * (c.c1p / 8), D, H, W, c.cb_ch / 8, 1));
-  else t1 = t0;
+  CUtensorMap t[4];
+  TRY(make_act_tmap(&t[0], src0.hi, B * (c.c0p / 8), D, H, W, c.cb_ch / 8, 1));
+  t[1] = t[2] = t[3] = t[0];
+  if (c.nb1 > 0) TRY(make_act_tmap(&t[1], src1.hi, B * (c.c1p / 8), D, H, W, c.cb_ch / 8, 1));
+  if (prec) {
+    TRY(make_act_tmap(&t[2], src0.lo, B * (c.c0p / 8), D, H, W, c.cb_ch / 8, 1));
+    if (c.nb1 > 0) TRY(make_act_tmap(&t[3], src1.lo, B * (c.c1p / 8), D, H, W, c.cb_ch / 8, 1));
+  }
+  const ConvSegs segs = make_segs(c.nb0, c.c0p / 8, c.nb1, c.c1p / 8, prec);
   const ConvGeom g = conv_geom(p, c, lvl, B);
   const int want_split = (splitk && partial) ? g.ksplit : 1;
   if (c.packed64 && want_split == 1 && g.zt == CONV_ZT && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {
     ConvTc64Args b;
     memset(&b, 0, sizeof b);
-    b.w = c.packed64; b.out = out; b.stats = partial; b.nb0 = c.nb0; b.nb1 = c.nb1; b.chunks0 = c.c0p / 8; b.chunks1 = c.c1p / 8;
+    b.w = c.packed64; b.out = out.hi; b.out_lo = out.lo; b.stats = partial; b.segs = segs;
     b.D = D; b.H = H; b.W = W; b.tiles_x = g.tiles_x; b.tiles_y = g.tiles_y; b.tiles_z = g.tiles_z; b.batch = B;
     unsigned grid = 0;
-    TRY(c.cb_ch == 32 ? launch_conv_tc64<32>(t0, t1, b, &grid, st) : launch_conv_tc64<64>(t0, t1, b, &grid, st));
+    TRY(c.cb_ch == 32 ? launch_conv_tc64<32>(t, b, &grid, st) : launch_conv_tc64<64>(t, b, &grid, st));
     if (partial) *nseg_out = (int)grid;  // one statistics row per persistent CTA and sample
     return 0;
   }
   ConvTcArgs a;
   memset(&a, 0, sizeof a);
-  a.w = c.packed; a.out = out; a.nb0 = c.nb0; a.nb1 = c.nb1; a.chunks0 = c.c0p / 8; a.chunks1 = c.c1p / 8;
+  a.w = c.packed; a.out = out.hi; a.out_lo = out.lo; a.segs = segs;
   a.cout = c.coutp; a.D = D; a.H = H; a.W = W;
   a.tiles_x = g.tiles_x; a.tiles_y = g.tiles_y; a.tiles_z = g.tiles_z; a.n_tiles = c.n_tiles; a.batch = B;
   a.ksplit = want_split;
@@ -490,19 +540,19 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
   if (a.ksplit > 1) a.out_partial = splitk;
   else a.stats = partial;
   int rc;
-  if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
-  else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 64 && g.zt == 2) rc = launch_conv_tc<64, 64, 2, MODE_CONV3>(t0, t1, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 128 && g.zt == 2) rc = launch_conv_tc<64, 128, 2, MODE_CONV3>(t0, t1, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3>(t0, t1, a, st);
+  if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3>(t, a, st);
+  else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3>(t, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 64 && g.zt == 2) rc = launch_conv_tc<64, 64, 2, MODE_CONV3>(t, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 128 && g.zt == 2) rc = launch_conv_tc<64, 128, 2, MODE_CONV3>(t, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3>(t, a, st);
+  else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3>(t, a, st);
   else return fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
   TRY(rc);
   if (a.ksplit > 1) {
     const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
     TRY(prof_begin(PROF_SPLITK, st));
     splitk_reduce_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(
-        splitk, a.ksplit, (long long)B * c.coutp * p->V[lvl], out, partial, p->V[lvl], nseg);
+        splitk, a.ksplit, (long long)B * c.coutp * p->V[lvl], out.hi, out.lo, partial, p->V[lvl], nseg);
     LAUNCH_CHECK();
     TRY(prof_end(st));
     *nseg_out = nseg;
@@ -513,27 +563,39 @@ static int run_conv(const dunet_plan* p, const ConvW& c, const bf16* src0, const
 }
 
 // statistics (reduced in the kernel prologue) -> fused normalise/activation(/bias/add/pool)
-static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, const float* partial, int nseg,
-                    const float* bias, const bf16* add, bf16* out, bf16* pooled, int lvl, int B, cudaStream_t st) {
+static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* partial, int nseg, const float* bias, Act add,
+                    Act out, Act pooled, int lvl, int B, cudaStream_t st) {
   const int planes = B * (c.coutp / 8);
+  const bool prec = raw.lo != nullptr;
   NormActArgs a;
-  a.raw = raw; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias; a.add = add;
-  a.out = out; a.pooled = pooled; a.chunks = c.coutp / 8; a.D = p->D[lvl]; a.H = p->H[lvl]; a.W = p->W[lvl];
+  a.raw = raw.hi; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias; a.add = add.hi;
+  a.out = out.hi; a.pooled = pooled.hi; a.raw_lo = raw.lo; a.add_lo = add.lo; a.out_lo = out.lo; a.pooled_lo = pooled.lo;
+  a.chunks = c.coutp / 8; a.D = p->D[lvl]; a.H = p->H[lvl]; a.W = p->W[lvl];
   a.eps = 1e-5f; a.slope = 0.1f;
   // ~4 resident blocks per SM in total, each streaming a long contiguous range of one 8-channel plane (the
   // statistics prologue is paid once per block)
   const int per_plane = std::max(1, (148 * 8 + planes - 1) / planes);
   if (g_prof_on)  // one bf16 read + one bf16 write per element (+ read of the residual, + 1/8 write of the pooled tensor)
-    g_prof_bytes[PROF_NORM] += (double)B * c.coutp * (double)p->V[lvl] * (4.0 + (add ? 2.0 : 0.0) + (pooled ? 0.25 : 0.0));
+    g_prof_bytes[PROF_NORM] += (prec ? 2.0 : 1.0) * B * c.coutp * (double)p->V[lvl] * (4.0 + (add.hi ? 2.0 : 0.0) + (pooled.hi ? 0.25 : 0.0));
   TRY(prof_begin(PROF_NORM, st));
-  if (pooled) {
+  if (pooled.hi) {
     const dim3 grid(grid_for(p->V[lvl] / 4, NORM_THREADS, per_plane), planes);
-    if (add) norm_act_pool_kernel<true><<<grid, NORM_THREADS, 0, st>>>(a);
-    else norm_act_pool_kernel<false><<<grid, NORM_THREADS, 0, st>>>(a);
+    if (prec) {
+      if (add.hi) norm_act_pool_kernel<true, true><<<grid, NORM_THREADS, 0, st>>>(a);
+      else norm_act_pool_kernel<false, true><<<grid, NORM_THREADS, 0, st>>>(a);
+    } else {
+      if (add.hi) norm_act_pool_kernel<true, false><<<grid, NORM_THREADS, 0, st>>>(a);
+      else norm_act_pool_kernel<false, false><<<grid, NORM_THREADS, 0, st>>>(a);
+    }
   } else {
-    const dim3 grid(grid_for(p->V[lvl], NORM_THREADS * 4, per_plane), planes);
-    if (add) norm_act_kernel<true><<<grid, NORM_THREADS, 0, st>>>(a);
-    else norm_act_kernel<false><<<grid, NORM_THREADS, 0, st>>>(a);
+    const dim3 grid(grid_for(p->V[lvl], NORM_THREADS * (prec ? 2 : 4), per_plane), planes);
+    if (prec) {
+      if (add.hi) norm_act_kernel<true, true><<<grid, NORM_THREADS, 0, st>>>(a);
+      else norm_act_kernel<false, true><<<grid, NORM_THREADS, 0, st>>>(a);
+    } else {
+      if (add.hi) norm_act_kernel<true, false><<<grid, NORM_THREADS, 0, st>>>(a);
+      else norm_act_kernel<false, false><<<grid, NORM_THREADS, 0, st>>>(a);
+    }
   }
   LAUNCH_CHECK();
   TRY(prof_end(st));
@@ -543,47 +605,50 @@ static int run_norm(const dunet_plan* p, const ConvW& c, const bf16* raw, const 
 // conv -> IN -> LReLU (+temb bias) -> conv -> IN -> LReLU (+add, +pool).  With `defer_last_norm` the second normalise
 // pass is left to the consumer (the final 1x1 conv kernel applies it on the fly): the raw output stays in ws.raw and
 // *nseg_out describes its statistics rows in ws.partial.
-static int run_twoconv(const dunet_plan* p, const TwoConvW& t, const bf16* src0, const bf16* src1, const float* temb_bias,
-                       const bf16* add, bf16* out, bf16* pooled, int lvl, int B, uint8_t* ws, const WsLayout& L,
-                       cudaStream_t st, bool defer_last_norm = false, int* nseg_out = nullptr) {
-  bf16* raw = reinterpret_cast<bf16*>(ws + L.raw);
-  bf16* mid = reinterpret_cast<bf16*>(ws + L.mid);
+static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src1, const float* temb_bias, Act add, Act out,
+                       Act pooled, int lvl, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
+                       bool defer_last_norm = false, int* nseg_out = nullptr) {
+  const Act raw_a = ws_act(p, ws, L.raw, t.a.coutp, lvl, B), mid = ws_act(p, ws, L.mid, t.a.coutp, lvl, B);
+  const Act raw_b = ws_act(p, ws, L.raw, t.b.coutp, lvl, B);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
   float* splitk = reinterpret_cast<float*>(ws + L.splitk);
   int nseg = 0;
-  TRY(run_conv(p, t.a, src0, src1, raw, partial, splitk, &nseg, lvl, B, st));
-  TRY(run_norm(p, t.a, raw, partial, nseg, temb_bias, nullptr, mid, nullptr, lvl, B, st));
-  TRY(run_conv(p, t.b, mid, nullptr, raw, partial, splitk, &nseg, lvl, B, st));
+  TRY(run_conv(p, t.a, src0, src1, raw_a, partial, splitk, &nseg, lvl, B, st));
+  TRY(run_norm(p, t.a, raw_a, partial, nseg, temb_bias, Act(), mid, Act(), lvl, B, st));
+  TRY(run_conv(p, t.b, mid, Act(), raw_b, partial, splitk, &nseg, lvl, B, st));
   if (defer_last_norm) {
     *nseg_out = nseg;
     return 0;
   }
-  TRY(run_norm(p, t.b, raw, partial, nseg, nullptr, add, out, pooled, lvl, B, st));
+  TRY(run_norm(p, t.b, raw_b, partial, nseg, nullptr, add, out, pooled, lvl, B, st));
   return 0;
 }
 
-static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf16* out, int lvl_in, int B, cudaStream_t st) {
+static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, int lvl_in, int B, cudaStream_t st) {
+  const bool prec = d.parts == 3;
   if (p->cfg.flags & DUNET_FLAG_REF_CONV) {  // CUDA-core debug kernel
+    if (prec) return fail(DUNET_E_UNSUPPORTED, "DUNET_FLAG_REF_CONV and DUNET_FLAG_FP32X3 are mutually exclusive");
     const long long total = (long long)B * (d.coutp / 8) * 8 * p->V[lvl_in];
-    deconv2_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in, d.cinp, d.packed, d.bias, out, d.coutp, p->D[lvl_in],
+    deconv2_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in.hi, d.cinp, d.packed, d.bias, out.hi, d.coutp, p->D[lvl_in],
                                                                     p->H[lvl_in], p->W[lvl_in], B);
     LAUNCH_CHECK();
     return 0;
   }
   const int D = p->D[lvl_in], H = p->H[lvl_in], W = p->W[lvl_in];
-  CUtensorMap t0;
-  TRY(make_act_tmap(&t0, in, B * (d.cinp / 8), D, H, W, 8, 0));
-  if (d.cinp <= 128 && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {  // persistent, HBM-write-bound variant
+  CUtensorMap t[4];
+  TRY(make_act_tmap(&t[0], in.hi, B * (d.cinp / 8), D, H, W, 8, 0));
+  t[1] = t[2] = t[3] = t[0];
+  if (prec) {
+    if (!in.lo || !out.lo) return fail(DUNET_E_STATE, "fp32x3 transposed conv needs hi + lo tensors");
+    TRY(make_act_tmap(&t[1], in.lo, B * (d.cinp / 8), D, H, W, 8, 0));
+  }
+  if (d.cinp <= 128 && !prec && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {  // persistent, HBM-write-bound variant
     DeconvTcArgs b;
     memset(&b, 0, sizeof b);
-    b.w = d.packed_tc; b.out = out; b.bias = d.bias; b.chunks_in = d.cinp / 8; b.cout = d.coutp; b.D = D; b.H = H; b.W = W;
+    b.w = d.packed_tc; b.out = out.hi; b.bias = d.bias; b.chunks_in = d.cinp / 8; b.cout = d.coutp; b.D = D; b.H = H; b.W = W;
     b.tiles_x = (W + CONV_TX - 1) / CONV_TX; b.tiles_y = (H + CONV_TY - 1) / CONV_TY; b.tiles_z = (D + 1) / 2;
     b.n_tiles = 8 * d.coutp / 128; b.batch = B; b.dbg = g_conv_dbg;
-    if (!g_num_sms) {
-      int dev = 0;
-      CUDA_TRY(cudaGetDevice(&dev));
-      CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    TRY(ensure_num_sms());
     const long long tiles = (long long)b.tiles_x * b.tiles_y * b.tiles_z * B;
     const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
     static bool attr1 = false, attr2 = false;
@@ -591,10 +656,10 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf1
     TRY(prof_begin(PROF_DECONV, st));
     if (d.cinp == 64) {
       if (!attr1) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<1, 2>::SMEM_BYTES)); attr1 = true; }
-      deconv2_tc_kernel<1, 2><<<grid, CONV_THREADS, DeconvTc<1, 2>::SMEM_BYTES, st>>>(t0, b);
+      deconv2_tc_kernel<1, 2><<<grid, CONV_THREADS, DeconvTc<1, 2>::SMEM_BYTES, st>>>(t[0], b);
     } else {
       if (!attr2) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<2, 2>::SMEM_BYTES)); attr2 = true; }
-      deconv2_tc_kernel<2, 2><<<grid, CONV_THREADS, DeconvTc<2, 2>::SMEM_BYTES, st>>>(t0, b);
+      deconv2_tc_kernel<2, 2><<<grid, CONV_THREADS, DeconvTc<2, 2>::SMEM_BYTES, st>>>(t[0], b);
     }
     LAUNCH_CHECK();
     TRY(prof_end(st));
@@ -602,11 +667,19 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, const bf16* in, bf1
   }
   ConvTcArgs a;
   memset(&a, 0, sizeof a);
-  a.w = d.packed_tc; a.out = out; a.bias = d.bias; a.nb0 = d.cinp / 64; a.nb1 = 0; a.chunks0 = d.cinp / 8; a.chunks1 = 0;
+  a.w = d.packed_tc; a.out = out.hi; a.out_lo = out.lo; a.bias = d.bias;
+  // fp32x3: [in.hi | in.lo | in.hi] x [W.hi | W.hi | W.lo]
+  a.segs = make_segs(d.cinp / 64, d.cinp / 8, 0, 0, false);
+  if (prec) {
+    a.segs.n = 3; a.segs.ncb = 3 * (d.cinp / 64);
+    a.segs.s[1] = a.segs.s[0]; a.segs.s[1].tmap = 1;
+    a.segs.s[2] = a.segs.s[0];
+  }
   a.cout = d.coutp; a.D = D; a.H = H; a.W = W;
   a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + 1) / 2;
   a.n_tiles = 8 * d.coutp / 128; a.ksplit = 1; a.batch = B; a.dbg = nullptr;
-  return launch_conv_tc<64, 128, 2, MODE_DECONV2>(t0, t0, a, st);
+  if (g_prof_on) g_prof_bytes[PROF_DECONV] += (prec ? 2.0 : 1.0) * B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
+  return launch_conv_tc<64, 128, 2, MODE_DECONV2>(t, a, st);
 }
 
 static int check_call(const dunet_plan* p, int B, const void* ws) {
@@ -617,37 +690,43 @@ static int check_call(const dunet_plan* p, int B, const void* ws) {
   return 0;
 }
 
-static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
-  bf16* in_pack = reinterpret_cast<bf16*>(ws + L.in_pack);
-  pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
-      image, p->cfg.in_channels, nullptr, 0, in_pack, p->in_pad, p->V[0], B);
+static int launch_pack(const dunet_plan* p, const float* src0, int c0, const float* src1, int c1, Act dst, int c_pad,
+                       long long vox, int B, cudaStream_t st) {
+  (void)p;
+  pack_c8_kernel<<<grid_for((long long)B * (c_pad / 8) * vox, 256), 256, 0, st>>>(src0, c0, src1, c1, dst.hi, dst.lo, c_pad, vox, B);
   LAUNCH_CHECK();
+  return 0;
+}
+
+static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
+  const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
+  TRY(launch_pack(p, image, p->cfg.in_channels, nullptr, 0, in_pack, p->in_pad, p->V[0], B, st));
   for (int l = 0; l < 5; ++l) {
-    const bf16* src = l ? reinterpret_cast<bf16*>(ws + L.epool[l]) : in_pack;
-    bf16* pooled = l < 4 ? reinterpret_cast<bf16*>(ws + L.epool[l + 1]) : nullptr;
-    TRY(run_twoconv(p, p->enc[l], src, nullptr, nullptr, nullptr, reinterpret_cast<bf16*>(ws + L.emb[l]), pooled, l, B,
-                    ws, L, st));
+    const Act src = l ? ws_act(p, ws, L.epool[l], p->fp[l - 1], l, B) : in_pack;
+    const Act pooled = l < 4 ? ws_act(p, ws, L.epool[l + 1], p->fp[l], l + 1, B) : Act();
+    TRY(run_twoconv(p, p->enc[l], src, Act(), nullptr, Act(), ws_act(p, ws, L.emb[l], p->fp[l], l, B), pooled, l, B, ws, L, st));
   }
   return 0;
 }
 
-// U-Net body given in_pack = cat([image, x_t]); leaves u1 in ws.u[1]
+// U-Net body given in_pack = cat([image, x_t]); leaves the RAW output of upcat_1.conv_1 in ws.raw
 static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
                      int* last_nseg) {
-  bf16* in_pack = reinterpret_cast<bf16*>(ws + L.in_pack);
+  const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
   for (int l = 0; l < 5; ++l) {
-    const bf16* src = l ? reinterpret_cast<bf16*>(ws + L.dpool[l]) : in_pack;
-    bf16* pooled = l < 4 ? reinterpret_cast<bf16*>(ws + L.dpool[l + 1]) : nullptr;
-    TRY(run_twoconv(p, p->den[l], src, nullptr, temb_row + p->temb_off[l], reinterpret_cast<bf16*>(ws + L.emb[l]),
-                    reinterpret_cast<bf16*>(ws + L.x[l]), pooled, l, B, ws, L, st));
+    const Act src = l ? ws_act(p, ws, L.dpool[l], p->fp[l - 1], l, B) : in_pack;
+    const Act pooled = l < 4 ? ws_act(p, ws, L.dpool[l + 1], p->fp[l], l + 1, B) : Act();
+    TRY(run_twoconv(p, p->den[l], src, Act(), temb_row + p->temb_off[l], ws_act(p, ws, L.emb[l], p->fp[l], l, B),
+                    ws_act(p, ws, L.x[l], p->fp[l], l, B), pooled, l, B, ws, L, st));
   }
-  const bf16* prev = reinterpret_cast<bf16*>(ws + L.x[4]);
+  Act prev = ws_act(p, ws, L.x[4], p->fp[4], 4, B);
   for (int l = 4; l >= 1; --l) {
-    bf16* up = reinterpret_cast<bf16*>(ws + L.up[l]);
+    const Act up = ws_act(p, ws, L.up[l], p->upp[l], l - 1, B);
     TRY(run_deconv(p, p->dec[l], prev, up, l, B, st));
-    TRY(run_twoconv(p, p->upc[l], reinterpret_cast<bf16*>(ws + L.x[l - 1]), up, temb_row + p->temb_off[5 + (4 - l)], nullptr,
-                    reinterpret_cast<bf16*>(ws + L.u[l]), nullptr, l - 1, B, ws, L, st, /*defer_last_norm=*/l == 1, last_nseg));
-    prev = reinterpret_cast<bf16*>(ws + L.u[l]);
+    const Act u = ws_act(p, ws, L.u[l], p->uoutp[l], l - 1, B);
+    TRY(run_twoconv(p, p->upc[l], ws_act(p, ws, L.x[l - 1], p->fp[l - 1], l - 1, B), up, temb_row + p->temb_off[5 + (4 - l)],
+                    Act(), u, Act(), l - 1, B, ws, L, st, /*defer_last_norm=*/l == 1, last_nseg));
+    prev = u;
   }
   return 0;
 }
@@ -669,7 +748,8 @@ static int launch_temb(dunet_plan* p, const int* d_t, int rows, float* table, cu
 // fills the part of FinalDdimArgs that folds upcat_1.conv_1's InstanceNorm + LeakyReLU into the final 1x1 conv
 static void final_args_common(dunet_plan* p, FinalDdimArgs& a, uint8_t* ws, const WsLayout& L, int nseg, int B) {
   memset(&a, 0, sizeof a);
-  a.feat = reinterpret_cast<bf16*>(ws + L.raw); a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
+  const Act feat = ws_act(p, ws, L.raw, p->fp[5], 0, B);
+  a.feat = feat.hi; a.feat_lo = feat.lo; a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
   a.partial = reinterpret_cast<float*>(ws + L.partial); a.nseg = nseg; a.gamma = p->upc[1].b.gamma; a.beta = p->upc[1].b.beta;
   a.eps = 1e-5f; a.slope = 0.1f; a.in_pad = p->in_pad; a.vox = p->V[0]; a.batch = B;
 }
@@ -677,13 +757,19 @@ static void final_args_common(dunet_plan* p, FinalDdimArgs& a, uint8_t* ws, cons
 static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) {
   const dim3 grid(grid_for((a.vox + 15) / 16 * 32, FINAL_THREADS, std::max(1, 148 * 3 / a.batch)), a.batch);
   if (a.F != 64 && a.F != 128) return fail(DUNET_E_UNSUPPORTED, "final conv: padded features[5] must be 64 or 128");
-#define DUNET_FINAL(NT)                                                                   \
-  do {                                                                                    \
-    if (a.F == 64) final_ddim_kernel<NT, 4><<<grid, FINAL_THREADS, 0, st>>>(a);           \
-    else final_ddim_kernel<NT, 8><<<grid, FINAL_THREADS, 0, st>>>(a);                     \
+  const bool prec = a.feat_lo != nullptr;
+#define DUNET_FINAL(NT)                                                                            \
+  do {                                                                                             \
+    if (prec) {                                                                                    \
+      if (a.F == 64) final_ddim_kernel<NT, 4, true><<<grid, FINAL_THREADS, 0, st>>>(a);            \
+      else final_ddim_kernel<NT, 8, true><<<grid, FINAL_THREADS, 0, st>>>(a);                      \
+    } else {                                                                                       \
+      if (a.F == 64) final_ddim_kernel<NT, 4, false><<<grid, FINAL_THREADS, 0, st>>>(a);           \
+      else final_ddim_kernel<NT, 8, false><<<grid, FINAL_THREADS, 0, st>>>(a);                     \
+    }                                                                                              \
   } while (0)
   if (g_prof_on)  // feature map read once (bf16) + fp32 state x_t and sum(x0) read+written + bf16 re-pack of the next input
-    g_prof_bytes[PROF_FINAL] += (double)a.batch * (double)a.vox * (2.0 * a.F + (a.x_t ? 16.0 * a.C : 0.0) + (a.logits_out ? 4.0 * a.C : 0.0) + (a.next_in ? 2.0 * a.C : 0.0));
+    g_prof_bytes[PROF_FINAL] += (double)a.batch * (double)a.vox * ((prec ? 4.0 : 2.0) * a.F + (a.x_t ? 16.0 * a.C : 0.0) + (a.logits_out ? 4.0 * a.C : 0.0) + (a.next_in ? 2.0 * a.C : 0.0));
   TRY(prof_begin(PROF_FINAL, st));
   if (a.C <= 8) DUNET_FINAL(1);
   else if (a.C <= 16) DUNET_FINAL(2);
@@ -778,8 +864,11 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
   if (cfg->batch_max < 1 || cfg->num_steps < 1 || cfg->num_steps > 1000) return fail(DUNET_E_INVALID, "bad batch_max / num_steps");
   if (pad_to(cfg->features[5], 64) > FINAL_MAX_F) return fail(DUNET_E_UNSUPPORTED, "features[5] > %d not implemented", FINAL_MAX_F);
 
+  if ((cfg->flags & DUNET_FLAG_FP32X3) && (cfg->flags & DUNET_FLAG_REF_CONV))
+    return fail(DUNET_E_UNSUPPORTED, "DUNET_FLAG_REF_CONV and DUNET_FLAG_FP32X3 are mutually exclusive");
   dunet_plan* p = new dunet_plan();
   p->cfg = *cfg;
+  const int parts = (cfg->flags & DUNET_FLAG_FP32X3) ? 3 : 1;
   p->C = cfg->num_classes;
   for (int l = 0; l < 5; ++l) {
     p->D[l] = cfg->patch[0] >> l; p->H[l] = cfg->patch[1] >> l; p->W[l] = cfg->patch[2] >> l;
@@ -796,22 +885,22 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
   // encoder (no temb), pretrained/basic_unet.py:491-494
   for (int l = 0; l < 5; ++l) {
     TwoConvW& e = p->enc[l];
-    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0]);
-    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l]);
-    e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l]);
+    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], parts);
+    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts);
+    e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts);
     TwoConvW& d = p->den[l];
     d.has_temb = true;
-    if (l == 0) { d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0]); d.a.rot = 1; }
-    else d.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l]);
-    d.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l]);
+    if (l == 0) { d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0], parts); d.a.rot = 1; }
+    else d.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts);
+    d.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts);
   }
   for (int l = 4; l >= 1; --l) {
     TwoConvW& u = p->upc[l];
     u.has_temb = true;
-    u.a.shape(p->fr[l - 1], p->fp[l - 1], p->upr[l], p->upp[l], p->uoutr[l]);  // cat([skip, up]) denoiser.py:190
-    u.b.shape(p->uoutr[l], p->uoutp[l], 0, 0, p->uoutr[l]);
+    u.a.shape(p->fr[l - 1], p->fp[l - 1], p->upr[l], p->upp[l], p->uoutr[l], parts);  // cat([skip, up]) denoiser.py:190
+    u.b.shape(p->uoutr[l], p->uoutp[l], 0, 0, p->uoutr[l], parts);
     DeconvW& d = p->dec[l];
-    d.cinr = p->fr[l]; d.cinp = p->fp[l]; d.coutr = p->upr[l]; d.coutp = p->upp[l];
+    d.cinr = p->fr[l]; d.cinp = p->fp[l]; d.coutr = p->upr[l]; d.coutp = p->upp[l]; d.parts = parts;
   }
   // checkpoint keys
   add_twoconv_slots(p, "embed_model.conv_0", &p->enc[0]);
@@ -870,13 +959,13 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       if (!c->packed) TRY(dev_alloc(p, (void**)&c->packed, c->packed_elems() * sizeof(bf16)));
       const int cinr = c->c0r + c->c1r;
       pack_conv_w_kernel<<<grid_for((long long)c->packed_elems(), 256), 256, 0, st>>>(
-          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->nb0 + c->nb1, c->n_tiles, c->rot);
+          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->ncb(), c->n_tiles, c->rot, c->parts);
       LAUNCH_CHECK();
       if (c->coutp == 64) {
-        const size_t n64 = (size_t)(c->nb0 + c->nb1) * 9 * c->cb_ch * 192;
+        const size_t n64 = c->packed64_elems();
         if (!c->packed64) TRY(dev_alloc(p, (void**)&c->packed64, n64 * sizeof(bf16)));
         pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(src, c->packed64, c->coutr, cinr, c->c0r, c->c0p,
-                                                                             c->c1r, c->cb_ch, c->nb0 + c->nb1, c->rot);
+                                                                             c->c1r, c->cb_ch, c->ncb(), c->rot, c->parts);
         LAUNCH_CHECK();
       }
       if (p->cfg.flags & DUNET_FLAG_KEEP_FP32_WEIGHTS) {
@@ -923,8 +1012,9 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       if (!d->packed) TRY(dev_alloc(p, (void**)&d->packed, n * sizeof(bf16)));
       pack_deconv_w_kernel<<<grid_for((long long)n, 256), 256, 0, st>>>(src, d->packed, d->cinr, d->coutr, d->cinp, d->coutp);
       LAUNCH_CHECK();
-      if (!d->packed_tc) TRY(dev_alloc(p, (void**)&d->packed_tc, n * sizeof(bf16)));
-      pack_deconv_tc_w_kernel<<<grid_for((long long)n, 256), 256, 0, st>>>(src, d->packed_tc, d->cinr, d->coutr, d->cinp, d->coutp);
+      if (!d->packed_tc) TRY(dev_alloc(p, (void**)&d->packed_tc, n * d->parts * sizeof(bf16)));
+      pack_deconv_tc_w_kernel<<<grid_for((long long)n * d->parts, 256), 256, 0, st>>>(src, d->packed_tc, d->cinr, d->coutr, d->cinp,
+                                                                                      d->coutp, d->parts);
       LAUNCH_CHECK();
       d->have_w = true;
       break;
@@ -1000,8 +1090,9 @@ int dunet_get_embedding(dunet_plan* p, int32_t level, float* out, int32_t B, voi
   TRY(check_call(p, B, workspace));
   if (level < 0 || level > 4 || !out) return fail(DUNET_E_INVALID, "bad level / NULL out");
   const WsLayout L = ws_layout(p, B);
+  const Act e = ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B);
   unpack_c8_kernel<<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + L.emb[level]), p->fp[level], out, p->fr[level], p->V[level], B);
+      e.hi, e.lo, p->fp[level], out, p->fr[level], p->V[level], B);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1010,11 +1101,8 @@ int dunet_set_embedding(dunet_plan* p, int32_t level, const float* in, int32_t B
   TRY(check_call(p, B, workspace));
   if (level < 0 || level > 4 || !in) return fail(DUNET_E_INVALID, "bad level / NULL in");
   const WsLayout L = ws_layout(p, B);
-  pack_c8_kernel<<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, p->fr[level], nullptr, 0, reinterpret_cast<bf16*>(static_cast<uint8_t*>(workspace) + L.emb[level]), p->fp[level],
-      p->V[level], B);
-  LAUNCH_CHECK();
-  return 0;
+  return launch_pack(p, in, p->fr[level], nullptr, 0, ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B),
+                     p->fp[level], p->V[level], B, static_cast<cudaStream_t>(stream));
 }
 
 int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int32_t t_original, float* logits_out,
@@ -1032,9 +1120,7 @@ int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int3
     CUDA_TRY(cudaMemcpyAsync(p->d_tmap + row, &t_original, sizeof(int), cudaMemcpyHostToDevice, st));
     TRY(launch_temb(p, p->d_tmap + row, 1, p->temb_table + (size_t)row * p->temb_row, st));
   }
-  pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
-      x_t, p->C, image, p->cfg.in_channels, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
-  LAUNCH_CHECK();
+  TRY(launch_pack(p, x_t, p->C, image, p->cfg.in_channels, ws_act(p, ws, L.in_pack, p->in_pad, 0, B), p->in_pad, p->V[0], B, st));
   int nseg = 0;
   TRY(unet_body(p, p->temb_table + (size_t)row * p->temb_row, B, ws, L, st, &nseg));
   FinalDdimArgs a;
@@ -1059,9 +1145,8 @@ static int ddim_sample_impl(dunet_plan* p, const float* image, const float* nois
   LAUNCH_CHECK();
   state_to_vm_kernel<<<sgrid, 256, 0, st>>>(nullptr, acc, p->C, CP, p->V[0], B);
   LAUNCH_CHECK();
-  pack_c8_kernel<<<grid_for((long long)B * (p->in_pad / 8) * p->V[0], 256), 256, 0, st>>>(
-      noise, p->C, image, p->cfg.in_channels, reinterpret_cast<bf16*>(ws + L.in_pack), p->in_pad, p->V[0], B);
-  LAUNCH_CHECK();
+  const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
+  TRY(launch_pack(p, noise, p->C, image, p->cfg.in_channels, in_pack, p->in_pad, p->V[0], B, st));
   for (int i = p->n_steps - 1, k = 0; i >= 0; --i, ++k) {  // gaussian_diffusion.py:694 indices high -> low
     int nseg = 0;
     TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st, &nseg));
@@ -1069,7 +1154,8 @@ static int ddim_sample_impl(dunet_plan* p, const float* image, const float* nois
     final_args_common(p, a, ws, L, nseg, B);
     a.image = image; a.x_t = x_t; a.acc = acc;
     a.logits_out = per_step_logits ? per_step_logits + (size_t)k * per_step_stride : nullptr;
-    a.next_in = i > 0 ? reinterpret_cast<bf16*>(ws + L.in_pack) : nullptr;
+    a.next_in = i > 0 ? in_pack.hi : nullptr;
+    a.next_in_lo = i > 0 ? in_pack.lo : nullptr;
     a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
     TRY(launch_final(p, a, st));
   }
@@ -1158,26 +1244,30 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
                        float* out, int32_t B, const int32_t dims[3], int32_t use_ref, void* stream) {
   if (!src0 || !weight || !out || !dims || c0 < 1 || cout < 1 || B < 1) return fail(DUNET_E_INVALID, "bad argument");
   if (c1 > 0 && !src1) return fail(DUNET_E_INVALID, "src1 is NULL but c1 > 0");
+  if (use_ref < 0 || use_ref > 4) return fail(DUNET_E_INVALID, "use_ref_kernel must be 0..4");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool prec = use_ref >= 3;
+  const bool generic_only = use_ref == 2 || use_ref == 4;
   dunet_plan tmp;  // only geometry fields are used by run_conv
   memset(&tmp.cfg, 0, sizeof tmp.cfg);
-  tmp.cfg.flags = use_ref == 1 ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : 0;
+  tmp.cfg.flags = use_ref == 1 ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : (prec ? DUNET_FLAG_FP32X3 : 0);
   tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
   tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
   ConvW c;
   const bool small = (c1 == 0 && c0 <= 32);
-  c.shape(c0, small ? 32 : pad_to(c0, 64), c1, c1 > 0 ? pad_to(c1, 64) : 0, cout);
+  c.shape(c0, small ? 32 : pad_to(c0, 64), c1, c1 > 0 ? pad_to(c1, 64) : 0, cout, prec ? 3 : 1);
   if (c1 > 0 && (c0 % 8)) return fail(DUNET_E_UNSUPPORTED, "concat needs c0 %% 8 == 0");
   const long long vox = tmp.V[0];
-  bf16 *a0 = nullptr, *a1 = nullptr, *raw = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&a0, (size_t)B * c.c0p * vox * sizeof(bf16), st));
-  CUDA_TRY(cudaMallocAsync((void**)&raw, (size_t)B * c.coutp * vox * sizeof(bf16), st));
-  pack_c8_kernel<<<grid_for((long long)B * (c.c0p / 8) * vox, 256), 256, 0, st>>>(src0, c0, nullptr, 0, a0, c.c0p, vox, B);
-  LAUNCH_CHECK();
+  const size_t pm = prec ? 2 : 1;
+  Act a0, a1, raw;
+  CUDA_TRY(cudaMallocAsync((void**)&a0.hi, pm * B * c.c0p * vox * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&raw.hi, pm * B * c.coutp * vox * sizeof(bf16), st));
+  if (prec) { a0.lo = a0.hi + (size_t)B * c.c0p * vox; raw.lo = raw.hi + (size_t)B * c.coutp * vox; }
+  TRY(launch_pack(&tmp, src0, c0, nullptr, 0, a0, c.c0p, vox, B, st));
   if (c1 > 0) {
-    CUDA_TRY(cudaMallocAsync((void**)&a1, (size_t)B * c.c1p * vox * sizeof(bf16), st));
-    pack_c8_kernel<<<grid_for((long long)B * (c.c1p / 8) * vox, 256), 256, 0, st>>>(src1, c1, nullptr, 0, a1, c.c1p, vox, B);
-    LAUNCH_CHECK();
+    CUDA_TRY(cudaMallocAsync((void**)&a1.hi, pm * B * c.c1p * vox * sizeof(bf16), st));
+    if (prec) a1.lo = a1.hi + (size_t)B * c.c1p * vox;
+    TRY(launch_pack(&tmp, src1, c1, nullptr, 0, a1, c.c1p, vox, B, st));
   }
   int rc = 0;
   if (use_ref == 1) {
@@ -1185,26 +1275,26 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   } else {
     CUDA_TRY(cudaMallocAsync((void**)&c.packed, c.packed_elems() * sizeof(bf16), st));
     pack_conv_w_kernel<<<grid_for((long long)c.packed_elems(), 256), 256, 0, st>>>(
-        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.nb0 + c.nb1, c.n_tiles, 0);
+        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.ncb(), c.n_tiles, 0, c.parts);
     LAUNCH_CHECK();
-    if (c.coutp == 64 && use_ref != 2) {
-      const size_t n64 = (size_t)(c.nb0 + c.nb1) * 9 * c.cb_ch * 192;
+    if (c.coutp == 64 && !generic_only) {
+      const size_t n64 = c.packed64_elems();
       CUDA_TRY(cudaMallocAsync((void**)&c.packed64, n64 * sizeof(bf16), st));
       pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(weight, c.packed64, c.coutr, c0 + c1, c.c0r, c.c0p,
-                                                                           c.c1r, c.cb_ch, c.nb0 + c.nb1, 0);
+                                                                           c.c1r, c.cb_ch, c.ncb(), 0, c.parts);
       LAUNCH_CHECK();
     }
   }
   int nseg_unused = 0;
   rc = run_conv(&tmp, c, a0, a1, raw, nullptr, nullptr, &nseg_unused, 0, B, st);
   if (rc == 0) {
-    unpack_c8_kernel<<<grid_for((long long)B * (c.coutp / 8) * vox, 256), 256, 0, st>>>(raw, c.coutp, out, cout, vox, B);
+    unpack_c8_kernel<<<grid_for((long long)B * (c.coutp / 8) * vox, 256), 256, 0, st>>>(raw.hi, raw.lo, c.coutp, out, cout, vox, B);
     g_launches.fetch_add(1);
     if (cudaGetLastError() != cudaSuccess) rc = fail(DUNET_E_CUDA, "unpack launch failed");
   }
-  cudaFreeAsync(a0, st);
-  cudaFreeAsync(raw, st);
-  if (a1) cudaFreeAsync(a1, st);
+  cudaFreeAsync(a0.hi, st);
+  cudaFreeAsync(raw.hi, st);
+  if (a1.hi) cudaFreeAsync(a1.hi, st);
   if (c.packed) cudaFreeAsync(c.packed, st);
   if (c.packed64) cudaFreeAsync(c.packed64, st);
   return rc;
@@ -1213,37 +1303,41 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
 int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, const float* bias, int32_t cout, float* out,
                          int32_t B, const int32_t dims[3], int32_t use_ref, void* stream) {
   if (!src || !weight || !bias || !out || !dims || cin < 1 || cout < 1 || B < 1) return fail(DUNET_E_INVALID, "bad argument");
+  if (use_ref < 0 || use_ref > 4) return fail(DUNET_E_INVALID, "use_ref_kernel must be 0..4");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool prec = use_ref >= 3;
   dunet_plan tmp;
   memset(&tmp.cfg, 0, sizeof tmp.cfg);
-  tmp.cfg.flags = use_ref == 1 ? DUNET_FLAG_REF_CONV : (use_ref == 2 ? DUNET_FLAG_GENERIC_CONV : 0);
+  tmp.cfg.flags = use_ref == 1 ? DUNET_FLAG_REF_CONV : ((use_ref == 2 || use_ref == 4) ? DUNET_FLAG_GENERIC_CONV : 0);
+  if (prec) tmp.cfg.flags |= DUNET_FLAG_FP32X3;
   tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
   tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
   DeconvW d;
-  d.cinr = cin; d.cinp = pad_to(cin, 64); d.coutr = cout; d.coutp = pad_to(cout, 64);
+  d.cinr = cin; d.cinp = pad_to(cin, 64); d.coutr = cout; d.coutp = pad_to(cout, 64); d.parts = prec ? 3 : 1;
   const long long vox = tmp.V[0];
   const size_t nw = 8ull * d.cinp * d.coutp;
-  bf16 *a0 = nullptr, *o = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&a0, (size_t)B * d.cinp * vox * sizeof(bf16), st));
-  CUDA_TRY(cudaMallocAsync((void**)&o, (size_t)B * d.coutp * vox * 8 * sizeof(bf16), st));
+  const size_t pm = prec ? 2 : 1;
+  Act a0, o;
+  CUDA_TRY(cudaMallocAsync((void**)&a0.hi, pm * B * d.cinp * vox * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&o.hi, pm * B * d.coutp * vox * 8 * sizeof(bf16), st));
+  if (prec) { a0.lo = a0.hi + (size_t)B * d.cinp * vox; o.lo = o.hi + (size_t)B * d.coutp * vox * 8; }
   CUDA_TRY(cudaMallocAsync((void**)&d.packed, nw * sizeof(bf16), st));
-  CUDA_TRY(cudaMallocAsync((void**)&d.packed_tc, nw * sizeof(bf16), st));
+  CUDA_TRY(cudaMallocAsync((void**)&d.packed_tc, nw * d.parts * sizeof(bf16), st));
   CUDA_TRY(cudaMallocAsync((void**)&d.bias, d.coutp * sizeof(float), st));
-  pack_c8_kernel<<<grid_for((long long)B * (d.cinp / 8) * vox, 256), 256, 0, st>>>(src, cin, nullptr, 0, a0, d.cinp, vox, B);
-  LAUNCH_CHECK();
+  TRY(launch_pack(&tmp, src, cin, nullptr, 0, a0, d.cinp, vox, B, st));
   pack_deconv_w_kernel<<<grid_for((long long)nw, 256), 256, 0, st>>>(weight, d.packed, cin, cout, d.cinp, d.coutp);
   LAUNCH_CHECK();
-  pack_deconv_tc_w_kernel<<<grid_for((long long)nw, 256), 256, 0, st>>>(weight, d.packed_tc, cin, cout, d.cinp, d.coutp);
+  pack_deconv_tc_w_kernel<<<grid_for((long long)nw * d.parts, 256), 256, 0, st>>>(weight, d.packed_tc, cin, cout, d.cinp, d.coutp, d.parts);
   LAUNCH_CHECK();
   copy_pad_rows_kernel<<<1, 256, 0, st>>>(bias, d.bias, 1, cout, 1, d.coutp);
   LAUNCH_CHECK();
   int rc = run_deconv(&tmp, d, a0, o, 0, B, st);
   if (rc == 0) {
-    unpack_c8_kernel<<<grid_for((long long)B * (d.coutp / 8) * vox * 8, 256), 256, 0, st>>>(o, d.coutp, out, cout, vox * 8, B);
+    unpack_c8_kernel<<<grid_for((long long)B * (d.coutp / 8) * vox * 8, 256), 256, 0, st>>>(o.hi, o.lo, d.coutp, out, cout, vox * 8, B);
     g_launches.fetch_add(1);
     if (cudaGetLastError() != cudaSuccess) rc = fail(DUNET_E_CUDA, "unpack launch failed");
   }
-  cudaFreeAsync(a0, st); cudaFreeAsync(o, st); cudaFreeAsync(d.packed, st); cudaFreeAsync(d.packed_tc, st); cudaFreeAsync(d.bias, st);
+  cudaFreeAsync(a0.hi, st); cudaFreeAsync(o.hi, st); cudaFreeAsync(d.packed, st); cudaFreeAsync(d.packed_tc, st); cudaFreeAsync(d.bias, st);
   return rc;
 }
 

@@ -29,12 +29,37 @@ __device__ __forceinline__ BF8 float_to_bf8(const float (&f)[8]) {
   return b;
 }
 
+// fp32x3 ("split-bf16") mode: a tensor is a PAIR of C8-planar bf16 tensors, value = hi + lo, where hi = bf16(v) and
+// lo = bf16(v - hi) (v - hi is exact in fp32), so the pair carries ~16 mantissa bits.  `lo == nullptr` is the plain
+// bf16 mode everywhere below.
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx8, const float (&f)[8]) {
+  const BF8 h = float_to_bf8(f);
+  reinterpret_cast<BF8*>(hi)[idx8] = h;
+  if (lo) {
+    float hf[8], r[8];
+    bf8_to_float(h, hf);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = f[j] - hf[j];
+    reinterpret_cast<BF8*>(lo)[idx8] = float_to_bf8(r);
+  }
+}
+__device__ __forceinline__ void load_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long idx8, float (&f)[8]) {
+  bf8_to_float(reinterpret_cast<const BF8*>(hi)[idx8], f);
+  if (lo) {
+    float g[8];
+    bf8_to_float(reinterpret_cast<const BF8*>(lo)[idx8], g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += g[j];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pack: fp32 NCDHW (two concatenated sources) -> bf16 C8-planar with c_pad channels (zero padded).
 // Used for the denoiser input cat([image, x_t]) (reference denoiser.py:298) and for boundary tensors.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void pack_c8_kernel(const float* __restrict__ src0, int c0, const float* __restrict__ src1, int c1,
-                               __nv_bfloat16* __restrict__ dst, int c_pad, long long vox, int batch) {
+                               __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo, int c_pad, long long vox,
+                               int batch) {
   const int chunks = c_pad / 8;
   long long total = (long long)batch * chunks * vox;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -51,13 +76,13 @@ __global__ void pack_c8_kernel(const float* __restrict__ src0, int c0, const flo
       else if (c < c0 + c1) val = src1[((long long)n * c1 + (c - c0)) * vox + v];
       f[j] = val;
     }
-    reinterpret_cast<BF8*>(dst)[i] = float_to_bf8(f);
+    store_split(dst, dst_lo, i, f);
   }
 }
 
-// unpack: bf16 C8-planar -> fp32 NCDHW (first c_out channels).
-__global__ void unpack_c8_kernel(const __nv_bfloat16* __restrict__ src, int c_pad, float* __restrict__ dst, int c_out,
-                                 long long vox, int batch) {
+// unpack: bf16 C8-planar (hi [+ lo]) -> fp32 NCDHW (first c_out channels).
+__global__ void unpack_c8_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ src_lo, int c_pad,
+                                 float* __restrict__ dst, int c_out, long long vox, int batch) {
   const int chunks = c_pad / 8;
   long long total = (long long)batch * chunks * vox;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -66,7 +91,7 @@ __global__ void unpack_c8_kernel(const __nv_bfloat16* __restrict__ src, int c_pa
     int ck = (int)((i / vox) % chunks);
     int n = (int)(i / (vox * chunks));
     float f[8];
-    bf8_to_float(reinterpret_cast<const BF8*>(src)[i], f);
+    load_split(src, src_lo, i, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int c = ck * 8 + j;
@@ -129,11 +154,11 @@ __global__ void __launch_bounds__(STATS_THREADS) in_stats_kernel(const __nv_bflo
 __global__ void __launch_bounds__(STATS_THREADS) splitk_reduce_stats_kernel(const float* __restrict__ part, int ksplit,
                                                                             long long split_stride /*floats*/,
                                                                             __nv_bfloat16* __restrict__ raw,
+                                                                            __nv_bfloat16* __restrict__ raw_lo,
                                                                             float* __restrict__ partial, long long vox,
                                                                             int nseg) {
   const int plane = blockIdx.y, seg = blockIdx.x;
   const float4* p = reinterpret_cast<const float4*>(part) + (long long)plane * vox * 2;
-  BF8* o = reinterpret_cast<BF8*>(raw) + (long long)plane * vox;
   long long per = (vox + nseg - 1) / nseg;
   long long lo = seg * per, hi = min(vox, lo + per);
   float s[8], q[8];
@@ -148,7 +173,7 @@ __global__ void __launch_bounds__(STATS_THREADS) splitk_reduce_stats_kernel(cons
       f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
       f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
     }
-    o[v] = float_to_bf8(f);
+    store_split(raw, raw_lo, (long long)plane * vox + v, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j] += f[j];
@@ -196,6 +221,8 @@ struct NormActArgs {
   const __nv_bfloat16* add;  // C8-planar tensor added after activation (encoder feature) or nullptr
   __nv_bfloat16* out;
   __nv_bfloat16* pooled;   // POOL only
+  const __nv_bfloat16 *raw_lo, *add_lo;  // fp32x3 mode: low parts (all four set, or all nullptr)
+  __nv_bfloat16 *out_lo, *pooled_lo;
   int chunks;              // C/8
   int D, H, W;
   float eps, slope;
@@ -252,10 +279,11 @@ __device__ __forceinline__ void norm_apply(float (&f)[8], const float* sc, const
   }
 }
 
-// ADD: the encoder-feature residual is present.  Both variants keep 4 independent 16-byte loads per tensor in flight per
-// thread; __launch_bounds__ asks for 3-4 resident blocks per SM so ~64 KB of loads are outstanding per SM.
-template <bool ADD>
-__global__ void __launch_bounds__(NORM_THREADS, ADD ? 3 : 4) norm_act_kernel(NormActArgs a) {
+// ADD: the encoder-feature residual is present.  PREC: fp32x3 mode (hi + lo pairs in, hi + lo pairs out).  All variants
+// keep 4 independent 16-byte loads per tensor in flight per thread; __launch_bounds__ asks for 3-4 resident blocks per
+// SM so ~64 KB of loads are outstanding per SM.
+template <bool ADD, bool PREC>
+__global__ void __launch_bounds__(NORM_THREADS, (ADD || PREC) ? 3 : 4) norm_act_kernel(NormActArgs a) {
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;  // n*chunks + chunk
@@ -263,17 +291,20 @@ __global__ void __launch_bounds__(NORM_THREADS, ADD ? 3 : 4) norm_act_kernel(Nor
   const long long vox = (long long)a.D * a.H * a.W;
   const BF8* __restrict__ in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
   const BF8* __restrict__ add = reinterpret_cast<const BF8*>(a.add) + plane * vox;
-  BF8* __restrict__ out = reinterpret_cast<BF8*>(a.out) + plane * vox;
-  constexpr int U = 4;
+  const BF8* __restrict__ in_lo = reinterpret_cast<const BF8*>(a.raw_lo) + plane * vox;
+  const BF8* __restrict__ add_lo = reinterpret_cast<const BF8*>(a.add_lo) + plane * vox;
+  constexpr int U = PREC ? 2 : 4;
   const long long stride = (long long)gridDim.x * NORM_THREADS;
   for (long long v0 = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; v0 < vox; v0 += stride * U) {
-    BF8 xin[U], ain[U];
+    BF8 xin[U], ain[U], xlo[U], alo[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long v = v0 + u * stride;
       if (v < vox) {
         xin[u] = in[v];
+        if constexpr (PREC) xlo[u] = in_lo[v];
         if constexpr (ADD) ain[u] = add[v];
+        if constexpr (ADD && PREC) alo[u] = add_lo[v];
       }
     }
 #pragma unroll
@@ -282,14 +313,26 @@ __global__ void __launch_bounds__(NORM_THREADS, ADD ? 3 : 4) norm_act_kernel(Nor
       if (v < vox) {
         float f[8];
         bf8_to_float(xin[u], f);
+        if constexpr (PREC) {
+          float g[8];
+          bf8_to_float(xlo[u], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += g[j];
+        }
         norm_apply(f, sc, sh, bi, a.slope);
         if constexpr (ADD) {
           float g[8];
           bf8_to_float(ain[u], g);
+          if constexpr (PREC) {
+            float h[8];
+            bf8_to_float(alo[u], h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] += h[j];
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
-        out[v] = float_to_bf8(f);
+        store_split(a.out, PREC ? a.out_lo : nullptr, plane * vox + v, f);
       }
     }
   }
@@ -297,10 +340,10 @@ __global__ void __launch_bounds__(NORM_THREADS, ADD ? 3 : 4) norm_act_kernel(Nor
 
 // Same pass + the 2x2x2 max-pool of the result (Down, denoiser.py:105-108).  thread = (x, y/2, z/2): it handles the four
 // (dz, dy) voxels at its x (lanes run along x: every load/store instruction covers 512 contiguous bytes) and completes
-// the pool with its x^1 neighbour through a shuffle; the pooled tensor is built from the ROUNDED outputs so that
-// pooled == maxpool(out) exactly.
-template <bool ADD>
-__global__ void __launch_bounds__(NORM_THREADS, 3) norm_act_pool_kernel(NormActArgs a) {
+// the pool with its x^1 neighbour through a shuffle; the pooled tensor is built from the ROUNDED outputs (bf16, or the
+// hi + lo sum in fp32x3 mode) so that pooled == maxpool(out) exactly.
+template <bool ADD, bool PREC>
+__global__ void __launch_bounds__(NORM_THREADS, PREC ? 2 : 3) norm_act_pool_kernel(NormActArgs a) {
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;
@@ -308,23 +351,28 @@ __global__ void __launch_bounds__(NORM_THREADS, 3) norm_act_pool_kernel(NormActA
   const long long vox = (long long)a.D * a.H * a.W;
   const BF8* __restrict__ in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
   const BF8* __restrict__ add = reinterpret_cast<const BF8*>(a.add) + plane * vox;
+  const BF8* __restrict__ in_lo = reinterpret_cast<const BF8*>(a.raw_lo) + plane * vox;
+  const BF8* __restrict__ add_lo = reinterpret_cast<const BF8*>(a.add_lo) + plane * vox;
   BF8* __restrict__ out = reinterpret_cast<BF8*>(a.out) + plane * vox;
+  BF8* __restrict__ out_lo = reinterpret_cast<BF8*>(a.out_lo) + plane * vox;
   const int D2 = a.D / 2, H2 = a.H / 2, W2 = a.W / 2;
-  BF8* __restrict__ pooled = reinterpret_cast<BF8*>(a.pooled) + plane * ((long long)D2 * H2 * W2);
+  const long long pvox = (long long)D2 * H2 * W2;
   const long long total = (long long)D2 * H2 * a.W;  // even: W is even
   const int lane = threadIdx.x & 31;
   for (long long p = blockIdx.x * (long long)NORM_THREADS + threadIdx.x; p - lane < total;
        p += (long long)gridDim.x * NORM_THREADS) {
     const bool valid = p < total;
     const int x = (int)(p % a.W), y2 = (int)((p / a.W) % H2), z2 = (int)(p / ((long long)a.W * H2));
-    BF8 xin[4], ain[4];
+    BF8 xin[4], ain[4], xlo[4], alo[4];
     long long vv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       vv[k] = ((long long)(2 * z2 + (k >> 1)) * a.H + (2 * y2 + (k & 1))) * a.W + x;
       if (valid) {
         xin[k] = in[vv[k]];
+        if constexpr (PREC) xlo[k] = in_lo[vv[k]];
         if constexpr (ADD) ain[k] = add[vv[k]];
+        if constexpr (ADD && PREC) alo[k] = add_lo[vv[k]];
       }
     }
     float m[8];
@@ -335,10 +383,22 @@ __global__ void __launch_bounds__(NORM_THREADS, 3) norm_act_pool_kernel(NormActA
       for (int k = 0; k < 4; ++k) {
         float f[8];
         bf8_to_float(xin[k], f);
+        if constexpr (PREC) {
+          float g[8];
+          bf8_to_float(xlo[k], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += g[j];
+        }
         norm_apply(f, sc, sh, bi, a.slope);
         if constexpr (ADD) {
           float g[8];
           bf8_to_float(ain[k], g);
+          if constexpr (PREC) {
+            float h[8];
+            bf8_to_float(alo[k], h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] += h[j];
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
@@ -346,13 +406,25 @@ __global__ void __launch_bounds__(NORM_THREADS, 3) norm_act_pool_kernel(NormActA
         out[vv[k]] = o;
         float r[8];
         bf8_to_float(o, r);
+        if constexpr (PREC) {
+          float d[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = f[j] - r[j];
+          const BF8 ol = float_to_bf8(d);
+          out_lo[vv[k]] = ol;
+          float rl[8];
+          bf8_to_float(ol, rl);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] += rl[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], r[j]);
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], 1));
-    if (valid && !(x & 1)) pooled[((long long)z2 * H2 + y2) * W2 + (x >> 1)] = float_to_bf8(m);
+    if (valid && !(x & 1))
+      store_split(a.pooled, PREC ? a.pooled_lo : nullptr, plane * pvox + ((long long)z2 * H2 + y2) * W2 + (x >> 1), m);
   }
 }
 
@@ -412,6 +484,8 @@ __global__ void __launch_bounds__(256) deconv2_kernel(const __nv_bfloat16* __res
 // ---------------------------------------------------------------------------------------------------------------
 struct FinalDdimArgs {
   const __nv_bfloat16* feat;  // RAW output of the last conv (or, with partial == nullptr, the activated u1), C8-planar
+  const __nv_bfloat16* feat_lo;  // fp32x3 mode: low part of feat
+  __nv_bfloat16* next_in_lo;     // fp32x3 mode: low part of next_in
   int F;                      // feature channels (multiple of 16, <= 128)
   const float* partial;       // InstanceNorm partial statistics of `feat` [n*F/8 + chunk][nseg][16] or nullptr
   int nseg;
@@ -447,7 +521,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // NT = number of 8-class column tiles (C <= 8 * NT); NKS = F / 16 k-steps
-template <int NT, int NKS>
+template <int NT, int NKS, bool PREC>
 __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs a) {
   // B fragments of the weights: [k-step][n-tile][hi|lo][b0|b1][lane]
   __shared__ uint32_t wfrag[(FINAL_MAX_F / 16) * NT * 2 * 2 * 32];
@@ -491,6 +565,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
   // (voxels per window < 2^26 and every per-sample tensor < 2^31 elements: checked on the host.)
   const unsigned vox = (unsigned)a.vox;
   const uint32_t* __restrict__ fw = reinterpret_cast<const uint32_t*>(a.feat) + (size_t)n * fch * vox * 4 + t;
+  const uint32_t* __restrict__ fw_lo = reinterpret_cast<const uint32_t*>(a.feat_lo) + (size_t)n * fch * vox * 4 + t;
   const float* __restrict__ img_n = a.image ? a.image + (size_t)n * vox : nullptr;
   // voxel-major state: a quad of lanes (t = 0..3) covers 8 consecutive classes of one voxel with float2 accesses, so
   // the 8 voxels x NT*8 classes a warp touches per access form one contiguous run
@@ -498,6 +573,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
   float2* acc_n = a.acc ? reinterpret_cast<float2*>(a.acc) + (size_t)n * vox * (NT * 4) + t : nullptr;
   float* lg_n = a.logits_out ? a.logits_out + (size_t)n * a.C * vox : nullptr;
   uint32_t* np_n = a.next_in ? reinterpret_cast<uint32_t*>(a.next_in) + (size_t)n * (a.in_pad / 8) * vox * 4 + t : nullptr;
+  uint32_t* np_lo_n = (PREC && a.next_in) ? reinterpret_cast<uint32_t*>(a.next_in_lo) + (size_t)n * (a.in_pad / 8) * vox * 4 + t : nullptr;
   unsigned cls_off[NT][2];
   bool cls_ok[NT][2], cls_img[NT][2];
 #pragma unroll
@@ -529,7 +605,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
     const float img0 = (np_n && ok0) ? img_n[v0] : 0.f;
     const float img1 = (np_n && ok1) ? img_n[v1] : 0.f;
     // A fragments: rows (voxels) v0 / v1, channel pairs (2t, 2t+1) of chunk 2ks and of chunk 2ks+1
-    uint32_t af[NKS][4];
+    uint32_t af[NKS][4], al[PREC ? NKS : 1][4];
 #pragma unroll
     for (int ks = 0; ks < NKS; ++ks) {
       const unsigned c0 = (2 * ks) * vox, c1 = c0 + vox;
@@ -537,6 +613,12 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
       af[ks][1] = ok1 ? __ldg(fw + (c0 + v1) * 4) : 0u;
       af[ks][2] = ok0 ? __ldg(fw + (c1 + v0) * 4) : 0u;
       af[ks][3] = ok1 ? __ldg(fw + (c1 + v1) * 4) : 0u;
+      if constexpr (PREC) {
+        al[ks][0] = ok0 ? __ldg(fw_lo + (c0 + v0) * 4) : 0u;
+        al[ks][1] = ok1 ? __ldg(fw_lo + (c0 + v1) * 4) : 0u;
+        al[ks][2] = ok0 ? __ldg(fw_lo + (c1 + v0) * 4) : 0u;
+        al[ks][3] = ok1 ? __ldg(fw_lo + (c1 + v1) * 4) : 0u;
+      }
     }
     float d[NT][4];
 #pragma unroll
@@ -550,12 +632,20 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = ks * 16 + (j >> 1) * 8 + 2 * t;
-          const float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&af[ks][j]));
+          float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&af[ks][j]));
+          if constexpr (PREC) {
+            const float2 xl = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&al[ks][j]));
+            x.x += xl.x; x.y += xl.y;
+          }
           const float2 sc2 = *reinterpret_cast<const float2*>(nsc + c), sh2 = *reinterpret_cast<const float2*>(nsh + c);
           float y0 = fmaf(x.x, sc2.x, sh2.x), y1 = fmaf(x.y, sc2.y, sh2.y);
           y0 = fmaxf(y0, y0 * a.slope);  // LeakyReLU with 0 < slope < 1
           y1 = fmaxf(y1, y1 * a.slope);
           af[ks][j] = pack_bf16x2(y0, y1);
+          if constexpr (PREC) {
+            const float2 h = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&af[ks][j]));
+            al[ks][j] = pack_bf16x2(y0 - h.x, y1 - h.y);
+          }
         }
       }
 #pragma unroll
@@ -563,6 +653,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
         const uint32_t* wf = wfrag + ((ks * NT + nt) * 4) * 32 + lane;
         mma_bf16_16816(d[nt], af[ks], wf[0], wf[32]);
         mma_bf16_16816(d[nt], af[ks], wf[64], wf[96]);
+        if constexpr (PREC) mma_bf16_16816(d[nt], al[ks], wf[0], wf[32]);
       }
     }
     // d[nt][0..1]: voxel v0, classes nt*8 + 2t, +1 ; d[nt][2..3]: voxel v1, same classes
@@ -597,8 +688,15 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
         if (ok1) { xt_n[v1 * (NT * 4) + nt * 4] = make_float2(xp4[2], xp4[3]); acc_n[v1 * (NT * 4) + nt * 4] = make_float2(ac4[2], ac4[3]); }
       }
       if (np_n && nt * 8 < a.in_pad) {
-        if (ok0) np_n[(nt * vox + v0) * 4] = pack_bf16x2(nxt[0], nxt[1]);
-        if (ok1) np_n[(nt * vox + v1) * 4] = pack_bf16x2(nxt[2], nxt[3]);
+        const uint32_t h0 = pack_bf16x2(nxt[0], nxt[1]), h1 = pack_bf16x2(nxt[2], nxt[3]);
+        if (ok0) np_n[(nt * vox + v0) * 4] = h0;
+        if (ok1) np_n[(nt * vox + v1) * 4] = h1;
+        if constexpr (PREC) {
+          const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h0));
+          const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h1));
+          if (ok0) np_lo_n[(nt * vox + v0) * 4] = pack_bf16x2(nxt[0] - f0.x, nxt[1] - f0.y);
+          if (ok1) np_lo_n[(nt * vox + v1) * 4] = pack_bf16x2(nxt[2] - f1.x, nxt[3] - f1.y);
+        }
       }
     }
   }

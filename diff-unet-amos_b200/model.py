@@ -308,7 +308,7 @@ class DiffUNetB200(nn.Module):
     def __init__(self, spatial_dims: int = 3, in_channels: int = 3, out_channels: int = 1, image_size=96,
                  spatial_size=96, features: Sequence[int] = DEFAULT_FEATURES, dropout: float = 0.2,
                  timesteps: int = 1000, mode: str = "train", *, num_steps: int = 10, batch_max: int = 4,
-                 debug_flags: int = 0):
+                 debug_flags: int = 0, precision: str = "bf16"):
         super().__init__()
         if spatial_dims != 3:
             raise NotImplementedError("only spatial_dims == 3")
@@ -322,7 +322,12 @@ class DiffUNetB200(nn.Module):
         # window shape (spatial_size, image_size, image_size) as Engine.infer builds it (engine.py:169)
         hw = (image_size, image_size) if isinstance(image_size, int) else tuple(image_size)
         self.patch = (int(spatial_size),) + tuple(int(v) for v in hw)
+        if precision not in ("bf16", "fp32x3"):
+            raise ValueError('precision must be "bf16" (2e-2 gate) or "fp32x3" (split-bf16 operands, 1e-4 gate; SURVEY 8d)')
+        self.precision = precision
         self.num_steps, self.batch_max, self.debug_flags = int(num_steps), int(batch_max), int(debug_flags)
+        if precision == "fp32x3":
+            self.debug_flags |= _lib.DUNET_FLAG_FP32X3
         self.timesteps = timesteps
         self.schedule = DdimSchedule.build(self.num_steps, timesteps)
         holder = _Node()

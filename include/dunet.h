@@ -45,6 +45,11 @@ enum {
                                     +3 % at batch 4, large loss at batch 2 -- the persistent conv kernels use a static tile
                                     schedule and do not share SMs gracefully; off by default) */
 
+#define DUNET_FLAG_FP32X3 16u /* fp32-class precision mode ("fp32x3"): every activation and weight is a
+                                 hi + lo pair of bf16 tensors and each product is formed as hi*hi + lo*hi + hi*lo on the
+                                 same tcgen05 kernels (3x the MMA work, 2x the activation traffic, fp32 accumulation and
+                                 fp32 elementwise math as in bf16 mode).  Meets north_star's 1e-4 / 99.9 % argmax gates */
+
 typedef struct dunet_plan dunet_plan;
 
 /* Mirrors DiffUNet.__init__(spatial_dims=3, in_channels, out_channels, image_size, spatial_size, features, ...)
@@ -127,7 +132,8 @@ int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channel
 
 /* Stand-alone operator (also the unit-test seam of the tensor-core kernel): y = conv3d(cat([src0, src1]), weight),
  * 3x3x3, stride 1, zero padding 1, no bias.  fp32 NCDHW in/out, bf16 operands + fp32 accumulation inside.
- * use_ref_kernel: 0 = production tcgen05 kernels, 1 = CUDA-core debug kernel, 2 = generic tcgen05 kernel only.
+ * use_ref_kernel: 0 = production tcgen05 kernels, 1 = CUDA-core debug kernel, 2 = generic tcgen05 kernel only,
+ * 3 / 4 = as 0 / 2 in fp32x3 mode (operands split into hi + lo bf16 pairs, see DUNET_FLAG_FP32X3).
  * replaces: nn.Conv3d inside MONAI Convolution (denoiser.py:56-58).  use_ref_kernel != 0 selects the debug CUDA-core
  * kernel.  Allocates its own scratch with cudaMallocAsync on `stream`. */
 int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t c1, const float* weight, int32_t cout,

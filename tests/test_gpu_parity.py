@@ -15,6 +15,7 @@ from tests.util import SMALL, load_golden, rel_l2, seeded_image, seeded_noise
 pytestmark = pytest.mark.gpu
 
 BF16_TOL = 2e-2  # north_star: per-patch logits within 2e-2 relative error in bf16
+FP32_TOL = 1e-4  # north_star: ... or 1e-4 in fp32 (precision="fp32x3": split-bf16 operands on the same tcgen05 kernels)
 
 
 def _p(t):
@@ -270,3 +271,87 @@ def test_odd_class_counts(cout):
         e = oracle_model.encoder_forward(sd, image[1:2])
         ref = oracle_ddim.ddim_sample_window(lambda x, t: oracle_model.denoiser_forward(sd, x, t, image[1:2], e), noise[1:2])
     assert rel_l2(out[1:2].cpu(), ref["sample_return"]) < BF16_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp32x3 mode (DUNET_FLAG_FP32X3): hi + lo bf16 operand pairs, three MMAs per product, fp32 everywhere else
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c0,c1,cout,B,dims", [(64, 0, 64, 1, (16, 16, 16)), (17, 0, 64, 2, (16, 32, 16)),
+                                              (64, 64, 64, 1, (16, 16, 16)), (128, 0, 128, 1, (12, 12, 12)),
+                                              (256, 256, 256, 1, (6, 6, 6)), (512, 0, 512, 2, (2, 2, 2)),
+                                              (8, 0, 16, 1, (16, 16, 16))])
+def test_conv3x3x3_fp32x3_vs_fp64(c0, c1, cout, B, dims):
+    """fp32x3 conv == fp64 conv3d of the UN-rounded fp32 operands to ~1e-5 (vs 4e-3 for one bf16 rounding)."""
+    torch.manual_seed(c0 + cout)
+    s0 = torch.randn(B, c0, *dims, device="cuda")
+    s1 = torch.randn(B, c1, *dims, device="cuda") if c1 else None
+    w = torch.randn(cout, c0 + c1, 3, 3, 3, device="cuda") / (27 * (c0 + c1)) ** 0.5
+    xin = s0 if s1 is None else torch.cat([s0, s1], 1)
+    exp = F.conv3d(xin.double(), w.double(), padding=1).float()
+    for kernel in (3, 4):  # 3: production dispatch, 4: generic tcgen05 kernel only
+        got = _conv_op(s0, w, s1, ref=kernel)
+        err = rel_l2(got, exp)
+        print(f"fp32x3 conv kernel {kernel}: rel-l2 {err:.3e}")
+        assert err < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,B,dims", [(64, 64, 1, (8, 16, 8)), (512, 256, 1, (2, 2, 2)), (128, 128, 2, (7, 9, 5))])
+def test_deconv2x2x2_fp32x3_vs_fp64(cin, cout, B, dims):
+    torch.manual_seed(cin + cout)
+    x = torch.randn(B, cin, *dims, device="cuda")
+    w = torch.randn(cin, cout, 2, 2, 2, device="cuda") / cin ** 0.5
+    b = torch.randn(cout, device="cuda")
+    exp = F.conv_transpose3d(x.double(), w.double(), b.double(), stride=2).float()
+    out = torch.zeros_like(exp)
+    _lib.check(_lib.load().dunet_op_deconv2x2x2(_p(x), cin, _p(w), _p(b), cout, _p(out), B, _lib.i32x3(dims), 3,
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert rel_l2(out, exp) < 2e-5
+
+
+@pytest.mark.parametrize("tag,cout,S,feats", [("S32_C2_small", 2, 32, SMALL), ("S48_C16_small", 16, 48, SMALL),
+                                              ("S32_C3_default", 3, 32, oracle_model.DEFAULT_FEATURES),
+                                              ("S32_C16_default", 16, 32, oracle_model.DEFAULT_FEATURES)])
+def test_window_vs_reference_golden_fp32x3(tag, cout, S, feats):
+    """The reference-run goldens at the fp32 gate: embeddings, one denoiser call and the whole DDIM window within 1e-4."""
+    g = load_golden(f"window_{tag}.npz")
+    s = slice(None, None, int(g["sub"]))
+    m = _build(cout, S, feats, precision="fp32x3")
+    image = seeded_image((1, 1, S, S, S)).cuda()
+    noise = seeded_noise((1, cout, S, S, S)).cuda()
+    with torch.no_grad():
+        emb = m.embed_model(image)
+        e0 = rel_l2(emb[0][:, ::8, ::4, ::4, ::4].cpu(), g["emb0"])
+        logits = m.model(noise, torch.tensor([999]), image=image, embeddings=emb)
+        e1 = rel_l2(logits[:, :, s, s, s].cpu(), g["logits999"])
+        acc = m(image=image, pred_type="ddim_sample", noise=noise)
+        e2 = rel_l2(acc[:, :, s, s, s].cpu(), g["acc"])
+    print(f"fp32x3 {tag}: emb0 {e0:.3e}  logits {e1:.3e}  ddim window {e2:.3e}")
+    assert e0 < FP32_TOL and e1 < FP32_TOL and e2 < FP32_TOL
+
+
+def test_full_size_window_fp32x3_label_agreement():
+    """BASELINE size (96^3, C=16, default features) in fp32x3 mode vs the oracle evaluated in fp32 on the GPU:
+    rel-l2 <= 1e-4 and >= 99.9 % agreement for both the reference's binarisation (out > 0) and argmax."""
+    cout, S = 16, 96
+    m = _build(cout, S, oracle_model.DEFAULT_FEATURES, batch_max=1, precision="fp32x3")
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    image, noise = seeded_image((1, 1, S, S, S)).cuda(), seeded_noise((1, cout, S, S, S)).cuda()
+    with torch.no_grad():
+        acc = m(image=image, pred_type="ddim_sample", noise=noise)
+        ref = _oracle_window_gpu(sd, image, noise, 10)
+    err = rel_l2(acc.cpu(), ref.cpu())
+    sign = ((acc > 0) == (ref > 0)).float().mean().item()
+    am = (acc.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"96^3 window fp32x3: rel-l2 {err:.3e}  sign agreement {sign:.5f}  argmax agreement {am:.5f}")
+    assert err < FP32_TOL
+    assert sign >= 0.999 and am >= 0.999
+
+
+def test_fp32x3_batching_is_transparent():
+    cout, S = 2, 32
+    m = _build(cout, S, SMALL, precision="fp32x3")
+    image, noise = seeded_image((3, 1, S, S, S)).cuda(), seeded_noise((3, cout, S, S, S)).cuda()
+    full = m(image=image, pred_type="ddim_sample", noise=noise)
+    one = m(image=image[1:2], pred_type="ddim_sample", noise=noise[1:2])
+    assert torch.equal(one[0], full[1])
