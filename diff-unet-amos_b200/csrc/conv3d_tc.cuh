@@ -33,6 +33,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "elementwise.cuh"
 #include "ptx.cuh"
 
@@ -206,6 +208,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -252,8 +255,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
     }
   } else if (warp == 2) {
     // =============================== MMA issuer (one thread) ===============================
+    // One thread must sustain an MMA every 48-64 clocks: plane descriptors are formed once per block, the tap loop is
+    // specialised on tz at compile time and all descriptor arithmetic is 32-bit (only the 14-bit start-address field
+    // of the low descriptor word ever changes).
     if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE);
+      static_assert((Cfg::W_SLOTS & (Cfg::W_SLOTS - 1)) == 0, "W_SLOTS must be a power of two");
+      const uint64_t a_desc0 = make_smem_desc(a_smem, Cfg::A_LBO, Cfg::A_SBO);
+      const uint64_t b_desc0 = make_smem_desc(w_smem, Cfg::B_LBO, Cfg::B_SBO);
+      const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
+      const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
       int ubase = 0, w = 0, li = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
         const ConvItem it = conv_item(a, item);
@@ -261,48 +272,65 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
         if (use > 0) { mbar_wait(acc_empty + 8 * buf, (use - 1) & 1); tc_fence_after(); }
         const uint32_t acc = tmem_base + buf * ACC_COLS;
         for (int cb = it.cb_lo; cb < it.cb_hi; ++cb, ubase += Cfg::PLANES) {
-          int waited = 0;
-#pragma unroll 1
-          for (int tz = 0; tz < Cfg::TZ; ++tz) {
-#pragma unroll 1
-            for (int tyx = 0; tyx < Cfg::TYX; ++tyx, ++w) {
-              const int ws = w % Cfg::W_SLOTS;
-              mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
-              tc_fence_after();
-              const uint32_t tap_off = ((tyx / 3) * Cfg::HX + (tyx % 3)) * 16;
-              const uint32_t wb = w_smem + ws * Cfg::W_UNIT_BYTES;
+          uint32_t pl_lo[Cfg::PLANES], pl_bar[Cfg::PLANES], par[Cfg::PLANES];
 #pragma unroll
-              for (int s = 0; s < ZT; ++s) {
-                const int p = s + tz;
-                while (waited <= p) {
-                  const int u = ubase + waited;
-                  mbar_wait(a_full + 8 * (u % Cfg::A_SLOTS), (u / Cfg::A_SLOTS) & 1);
-                  tc_fence_after();
-                  ++waited;
-                }
-                const int u = ubase + p;
-                const uint32_t ab = a_smem + (u % Cfg::A_SLOTS) * Cfg::PLANE_BYTES + tap_off;
+          for (int p = 0; p < Cfg::PLANES; ++p) {
+            const int u = ubase + p, slot = u % Cfg::A_SLOTS;
+            pl_lo[p] = a_lo0 + slot * (Cfg::PLANE_BYTES >> 4);
+            pl_bar[p] = 8 * slot;
+            par[p] = (u / Cfg::A_SLOTS) & 1;
+          }
+          const bool first_cb = cb == it.cb_lo;
+          // one weight tap (tz compile-time, tyx run-time): ZT slabs x CB_CH/16 k-steps
+          auto tap = [&](auto tzc, int tyx) {
+            constexpr int TZI = decltype(tzc)::value;
+            const int ws = w & (Cfg::W_SLOTS - 1);
+            mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
+            tc_fence_after();
+            if (tyx == 0) {  // planes first read in this tz phase: all ZT for tz = 0, one more for each later phase
 #pragma unroll
-                for (int k = 0; k < CB_CH / 16; ++k) {
-                  const uint64_t ad = make_smem_desc(ab + k * 2 * Cfg::A_LBO, Cfg::A_LBO, Cfg::A_SBO);
-                  const uint64_t bd = make_smem_desc(wb + k * 2 * Cfg::B_LBO, Cfg::B_LBO, Cfg::B_SBO);
-                  umma_bf16(acc + s * N_TILE, ad, bd, idesc, ((cb - it.cb_lo) | tz | tyx | k) != 0 ? 1u : 0u);
-                }
+              for (int p = (TZI == 0 ? 0 : ZT - 1 + TZI); p < ZT + TZI; ++p) {
+                mbar_wait(a_full + pl_bar[p], par[p]);
+                tc_fence_after();
               }
-              umma_commit(w_empty + 8 * ws);  // weight slot free once these MMAs retire
             }
-            // planes whose last reader was this tz phase go back to the producer
-            if (tz < Cfg::TZ - 1) {
-              umma_commit(a_empty + 8 * ((ubase + tz) % Cfg::A_SLOTS));
-            } else {
-              for (int p = tz; p < Cfg::PLANES; ++p) umma_commit(a_empty + 8 * ((ubase + p) % Cfg::A_SLOTS));
+            const uint32_t tap16 = (tyx / 3) * Cfg::HX + (tyx % 3);  // tap offset in 16-byte units
+            const uint32_t bl_u = b_lo0 + ws * (Cfg::W_UNIT_BYTES >> 4);
+            const uint32_t acc0 = (first_cb && TZI == 0 && tyx == 0) ? 0u : 1u;  // very first MMA of a slab overwrites
+#pragma unroll
+            for (int sl = 0; sl < ZT; ++sl) {
+              const uint32_t al_p = pl_lo[sl + TZI] + tap16;
+#pragma unroll
+              for (int k = 0; k < CB_CH / 16; ++k)
+                umma_bf16_lh(acc + sl * N_TILE, al_p + k * 2 * (Cfg::A_LBO >> 4), a_hi, bl_u + k * 2 * (Cfg::B_LBO >> 4), b_hi,
+                             idesc, k == 0 ? acc0 : 1u);
             }
+            umma_commit(w_empty + 8 * ws);  // weight slot free once these MMAs retire
+            ++w;
+          };
+          // planes whose last reader was a tz phase go back to the producer as soon as that phase is issued
+#pragma unroll 1
+          for (int tyx = 0; tyx < Cfg::TYX; ++tyx) tap(std::integral_constant<int, 0>{}, tyx);
+          if constexpr (Cfg::TZ == 3) {
+            umma_commit(a_empty + pl_bar[0]);
+#pragma unroll 1
+            for (int tyx = 0; tyx < Cfg::TYX; ++tyx) tap(std::integral_constant<int, 1>{}, tyx);
+            umma_commit(a_empty + pl_bar[1]);
+#pragma unroll 1
+            for (int tyx = 0; tyx < Cfg::TYX; ++tyx) tap(std::integral_constant<int, 2>{}, tyx);
+#pragma unroll
+            for (int p = 2; p < Cfg::PLANES; ++p) umma_commit(a_empty + pl_bar[p]);
+          } else {
+#pragma unroll
+            for (int p = 0; p < Cfg::PLANES; ++p) umma_commit(a_empty + pl_bar[p]);
           }
         }
         umma_commit(acc_full + 8 * buf);
       }
       if (a.dbg) a.dbg[blockIdx.x * 8 + 2] = clock64();
     }
+    __syncwarp();
+    pdl_trigger();  // all MMAs of this CTA are issued: only the last epilogue remains
   } else {
     // =============================== epilogue: TMEM -> registers -> HBM ===============================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read

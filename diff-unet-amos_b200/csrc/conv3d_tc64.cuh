@@ -11,10 +11,17 @@
 //   * PERSISTENT CTAs (one per SM) walk a static list of 8x16xZT output tiles; the plane/weight rings run ahead across
 //     tile boundaries and the accumulators are double-buffered in TMEM (2 x ZT x 64 columns), so the epilogue of tile i
 //     (TMEM -> bf16 -> HBM, InstanceNorm statistics) overlaps the MMAs of tile i+1.
+//   * FUSE (second conv of a TwoConv, bf16 mode): the input is the RAW output of the previous conv; four extra warps
+//     apply that conv's InstanceNorm + LeakyReLU (+ time-embedding bias) to every halo plane IN SHARED MEMORY between
+//     the TMA arrival and the MMAs (out-of-volume halo voxels stay the zeros TMA wrote: the padding of the normalised
+//     tensor).  The normalised intermediate never exists in HBM: one full read + write pass per TwoConv disappears.
+//     Same fp32 formulas as norm_act_kernel, so the result is bit-identical to the unfused path.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <type_traits>
 
 #include "conv3d_tc.cuh"
 
@@ -31,12 +38,15 @@ struct ConvTc64 {
   static constexpr int W_UNIT_BYTES = KCH * NROWS * 16;     // one (cin block, ty, tx) weight tile: 24 KB for 64 ch
   static constexpr int B_LBO = NROWS * 16, B_SBO = 128;
   static constexpr int PLANES = ZT + 2;
-  static constexpr int A_SLOTS = PLANES + 1;
-  static constexpr int W_SLOTS = 2;
+  // 32-channel blocks: the ring holds TWO blocks' planes, so the next block (or the next tile's first block) is loaded
+  // -- and, with FUSE, normalised -- entirely under the MMAs of the current one.  64-channel blocks: one block + 1.
+  static constexpr int A_SLOTS = CB_CH == 32 ? 2 * PLANES + 1 : PLANES + 1;
+  static constexpr int W_SLOTS = CB_CH == 32 ? 4 : 2;
   static constexpr int ACC_COLS = ZT * 64;                  // one accumulator set
   static constexpr int TMEM_COLS = 512;
   static constexpr int RED_BYTES = 4 * 128 * 4;
-  static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + RED_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + RED_BYTES + 1024 + 512;
+  static constexpr int THREADS_FUSED = CONV_THREADS + 4 * 32;  // + 4 transform warps
   static_assert(2 * ACC_COLS <= 512, "double-buffered accumulators exceed TMEM");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -49,6 +59,11 @@ struct ConvTc64Args {
   ConvSegs segs;           // input-channel block list (conv3d_tc.cuh)
   int D, H, W;
   int tiles_x, tiles_y, tiles_z, batch;
+  // FUSE only (single 64-channel source): affine map of the producer's InstanceNorm per (sample, 8-channel chunk),
+  // [n * 8 + chunk][16] = scale[8], shift[8] (in_affine_kernel); bias added after the activation [64] or nullptr
+  const float* in_affine;
+  const float* in_bias;
+  float slope;
 };
 
 // Static tile schedule.  Within EACH sample the tiles are dealt round-robin over the CTAs, so the set of tiles whose
@@ -64,8 +79,8 @@ __device__ __forceinline__ void for_each_tile(int tiles_per_n, int batch, F&& f)
   }
 }
 
-template <int CB_CH, int ZT>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+template <int CB_CH, int ZT, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? ConvTc64<CB_CH, ZT>::THREADS_FUSED : CONV_THREADS, 1)
 conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                    const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, ConvTc64Args a) {
   using Cfg = ConvTc64<CB_CH, ZT>;
@@ -80,6 +95,8 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   const uint32_t acc_full = w_empty + 8 * Cfg::W_SLOTS;  // [2]
   const uint32_t acc_empty = acc_full + 16;              // [2]
   const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t a_ready = tmem_slot + 8;                // [A_SLOTS], FUSE: plane normalised in place, MMAs may read it
+  static_assert(16 * Cfg::A_SLOTS + 16 * Cfg::W_SLOTS + 32 + 8 + 8 * Cfg::A_SLOTS <= 512, "barrier block");
   float* red = reinterpret_cast<float*>(smem_raw + (red_smem - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,7 +104,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   const int tiles_per_n = a.tiles_x * a.tiles_y * a.tiles_z;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); mbar_init(a_ready + 8 * i, 4); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
     fence_mbar_init();
@@ -104,6 +121,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -149,61 +167,152 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     }
   } else if (warp == 2) {
     // =============================== MMA issuer (one thread) ===============================
+    // The single issuing thread must sustain one MMA per ~50-100 clocks, so the per-MMA instruction count matters:
+    // plane descriptors are formed once per block, the tap loop is split into first / middle / last variants (plane
+    // waits and accumulator initialisation only in the first, plane release only in the last) and all descriptor
+    // arithmetic is 32-bit.
     if (elect_one_sync()) {
       const uint64_t a_desc0 = make_smem_desc(a_smem, Cfg::A_LBO, Cfg::A_SBO);
       const uint64_t b_desc0 = make_smem_desc(w_smem, Cfg::B_LBO, Cfg::B_SBO);
+      const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
+      const uint32_t b_lo0 = (uint32_t)b_desc0, b_hi = (uint32_t)(b_desc0 >> 32);
+      static_assert((Cfg::W_SLOTS & (Cfg::W_SLOTS - 1)) == 0, "W_SLOTS must be a power of two");
       int u0 = 0, w = 0, li = 0;
       for_each_tile(tiles_per_n, a.batch, [&](int, int) {
         const int buf = li & 1, use = li >> 1;
         if (use > 0) { mbar_wait(acc_empty + 8 * buf, (use - 1) & 1); tc_fence_after(); }
         const uint32_t acc = tmem_base + buf * Cfg::ACC_COLS;
         for (int cb = 0; cb < ncb; ++cb, u0 += Cfg::PLANES) {
-          int waited = 0;
-#pragma unroll 1
-          for (int tyx = 0; tyx < 9; ++tyx, ++w) {
-            const int ws = w % Cfg::W_SLOTS;
+          uint32_t pl_lo[Cfg::PLANES], pl_bar[Cfg::PLANES];  // descriptor low word / barrier offset of each plane's slot
+          uint32_t par[Cfg::PLANES];
+#pragma unroll
+          for (int p = 0; p < Cfg::PLANES; ++p) {
+            const int u = u0 + p, slot = u % Cfg::A_SLOTS;
+            pl_lo[p] = a_lo0 + slot * (Cfg::PLANE_BYTES >> 4);
+            pl_bar[p] = 8 * slot;
+            par[p] = (u / Cfg::A_SLOTS) & 1;
+          }
+          // KIND 0: first tap of the block (waits for the planes; with first_cb also initialises the accumulators),
+          // 1: middle taps, 2: last tap (hands the planes back to the producer)
+          auto tap = [&](auto kind, int tyx, bool first_cb) {
+            constexpr int KIND = decltype(kind)::value;
+            const int ws = w & (Cfg::W_SLOTS - 1);
             mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
             tc_fence_after();
             const uint32_t tap16 = (tyx / 3) * Cfg::HX + (tyx % 3);  // tap offset in 16-byte units
-            const uint64_t bd_u = b_desc0 + (uint64_t)(ws * (Cfg::W_UNIT_BYTES >> 4));
+            const uint32_t bl_u = b_lo0 + ws * (Cfg::W_UNIT_BYTES >> 4);
 #pragma unroll
             for (int p = 0; p < Cfg::PLANES; ++p) {
-              if (waited <= p) {
-                const int u = u0 + p;
-                mbar_wait(a_full + 8 * (u % Cfg::A_SLOTS), (u / Cfg::A_SLOTS) & 1);
+              if constexpr (KIND == 0) {
+                mbar_wait((FUSE ? a_ready : a_full) + pl_bar[p], par[p]);
                 tc_fence_after();
-                waited = p + 1;
               }
               constexpr int dummy = 0; (void)dummy;
               const int slab_lo = p >= 2 ? p - 2 : 0, slab_hi = p < ZT ? p : ZT - 1;
               const int nblk = slab_hi - slab_lo + 1;
               const int row0 = (2 - (p - slab_lo)) * 64;
-              const int slot = (u0 + p) % Cfg::A_SLOTS;
-              const uint64_t ad_p = a_desc0 + (uint64_t)(slot * (Cfg::PLANE_BYTES >> 4) + tap16);
-              const uint64_t bd_p = bd_u + (uint64_t)(row0 * 16 >> 4);
+              const uint32_t al_p = pl_lo[p] + tap16, bl_p = bl_u + row0;  // (row0 rows * 16 B) >> 4
 #pragma unroll
               for (int k = 0; k < Cfg::KC; ++k) {
-                const uint64_t ad = ad_p + (uint64_t)(k * 2 * (Cfg::A_LBO >> 4));
-                const uint64_t bd = bd_p + (uint64_t)(k * 2 * (Cfg::B_LBO >> 4));
-                if (cb == 0 && tyx == 0 && k == 0) {
+                const uint32_t al = al_p + k * 2 * (Cfg::A_LBO >> 4), bl = bl_p + k * 2 * (Cfg::B_LBO >> 4);
+                if (KIND == 0 && k == 0 && first_cb) {
                   // first contribution to every slab of this tile: per-slab MMAs so each gets its own accumulate flag
+#pragma unroll
                   for (int i = 0; i < nblk; ++i) {
-                    const int s = slab_lo + i, tz = p - s;
-                    umma_bf16(acc + s * 64, ad, bd + (uint64_t)(i * 64 * 16 >> 4), make_idesc_bf16(128, 64), tz != 0 ? 1u : 0u);
+                    const int sl = slab_lo + i, tz = p - sl;
+                    umma_bf16_lh(acc + sl * 64, al, a_hi, bl + i * 64, b_hi, make_idesc_bf16(128, 64), tz != 0 ? 1u : 0u);
                   }
                 } else {
-                  umma_bf16(acc + slab_lo * 64, ad, bd, make_idesc_bf16(128, 64 * nblk), 1u);
+                  umma_bf16_lh(acc + slab_lo * 64, al, a_hi, bl, b_hi, make_idesc_bf16(128, 64 * nblk), 1u);
                 }
               }
-              if (tyx == 8) umma_commit(a_empty + 8 * slot);  // last reader of this plane for this cin block
+              if constexpr (KIND == 2) umma_commit(a_empty + pl_bar[p]);  // last reader of this plane for this block
             }
             umma_commit(w_empty + 8 * ws);
-          }
+            ++w;
+          };
+          tap(std::integral_constant<int, 0>{}, 0, cb == 0);
+#pragma unroll 1
+          for (int tyx = 1; tyx < 8; ++tyx) tap(std::integral_constant<int, 1>{}, tyx, false);
+          tap(std::integral_constant<int, 2>{}, 8, false);
         }
         umma_commit(acc_full + 8 * buf);
         ++li;
       });
     }
+    __syncwarp();
+    pdl_trigger();  // all MMAs of this CTA are issued: only the last epilogue remains
+  } else if (FUSE && warp >= 7) {
+    // =============================== in-place normalise of arriving halo planes ===============================
+    // thread = (8-channel chunk of the block, 1 of LPC lanes walking that chunk's 18 x 10 halo positions): its 8 scales /
+    // shifts / biases are reloaded (L1 hits) when the (sample, block) changes
+    constexpr int LPC = 128 / Cfg::KCH;  // lanes per chunk: 16 (64-channel blocks) or 32 (32-channel blocks)
+    constexpr int NPOS = Cfg::HY * Cfg::HX;  // 180 halo positions of one chunk plane
+    constexpr int NV = (NPOS + LPC - 1) / LPC;  // vectors per thread per plane (6 or 12)
+    const int tt = threadIdx.x - 7 * 32, chunk = tt / LPC, l0 = tt % LPC;
+    uint8_t* const a_gen = smem_raw + (a_smem - smem_u32(smem_raw)) + chunk * (NPOS * 16) + l0 * 16;
+    // the halo positions this thread owns are the same for every plane and tile: i = l0 + j * LPC
+    int pos_y[NV], pos_x[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = l0 + j * LPC;
+      pos_y[j] = i < NPOS ? i / Cfg::HX : 1 << 20;  // out-of-range positions never pass the bounds test
+      pos_x[j] = i % Cfg::HX;
+    }
+    float sc[8], sh[8], bi[8];
+    int u = 0;
+    for_each_tile(tiles_per_n, a.batch, [&](int n, int lin) {
+      int t = lin;
+      const int tix = t % a.tiles_x; t /= a.tiles_x;
+      const int tiy = t % a.tiles_y; t /= a.tiles_y;
+      const int tiz = t;
+      const int x0 = tix * CONV_TX - 1, y0 = tiy * CONV_TY - 1, z0 = tiz * ZT - 1;
+      // which of this thread's positions lie inside the volume (the others keep TMA's zero fill = the padding)
+      uint32_t mask = 0;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int gy = y0 + pos_y[j], gx = x0 + pos_x[j];
+        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) mask |= 1u << j;
+      }
+      for (int cb = 0; cb < ncb; ++cb) {  // FUSE: one source tensor, blocks in channel order
+        {
+          const int gch = cb * Cfg::KCH + chunk;  // 8-channel chunk of the source tensor
+          const float4* src = reinterpret_cast<const float4*>(a.in_affine + ((long long)n * (ncb * Cfg::KCH) + gch) * 16);
+          const float4 s0 = __ldg(src), s1 = __ldg(src + 1), h0 = __ldg(src + 2), h1 = __ldg(src + 3);
+          sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+          sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bi[j] = a.in_bias ? __ldg(a.in_bias + gch * 8 + j) : 0.f;
+        }
+        for (int p = 0; p < Cfg::PLANES; ++p, ++u) {
+          const int slot = u % Cfg::A_SLOTS;
+          mbar_wait(a_full + 8 * slot, (u / Cfg::A_SLOTS) & 1);
+          const int gz = z0 + p;
+          if (gz >= 0 && gz < a.D) {
+            uint8_t* const pl = a_gen + slot * Cfg::PLANE_BYTES;
+            constexpr int G = 6;  // vectors in flight per thread: all loads of a group are issued before the math
+#pragma unroll
+            for (int j0 = 0; j0 < NV; j0 += G) {
+              BF8 v[G];
+#pragma unroll
+              for (int j = 0; j < G; ++j)
+                if (j0 + j < NV && (mask >> (j0 + j) & 1u)) v[j] = *reinterpret_cast<const BF8*>(pl + (j0 + j) * (LPC * 16));
+#pragma unroll
+              for (int j = 0; j < G; ++j)
+                if (j0 + j < NV && (mask >> (j0 + j) & 1u)) {
+                  float f[8];
+                  bf8_to_float(v[j], f);
+                  norm_apply(f, sc, sh, bi, a.slope);
+                  *reinterpret_cast<BF8*>(pl + (j0 + j) * (LPC * 16)) = float_to_bf8(f);
+                }
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes above -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_ready + 8 * slot);
+        }
+      }
+    });
   } else {
     // =============================== epilogue: TMEM -> bf16 -> HBM (+ IN statistics) ===============================
     const int q = warp & 3;

@@ -76,6 +76,7 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -150,6 +151,8 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
         }
       }
     }
+    __syncwarp();
+    pdl_trigger();  // all MMAs of this CTA are issued: only the last epilogue remains
   } else {
     // =============================== epilogue: TMEM -> +bias -> bf16 -> scatter ===============================
     const int q = warp & 3;

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -81,6 +82,24 @@ static int prof_end(cudaStream_t st) {
   CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].b, st));
   ++g_prof_used;
   return 0;
+}
+
+// Launch with programmatic stream serialization (see pdl_sync() in ptx.cuh): only for kernels that call pdl_sync().
+// DUNET_NO_PDL=1 in the environment falls back to plain stream order (debugging / A-B timing).
+static bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DUNET_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);  // the error is picked up by LAUNCH_CHECK()
 }
 
 static inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
@@ -241,8 +260,9 @@ struct ConvW {
   float *gamma = nullptr, *beta = nullptr;
   int rot = 0;  // 1: packed input channel j holds reference channel (j + 1) % c0r (denoiser input [x.., image])
   bool have_w = false, have_cb = false, have_g = false, have_b = false;
-  void shape(int c0r_, int c0p_, int c1r_, int c1p_, int coutr_, int parts_ = 1) {
+  void shape(int c0r_, int c0p_, int c1r_, int c1p_, int coutr_, int parts_ = 1, int cb64_ = 32) {
     c0r = c0r_; c0p = c0p_; c1r = c1r_; c1p = c1p_; coutr = coutr_; parts = parts_;
+    cb64 = (c1p == 0 && c0p == 32) ? 32 : cb64_;
     coutp = pad_to(coutr, 64);
     cb_ch = (c1p == 0 && c0p == 32) ? 32 : 64;
     n_tile = (coutp % 128 == 0) ? 128 : 64;
@@ -251,7 +271,10 @@ struct ConvW {
   }
   int ncb() const { return (nb0 + nb1) * parts; }  // input-channel blocks the kernels walk
   size_t packed_elems() const { return (size_t)n_tiles * ncb() * 27 * cb_ch * n_tile; }
-  size_t packed64_elems() const { return (size_t)ncb() * 9 * cb_ch * 192; }
+  // the Cout = 64 z-stacked kernel walks 32-channel blocks (its plane ring then holds two blocks, conv3d_tc64.cuh)
+  int cb64 = 32;
+  int ncb64() const { return (c0p + c1p) / cb64 * parts; }
+  size_t packed64_elems() const { return (size_t)ncb64() * 9 * cb64 * 192; }
 };
 struct Act {  // an activation tensor: C8-planar bf16, plus its low part in fp32x3 mode
   bf16* hi = nullptr;
@@ -280,7 +303,7 @@ struct Slot {
 };
 
 struct WsLayout {
-  size_t in_pack, raw, mid, partial, ss, splitk, x_t, acc, total;
+  size_t in_pack, raw, mid, partial, ss, splitk, affine, x_t, acc, total;
   size_t emb[5], epool[5], x[5], dpool[5], up[5], u[5];
 };
 
@@ -355,6 +378,7 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
     const int tz4 = (p->D[lvl] + CONV_ZT - 1) / CONV_ZT;
     const int items4 = g.tiles_x * g.tiles_y * tz4 * c.n_tiles * std::max(1, std::min(c.ncb(), 4));
     g.zt = (items4 < 64 && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
+    if (getenv("DUNET_EXP_ZT2") && c.n_tile == 128) g.zt = 2;
   }
   g.tiles_z = (p->D[lvl] + g.zt - 1) / g.zt;
   g.tiles = g.tiles_x * g.tiles_y * g.tiles_z;
@@ -404,6 +428,7 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
   L.partial = take(part_max);
   L.ss = take(ss_max);
   L.splitk = take(split_max);
+  L.affine = take(ss_max);  // [plane][16] affine maps for the normalise-on-load convs
   const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);  // voxel-major DDIM state, classes padded to the MMA column tiles
   L.x_t = take((size_t)B * CP * p->V[0] * sizeof(float));
   L.acc = take((size_t)B * CP * p->V[0] * sizeof(float));
@@ -446,17 +471,17 @@ static int launch_conv_tc(const CUtensorMap (&t)[4], const ConvTcArgs& a, cudaSt
   // persistent: one CTA per SM (each may own all 512 TMEM columns) walking the work items round-robin
   const long long grid = std::min<long long>(items, (long long)g_num_sms);
   TRY(prof_begin(MODE == MODE_CONV3 ? PROF_CONV : PROF_DECONV, st));
-  kern<<<(unsigned)grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t[0], t[1], t[2], t[3], a);
+  launch_k(kern, dim3((unsigned)grid), dim3(CONV_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
   return 0;
 }
 
-template <int CB_CH>
+template <int CB_CH, bool FUSE>
 static int launch_conv_tc64(const CUtensorMap (&t)[4], const ConvTc64Args& a, unsigned* grid_out, cudaStream_t st) {
   using Cfg = ConvTc64<CB_CH, CONV_ZT>;
   static bool attr_set = false;
-  auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT>;
+  auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT, FUSE>;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
@@ -466,7 +491,7 @@ static int launch_conv_tc64(const CUtensorMap (&t)[4], const ConvTc64Args& a, un
   const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
   *grid_out = grid;
   TRY(prof_begin(PROF_CONV, st));
-  kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, st>>>(t[0], t[1], t[2], t[3], a);
+  launch_k(kern, dim3(grid), dim3(FUSE ? Cfg::THREADS_FUSED : CONV_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
   return 0;
@@ -485,9 +510,25 @@ static ConvSegs make_segs(int nb0, int chunks0, int nb1, int chunks1, bool prec)
   return sg;
 }
 
+// normalise-on-load request for run_conv: src0 is the RAW output of the previous conv, to be seen through
+// LeakyReLU(x * scale + shift) + bias (in_affine_kernel output + optional time-embedding bias row)
+struct FuseIn {
+  const float* affine = nullptr;
+  const float* bias = nullptr;
+};
+
+// can conv `c` at level `lvl` take its input through the normalise-on-load path of the Cout = 64 kernel?
+static bool conv_can_fuse_input(const dunet_plan* p, const ConvW& c, int lvl, int B) {
+  if (!(p->cfg.flags & DUNET_FLAG_FUSED_NORM)) return false;  // opt-in: measured slower, see include/dunet.h
+  if (p->cfg.flags & (DUNET_FLAG_REF_CONV | DUNET_FLAG_GENERIC_CONV | DUNET_FLAG_FP32X3)) return false;
+  if (c.parts != 1 || c.coutp != 64 || c.nb1 != 0 || !c.packed64) return false;
+  const ConvGeom g = conv_geom(p, c, lvl, B);
+  return g.ksplit == 1 && g.zt == CONV_ZT;
+}
+
 // 3x3x3 conv -> raw output (bf16, or hi + lo in fp32x3 mode) + InstanceNorm partial statistics [plane][*nseg_out][16]
 static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act out, float* partial, float* splitk,
-                    int* nseg_out, int lvl, int B, cudaStream_t st) {
+                    int* nseg_out, int lvl, int B, cudaStream_t st, const FuseIn* fuse = nullptr) {
   const int D = p->D[lvl], H = p->H[lvl], W = p->W[lvl];
   const int planes = B * (c.coutp / 8);
   const bool prec = c.parts == 3;
@@ -509,27 +550,36 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     return 0;
   }
   if (g_prof_on) g_prof_flops += 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
-  CUtensorMap t[4];
-  TRY(make_act_tmap(&t[0], src0.hi, B * (c.c0p / 8), D, H, W, c.cb_ch / 8, 1));
-  t[1] = t[2] = t[3] = t[0];
-  if (c.nb1 > 0) TRY(make_act_tmap(&t[1], src1.hi, B * (c.c1p / 8), D, H, W, c.cb_ch / 8, 1));
-  if (prec) {
-    TRY(make_act_tmap(&t[2], src0.lo, B * (c.c0p / 8), D, H, W, c.cb_ch / 8, 1));
-    if (c.nb1 > 0) TRY(make_act_tmap(&t[3], src1.lo, B * (c.c1p / 8), D, H, W, c.cb_ch / 8, 1));
-  }
-  const ConvSegs segs = make_segs(c.nb0, c.c0p / 8, c.nb1, c.c1p / 8, prec);
   const ConvGeom g = conv_geom(p, c, lvl, B);
   const int want_split = (splitk && partial) ? g.ksplit : 1;
-  if (c.packed64 && want_split == 1 && g.zt == CONV_ZT && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {
+  const bool use64 = c.packed64 && want_split == 1 && g.zt == CONV_ZT && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV);
+  const int cb = use64 ? c.cb64 : c.cb_ch;  // input-channel block of the kernel that will run
+  CUtensorMap t[4];
+  TRY(make_act_tmap(&t[0], src0.hi, B * (c.c0p / 8), D, H, W, cb / 8, 1));
+  t[1] = t[2] = t[3] = t[0];
+  if (c.nb1 > 0) TRY(make_act_tmap(&t[1], src1.hi, B * (c.c1p / 8), D, H, W, cb / 8, 1));
+  if (prec) {
+    TRY(make_act_tmap(&t[2], src0.lo, B * (c.c0p / 8), D, H, W, cb / 8, 1));
+    if (c.nb1 > 0) TRY(make_act_tmap(&t[3], src1.lo, B * (c.c1p / 8), D, H, W, cb / 8, 1));
+  }
+  const ConvSegs segs = make_segs(c.c0p / cb, c.c0p / 8, c.c1p / cb, c.c1p / 8, prec);
+  if (use64) {
     ConvTc64Args b;
     memset(&b, 0, sizeof b);
     b.w = c.packed64; b.out = out.hi; b.out_lo = out.lo; b.stats = partial; b.segs = segs;
     b.D = D; b.H = H; b.W = W; b.tiles_x = g.tiles_x; b.tiles_y = g.tiles_y; b.tiles_z = g.tiles_z; b.batch = B;
     unsigned grid = 0;
-    TRY(c.cb_ch == 32 ? launch_conv_tc64<32>(t, b, &grid, st) : launch_conv_tc64<64>(t, b, &grid, st));
+    if (fuse) {
+      if (c.nb1 != 0 || prec) return fail(DUNET_E_STATE, "normalise-on-load needs a single bf16 source");
+      b.in_affine = fuse->affine; b.in_bias = fuse->bias; b.slope = 0.1f;
+      TRY(cb == 32 ? (launch_conv_tc64<32, true>(t, b, &grid, st)) : (launch_conv_tc64<64, true>(t, b, &grid, st)));
+    } else {
+      TRY(cb == 32 ? (launch_conv_tc64<32, false>(t, b, &grid, st)) : (launch_conv_tc64<64, false>(t, b, &grid, st)));
+    }
     if (partial) *nseg_out = (int)grid;  // one statistics row per persistent CTA and sample
     return 0;
   }
+  if (fuse) return fail(DUNET_E_STATE, "normalise-on-load requested for a conv outside the Cout = 64 kernel");
   ConvTcArgs a;
   memset(&a, 0, sizeof a);
   a.w = c.packed; a.out = out.hi; a.out_lo = out.lo; a.segs = segs;
@@ -551,8 +601,8 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
   if (a.ksplit > 1) {
     const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
     TRY(prof_begin(PROF_SPLITK, st));
-    splitk_reduce_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(
-        splitk, a.ksplit, (long long)B * c.coutp * p->V[lvl], out.hi, out.lo, partial, p->V[lvl], nseg);
+    launch_k(splitk_reduce_stats_kernel, dim3(nseg, planes), dim3(STATS_THREADS), 0, st, (const float*)splitk, a.ksplit,
+             (long long)B * c.coutp * p->V[lvl], out.hi, out.lo, partial, (long long)p->V[lvl], nseg);
     LAUNCH_CHECK();
     TRY(prof_end(st));
     *nseg_out = nseg;
@@ -581,20 +631,20 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
   if (pooled.hi) {
     const dim3 grid(grid_for(p->V[lvl] / 4, NORM_THREADS, per_plane), planes);
     if (prec) {
-      if (add.hi) norm_act_pool_kernel<true, true><<<grid, NORM_THREADS, 0, st>>>(a);
-      else norm_act_pool_kernel<false, true><<<grid, NORM_THREADS, 0, st>>>(a);
+      if (add.hi) launch_k(norm_act_pool_kernel<true, true>, grid, dim3(NORM_THREADS), 0, st, a);
+      else launch_k(norm_act_pool_kernel<false, true>, grid, dim3(NORM_THREADS), 0, st, a);
     } else {
-      if (add.hi) norm_act_pool_kernel<true, false><<<grid, NORM_THREADS, 0, st>>>(a);
-      else norm_act_pool_kernel<false, false><<<grid, NORM_THREADS, 0, st>>>(a);
+      if (add.hi) launch_k(norm_act_pool_kernel<true, false>, grid, dim3(NORM_THREADS), 0, st, a);
+      else launch_k(norm_act_pool_kernel<false, false>, grid, dim3(NORM_THREADS), 0, st, a);
     }
   } else {
     const dim3 grid(grid_for(p->V[lvl], NORM_THREADS * (prec ? 2 : 4), per_plane), planes);
     if (prec) {
-      if (add.hi) norm_act_kernel<true, true><<<grid, NORM_THREADS, 0, st>>>(a);
-      else norm_act_kernel<false, true><<<grid, NORM_THREADS, 0, st>>>(a);
+      if (add.hi) launch_k(norm_act_kernel<true, true>, grid, dim3(NORM_THREADS), 0, st, a);
+      else launch_k(norm_act_kernel<false, true>, grid, dim3(NORM_THREADS), 0, st, a);
     } else {
-      if (add.hi) norm_act_kernel<true, false><<<grid, NORM_THREADS, 0, st>>>(a);
-      else norm_act_kernel<false, false><<<grid, NORM_THREADS, 0, st>>>(a);
+      if (add.hi) launch_k(norm_act_kernel<true, false>, grid, dim3(NORM_THREADS), 0, st, a);
+      else launch_k(norm_act_kernel<false, false>, grid, dim3(NORM_THREADS), 0, st, a);
     }
   }
   LAUNCH_CHECK();
@@ -607,13 +657,36 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
 // *nseg_out describes its statistics rows in ws.partial.
 static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src1, const float* temb_bias, Act add, Act out,
                        Act pooled, int lvl, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
-                       bool defer_last_norm = false, int* nseg_out = nullptr) {
+                       bool defer_last_norm = false, int* nseg_out = nullptr, Act* raw_out = nullptr) {
   const Act raw_a = ws_act(p, ws, L.raw, t.a.coutp, lvl, B), mid = ws_act(p, ws, L.mid, t.a.coutp, lvl, B);
   const Act raw_b = ws_act(p, ws, L.raw, t.b.coutp, lvl, B);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
   float* splitk = reinterpret_cast<float*>(ws + L.splitk);
   int nseg = 0;
   TRY(run_conv(p, t.a, src0, src1, raw_a, partial, splitk, &nseg, lvl, B, st));
+  if (conv_can_fuse_input(p, t.b, lvl, B)) {
+    // conv_1 normalises conv_0's raw output on load: only the affine map is materialised.  conv_1 writes its own raw
+    // output to ws.mid (ws.raw is still being read) -- callers get the buffer through *raw_out.
+    float* affine = reinterpret_cast<float*>(ws + L.affine);
+    const int planes = B * (t.a.coutp / 8);
+    TRY(prof_begin(PROF_NORM, st));
+    launch_k(in_affine_kernel, dim3(planes), dim3(256), 0, st, (const float*)partial, nseg, (const float*)t.a.gamma,
+             (const float*)t.a.beta, t.a.coutp / 8, (double)p->V[lvl], 1e-5f, affine);
+    LAUNCH_CHECK();
+    TRY(prof_end(st));
+    FuseIn f;
+    f.affine = affine; f.bias = temb_bias;
+    const Act raw_b2 = ws_act(p, ws, L.mid, t.b.coutp, lvl, B);
+    TRY(run_conv(p, t.b, raw_a, Act(), raw_b2, partial, splitk, &nseg, lvl, B, st, &f));
+    if (raw_out) *raw_out = raw_b2;
+    if (defer_last_norm) {
+      *nseg_out = nseg;
+      return 0;
+    }
+    TRY(run_norm(p, t.b, raw_b2, partial, nseg, nullptr, add, out, pooled, lvl, B, st));
+    return 0;
+  }
+  if (raw_out) *raw_out = raw_b;
   TRY(run_norm(p, t.a, raw_a, partial, nseg, temb_bias, Act(), mid, Act(), lvl, B, st));
   TRY(run_conv(p, t.b, mid, Act(), raw_b, partial, splitk, &nseg, lvl, B, st));
   if (defer_last_norm) {
@@ -656,10 +729,10 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
     TRY(prof_begin(PROF_DECONV, st));
     if (d.cinp == 64) {
       if (!attr1) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<1, 2>::SMEM_BYTES)); attr1 = true; }
-      deconv2_tc_kernel<1, 2><<<grid, CONV_THREADS, DeconvTc<1, 2>::SMEM_BYTES, st>>>(t[0], b);
+      launch_k(deconv2_tc_kernel<1, 2>, dim3(grid), dim3(CONV_THREADS), DeconvTc<1, 2>::SMEM_BYTES, st, t[0], b);
     } else {
       if (!attr2) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<2, 2>::SMEM_BYTES)); attr2 = true; }
-      deconv2_tc_kernel<2, 2><<<grid, CONV_THREADS, DeconvTc<2, 2>::SMEM_BYTES, st>>>(t[0], b);
+      launch_k(deconv2_tc_kernel<2, 2>, dim3(grid), dim3(CONV_THREADS), DeconvTc<2, 2>::SMEM_BYTES, st, t[0], b);
     }
     LAUNCH_CHECK();
     TRY(prof_end(st));
@@ -693,7 +766,8 @@ static int check_call(const dunet_plan* p, int B, const void* ws) {
 static int launch_pack(const dunet_plan* p, const float* src0, int c0, const float* src1, int c1, Act dst, int c_pad,
                        long long vox, int B, cudaStream_t st) {
   (void)p;
-  pack_c8_kernel<<<grid_for((long long)B * (c_pad / 8) * vox, 256), 256, 0, st>>>(src0, c0, src1, c1, dst.hi, dst.lo, c_pad, vox, B);
+  launch_k(pack_c8_kernel, dim3(grid_for((long long)B * (c_pad / 8) * vox, 256)), dim3(256), 0, st, src0, c0, src1, c1, dst.hi, dst.lo,
+           c_pad, vox, B);
   LAUNCH_CHECK();
   return 0;
 }
@@ -711,7 +785,7 @@ static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, co
 
 // U-Net body given in_pack = cat([image, x_t]); leaves the RAW output of upcat_1.conv_1 in ws.raw
 static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
-                     int* last_nseg) {
+                     int* last_nseg, Act* last_raw) {
   const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
   for (int l = 0; l < 5; ++l) {
     const Act src = l ? ws_act(p, ws, L.dpool[l], p->fp[l - 1], l, B) : in_pack;
@@ -725,7 +799,7 @@ static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, c
     TRY(run_deconv(p, p->dec[l], prev, up, l, B, st));
     const Act u = ws_act(p, ws, L.u[l], p->uoutp[l], l - 1, B);
     TRY(run_twoconv(p, p->upc[l], ws_act(p, ws, L.x[l - 1], p->fp[l - 1], l - 1, B), up, temb_row + p->temb_off[5 + (4 - l)],
-                    Act(), u, Act(), l - 1, B, ws, L, st, /*defer_last_norm=*/l == 1, last_nseg));
+                    Act(), u, Act(), l - 1, B, ws, L, st, /*defer_last_norm=*/l == 1, last_nseg, l == 1 ? last_raw : nullptr));
     prev = u;
   }
   return 0;
@@ -746,9 +820,9 @@ static int launch_temb(dunet_plan* p, const int* d_t, int rows, float* table, cu
 }
 
 // fills the part of FinalDdimArgs that folds upcat_1.conv_1's InstanceNorm + LeakyReLU into the final 1x1 conv
-static void final_args_common(dunet_plan* p, FinalDdimArgs& a, uint8_t* ws, const WsLayout& L, int nseg, int B) {
+static void final_args_common(dunet_plan* p, FinalDdimArgs& a, uint8_t* ws, const WsLayout& L, int nseg, int B, Act feat) {
+  (void)ws; (void)L;
   memset(&a, 0, sizeof a);
-  const Act feat = ws_act(p, ws, L.raw, p->fp[5], 0, B);
   a.feat = feat.hi; a.feat_lo = feat.lo; a.F = p->fp[5]; a.w = p->final_w; a.b = p->final_b; a.C = p->C;
   a.partial = reinterpret_cast<float*>(ws + L.partial); a.nseg = nseg; a.gamma = p->upc[1].b.gamma; a.beta = p->upc[1].b.beta;
   a.eps = 1e-5f; a.slope = 0.1f; a.in_pad = p->in_pad; a.vox = p->V[0]; a.batch = B;
@@ -761,11 +835,11 @@ static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) 
 #define DUNET_FINAL(NT)                                                                            \
   do {                                                                                             \
     if (prec) {                                                                                    \
-      if (a.F == 64) final_ddim_kernel<NT, 4, true><<<grid, FINAL_THREADS, 0, st>>>(a);            \
-      else final_ddim_kernel<NT, 8, true><<<grid, FINAL_THREADS, 0, st>>>(a);                      \
+      if (a.F == 64) launch_k(final_ddim_kernel<NT, 4, true>, grid, dim3(FINAL_THREADS), 0, st, a);            \
+      else launch_k(final_ddim_kernel<NT, 8, true>, grid, dim3(FINAL_THREADS), 0, st, a);                      \
     } else {                                                                                       \
-      if (a.F == 64) final_ddim_kernel<NT, 4, false><<<grid, FINAL_THREADS, 0, st>>>(a);           \
-      else final_ddim_kernel<NT, 8, false><<<grid, FINAL_THREADS, 0, st>>>(a);                     \
+      if (a.F == 64) launch_k(final_ddim_kernel<NT, 4, false>, grid, dim3(FINAL_THREADS), 0, st, a);           \
+      else launch_k(final_ddim_kernel<NT, 8, false>, grid, dim3(FINAL_THREADS), 0, st, a);                     \
     }                                                                                              \
   } while (0)
   if (g_prof_on)  // feature map read once (bf16) + fp32 state x_t and sum(x0) read+written + bf16 re-pack of the next input
@@ -869,6 +943,7 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
   dunet_plan* p = new dunet_plan();
   p->cfg = *cfg;
   const int parts = (cfg->flags & DUNET_FLAG_FP32X3) ? 3 : 1;
+  const int cb64 = (cfg->flags & DUNET_FLAG_TC64_CB64) ? 64 : 32;
   p->C = cfg->num_classes;
   for (int l = 0; l < 5; ++l) {
     p->D[l] = cfg->patch[0] >> l; p->H[l] = cfg->patch[1] >> l; p->W[l] = cfg->patch[2] >> l;
@@ -885,20 +960,20 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
   // encoder (no temb), pretrained/basic_unet.py:491-494
   for (int l = 0; l < 5; ++l) {
     TwoConvW& e = p->enc[l];
-    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], parts);
-    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts);
-    e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts);
+    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], parts, cb64);
+    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts, cb64);
+    e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts, cb64);
     TwoConvW& d = p->den[l];
     d.has_temb = true;
-    if (l == 0) { d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0], parts); d.a.rot = 1; }
-    else d.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts);
-    d.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts);
+    if (l == 0) { d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0], parts, cb64); d.a.rot = 1; }
+    else d.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts, cb64);
+    d.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts, cb64);
   }
   for (int l = 4; l >= 1; --l) {
     TwoConvW& u = p->upc[l];
     u.has_temb = true;
-    u.a.shape(p->fr[l - 1], p->fp[l - 1], p->upr[l], p->upp[l], p->uoutr[l], parts);  // cat([skip, up]) denoiser.py:190
-    u.b.shape(p->uoutr[l], p->uoutp[l], 0, 0, p->uoutr[l], parts);
+    u.a.shape(p->fr[l - 1], p->fp[l - 1], p->upr[l], p->upp[l], p->uoutr[l], parts, cb64);  // cat([skip, up]) denoiser.py:190
+    u.b.shape(p->uoutr[l], p->uoutp[l], 0, 0, p->uoutr[l], parts, cb64);
     DeconvW& d = p->dec[l];
     d.cinr = p->fr[l]; d.cinp = p->fp[l]; d.coutr = p->upr[l]; d.coutp = p->upp[l]; d.parts = parts;
   }
@@ -965,7 +1040,7 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
         const size_t n64 = c->packed64_elems();
         if (!c->packed64) TRY(dev_alloc(p, (void**)&c->packed64, n64 * sizeof(bf16)));
         pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(src, c->packed64, c->coutr, cinr, c->c0r, c->c0p,
-                                                                             c->c1r, c->cb_ch, c->ncb(), c->rot, c->parts);
+                                                                             c->c1r, c->cb64, c->ncb64(), c->rot, c->parts);
         LAUNCH_CHECK();
       }
       if (p->cfg.flags & DUNET_FLAG_KEEP_FP32_WEIGHTS) {
@@ -1122,9 +1197,10 @@ int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int3
   }
   TRY(launch_pack(p, x_t, p->C, image, p->cfg.in_channels, ws_act(p, ws, L.in_pack, p->in_pad, 0, B), p->in_pad, p->V[0], B, st));
   int nseg = 0;
-  TRY(unet_body(p, p->temb_table + (size_t)row * p->temb_row, B, ws, L, st, &nseg));
+  Act feat;
+  TRY(unet_body(p, p->temb_table + (size_t)row * p->temb_row, B, ws, L, st, &nseg, &feat));
   FinalDdimArgs a;
-  final_args_common(p, a, ws, L, nseg, B);
+  final_args_common(p, a, ws, L, nseg, B, feat);
   a.image = image; a.logits_out = logits_out;
   a.r = 1.f; a.m = 1.f; a.abp = 1.f;
   return launch_final(p, a, st);
@@ -1141,17 +1217,18 @@ static int ddim_sample_impl(dunet_plan* p, const float* image, const float* nois
   float* acc = reinterpret_cast<float*>(ws + L.acc);
   if (run_encoder) TRY(encode_impl(p, image, B, ws, L, st));
   const int sgrid = grid_for((long long)B * p->V[0] * (CP / 4), 256, 148 * 8);
-  state_to_vm_kernel<<<sgrid, 256, 0, st>>>(noise, x_t, p->C, CP, p->V[0], B);
+  launch_k(state_to_vm_kernel, dim3(sgrid), dim3(256), 0, st, noise, x_t, p->C, CP, (long long)p->V[0], B);
   LAUNCH_CHECK();
-  state_to_vm_kernel<<<sgrid, 256, 0, st>>>(nullptr, acc, p->C, CP, p->V[0], B);
+  launch_k(state_to_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)nullptr, acc, p->C, CP, (long long)p->V[0], B);
   LAUNCH_CHECK();
   const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
   TRY(launch_pack(p, noise, p->C, image, p->cfg.in_channels, in_pack, p->in_pad, p->V[0], B, st));
   for (int i = p->n_steps - 1, k = 0; i >= 0; --i, ++k) {  // gaussian_diffusion.py:694 indices high -> low
     int nseg = 0;
-    TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st, &nseg));
+    Act feat;
+    TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st, &nseg, &feat));
     FinalDdimArgs a;
-    final_args_common(p, a, ws, L, nseg, B);
+    final_args_common(p, a, ws, L, nseg, B, feat);
     a.image = image; a.x_t = x_t; a.acc = acc;
     a.logits_out = per_step_logits ? per_step_logits + (size_t)k * per_step_stride : nullptr;
     a.next_in = i > 0 ? in_pack.hi : nullptr;
@@ -1159,10 +1236,11 @@ static int ddim_sample_impl(dunet_plan* p, const float* image, const float* nois
     a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
     TRY(launch_final(p, a, st));
   }
-  state_from_vm_kernel<<<sgrid, 256, 0, st>>>(acc, acc_out, p->C, CP, p->V[0], B, out_scale, out_accumulate);
+  launch_k(state_from_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)acc, acc_out, p->C, CP, (long long)p->V[0], B, out_scale,
+           out_accumulate);
   LAUNCH_CHECK();
   if (final_x) {
-    state_from_vm_kernel<<<sgrid, 256, 0, st>>>(x_t, final_x, p->C, CP, p->V[0], B, 1.f, 0);
+    launch_k(state_from_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)x_t, final_x, p->C, CP, (long long)p->V[0], B, 1.f, 0);
     LAUNCH_CHECK();
   }
   return 0;
@@ -1281,7 +1359,7 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
       const size_t n64 = c.packed64_elems();
       CUDA_TRY(cudaMallocAsync((void**)&c.packed64, n64 * sizeof(bf16), st));
       pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(weight, c.packed64, c.coutr, c0 + c1, c.c0r, c.c0p,
-                                                                           c.c1r, c.cb_ch, c.ncb(), 0, c.parts);
+                                                                           c.c1r, c.cb64, c.ncb64(), 0, c.parts);
       LAUNCH_CHECK();
     }
   }

@@ -8,6 +8,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "ptx.cuh"
+
 namespace dunet {
 
 struct alignas(16) BF8 {
@@ -60,6 +62,7 @@ __device__ __forceinline__ void load_split(const __nv_bfloat16* hi, const __nv_b
 __global__ void pack_c8_kernel(const float* __restrict__ src0, int c0, const float* __restrict__ src1, int c1,
                                __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo, int c_pad, long long vox,
                                int batch) {
+  pdl_wait();
   const int chunks = c_pad / 8;
   long long total = (long long)batch * chunks * vox;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -157,6 +160,7 @@ __global__ void __launch_bounds__(STATS_THREADS) splitk_reduce_stats_kernel(cons
                                                                             __nv_bfloat16* __restrict__ raw_lo,
                                                                             float* __restrict__ partial, long long vox,
                                                                             int nseg) {
+  pdl_wait();
   const int plane = blockIdx.y, seg = blockIdx.x;
   const float4* p = reinterpret_cast<const float4*>(part) + (long long)plane * vox * 2;
   long long per = (vox + nseg - 1) / nseg;
@@ -263,6 +267,20 @@ __device__ __forceinline__ void stats_to_affine(const float* __restrict__ partia
   __syncthreads();
 }
 
+// The affine map alone, for consumers that normalise on load (conv3d_tc64 FUSE): out[plane][16] = scale[8], shift[8].
+__global__ void __launch_bounds__(256) in_affine_kernel(const float* __restrict__ partial, int nseg,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int chunks, double count, float eps, float* __restrict__ out) {
+  __shared__ float sc[8], sh[8];
+  __shared__ double scratch[256];
+  pdl_wait();
+  stats_to_affine(partial, nseg, blockIdx.x, gamma, beta, chunks, count, eps, sc, sh, scratch);
+  if (threadIdx.x < 8) {
+    out[blockIdx.x * 16 + threadIdx.x] = sc[threadIdx.x];
+    out[blockIdx.x * 16 + 8 + threadIdx.x] = sh[threadIdx.x];
+  }
+}
+
 __device__ __forceinline__ void norm_prologue(const NormActArgs& a, int plane, float* sc, float* sh, float* bi,
                                               double* scratch) {
   if (threadIdx.x < 8) bi[threadIdx.x] = a.bias ? a.bias[(plane % a.chunks) * 8 + threadIdx.x] : 0.f;
@@ -274,7 +292,7 @@ __device__ __forceinline__ void norm_apply(float (&f)[8], const float* sc, const
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float y = fmaf(f[j], sc[j], sh[j]);
-    y = y > 0.f ? y : y * slope;
+    y = fmaxf(y, y * slope);  // LeakyReLU for 0 < slope < 1
     f[j] = y + bi[j];
   }
 }
@@ -287,6 +305,7 @@ __global__ void __launch_bounds__(NORM_THREADS, (ADD || PREC) ? 3 : 4) norm_act_
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;  // n*chunks + chunk
+  pdl_wait();
   norm_prologue(a, plane, sc, sh, bi, scratch);
   const long long vox = (long long)a.D * a.H * a.W;
   const BF8* __restrict__ in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
@@ -347,6 +366,7 @@ __global__ void __launch_bounds__(NORM_THREADS, PREC ? 2 : 3) norm_act_pool_kern
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;
+  pdl_wait();
   norm_prologue(a, plane, sc, sh, bi, scratch);
   const long long vox = (long long)a.D * a.H * a.W;
   const BF8* __restrict__ in = reinterpret_cast<const BF8*>(a.raw) + plane * vox;
@@ -532,10 +552,6 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
   const int fch = a.F / 8;
   const int n = blockIdx.y;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  if (a.partial) {
-    for (int k = 0; k < fch; ++k)
-      stats_to_affine(a.partial, a.nseg, n * fch + k, a.gamma, a.beta, fch, (double)a.vox, a.eps, nsc + k * 8, nsh + k * 8, scratch);
-  }
   for (int i = threadIdx.x; i < nks * NT * 32; i += FINAL_THREADS) {
     const int l = i & 31, nt = (i >> 5) % NT, ks = i / (32 * NT);
     const int cls = nt * 8 + (l >> 2), k0 = ks * 16 + 2 * (l & 3);
@@ -558,6 +574,11 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
     dst[96] = pack_bf16x2(lo[2], lo[3]);
   }
   for (int i = threadIdx.x; i < NT * 8; i += FINAL_THREADS) sbias[i] = i < a.C ? a.b[i] : 0.f;
+  pdl_wait();  // the weight fragments above are plan constants; everything below depends on the previous kernels
+  if (a.partial) {
+    for (int k = 0; k < fch; ++k)
+      stats_to_affine(a.partial, a.nseg, n * fch + k, a.gamma, a.beta, fch, (double)a.vox, a.eps, nsc + k * 8, nsh + k * 8, scratch);
+  }
   __syncthreads();
 
   const float s_abp = sqrtf(a.abp), s_1mabp = sqrtf(1.f - a.abp - 0.f);
@@ -707,6 +728,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
 // to_vm: dst_vm = src (or 0 when src == nullptr);  from_vm: dst planar = src_vm.   thread = (voxel, 4 classes)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void state_to_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch) {
+  pdl_wait();
   const int q4 = CP / 4;
   const long long total = (long long)batch * vox * q4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -725,6 +747,7 @@ __global__ void state_to_vm_kernel(const float* __restrict__ src, float* __restr
 // dst = (accumulate ? dst : 0) + scale * src   (ensemble averaging over independent noise draws)
 __global__ void state_from_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch,
                                      float scale, int accumulate) {
+  pdl_wait();
   const int q4 = CP / 4;
   const long long total = (long long)batch * vox * q4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {

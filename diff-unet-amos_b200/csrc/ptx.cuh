@@ -27,6 +27,17 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
   return pred;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the per-step path is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may
+// become resident (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous kernel
+// of the stream is still draining.  pdl_wait() blocks until that previous grid has completed and its writes are
+// visible; nothing that reads or writes global memory touched by other kernels may precede it.  pdl_trigger() lets the
+// NEXT kernel start launching: it is issued when a CTA's main loop is done (measured: dependents pre-launched at the
+// start of a long persistent kernel sit on the SMs and cost the running kernel ~3 %), always after pdl_wait(), so at
+// most one dependent grid is pre-launched and only after every CTA of the running grid has been scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -119,6 +130,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, with the descriptors given as (low word, high word): every tile / tap / k-step offset only moves the 14-bit
+// start-address field of the low word, so the single issuing thread does 32-bit adds instead of 64-bit arithmetic.
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Arrive on an mbarrier once all tcgen05 ops previously issued by this thread have completed.

@@ -355,3 +355,26 @@ def test_fp32x3_batching_is_transparent():
     full = m(image=image, pred_type="ddim_sample", noise=noise)
     one = m(image=image[1:2], pred_type="ddim_sample", noise=noise[1:2])
     assert torch.equal(one[0], full[1])
+
+
+def test_normalise_on_load_is_bit_identical():
+    """DUNET_FLAG_FUSED_NORM (experimental): the second conv of a TwoConv normalises its input on load in shared memory
+    (conv3d_tc64 FUSE) instead of reading the tensor norm_act_kernel materialises.  Same fp32 formulas, same bf16
+    rounding points -> the whole DDIM window must agree bit for bit with the default path."""
+    cout, S = 3, 64
+    image, noise = seeded_image((2, 1, S, S, S)).cuda(), seeded_noise((2, cout, S, S, S)).cuda()
+    a = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=3)(image=image, pred_type="ddim_sample", noise=noise)
+    b = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=3, debug_flags=_lib.DUNET_FLAG_FUSED_NORM)(
+        image=image, pred_type="ddim_sample", noise=noise)
+    assert torch.equal(a, b)
+
+
+def test_cout64_kernel_block_size_variants_agree():
+    """The Cout = 64 kernel with 32-channel blocks / 13-slot ring (default) and with 64-channel blocks / 7-slot ring
+    (DUNET_FLAG_TC64_CB64) are two orderings of the same fp32 accumulation: they agree to bf16 rounding noise."""
+    cout, S = 3, 64
+    image, noise = seeded_image((1, 1, S, S, S)).cuda(), seeded_noise((1, cout, S, S, S)).cuda()
+    a = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=2)(image=image, pred_type="ddim_sample", noise=noise)
+    b = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=2, debug_flags=_lib.DUNET_FLAG_TC64_CB64)(
+        image=image, pred_type="ddim_sample", noise=noise)
+    assert rel_l2(a, b) < BF16_TOL

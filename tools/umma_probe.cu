@@ -49,6 +49,74 @@ __global__ void __launch_bounds__(128, 1) probe(Params p, long long* out) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// z-stacked tile pattern of conv3d_tc64: per in-plane tap, planes p = 0..5 feed slabs [max(p-2,0), min(p,3)] with one
+// N = 64 * nblk MMA per K=16 step; KC k-steps per plane back to back (KC = 4: 64-channel blocks, 2: 32-channel blocks).
+// order 0: p outer / k inner (the kernel's order); 1: k outer / p inner; 2: planes interleaved so that consecutive
+// MMAs touch disjoint accumulator columns where possible (0,4,1,5,2,3)
+template <int KC, int ORDER>
+__global__ void __launch_bounds__(128, 1) probe_tile(int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + i * 4), "r"(0x3f803f80u));
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(&tslot), 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tslot;
+  if (warp == 1 && elect_one_sync()) {
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int perm[6] = {0, 4, 1, 5, 2, 3};
+      if (ORDER == 1) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k)
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+            const int lo = p >= 2 ? p - 2 : 0, hi = p < 4 ? p : 3, nblk = hi - lo + 1;
+            umma_bf16(tmem + lo * 64, make_smem_desc(base + p * 23040 + k * 5760, 2880, 160),
+                      make_smem_desc(base + 150 * 1024 + k * 6144, 3072, 128), make_idesc_bf16(128, 64 * nblk), 1u);
+          }
+      } else {
+#pragma unroll
+        for (int pp = 0; pp < 6; ++pp) {
+          const int p = ORDER == 2 ? perm[pp] : pp;
+          const int lo = p >= 2 ? p - 2 : 0, hi = p < 4 ? p : 3, nblk = hi - lo + 1;
+#pragma unroll
+          for (int k = 0; k < KC; ++k)
+            umma_bf16(tmem + lo * 64, make_smem_desc(base + p * 23040 + k * 5760, 2880, 160),
+                      make_smem_desc(base + 150 * 1024 + k * 6144, 3072, 128), make_idesc_bf16(128, 64 * nblk), 1u);
+        }
+      }
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    long long t2 = clock64();
+    out[blockIdx.x] = t2 - t0;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+template <int KC, int ORDER>
+void run_tile(long long* d) {
+  cudaFuncSetAttribute(probe_tile<KC, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  const int iters = 512;
+  probe_tile<KC, ORDER><<<148, 128, 220 * 1024>>>(iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("probe_tile: CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
+  long long h[148];
+  cudaMemcpy(h, d, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+  double tot = 0;
+  for (int i = 0; i < 148; ++i) tot += h[i];
+  const double cyc = tot / 148 / iters, ideal = 416.0 * KC;
+  printf("z-stacked tap, KC=%d order %d: %.0f cyc per tap (operand-fetch ideal %.0f => %.0f%%)\n", KC, ORDER, cyc, ideal, 100 * ideal / cyc);
+}
+
 template <int N>
 void run(const char* name, Params p, long long* d) {
   cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -77,5 +145,7 @@ int main() {
   run<192>("conv layout", {160, 2880, 512, 0}, d);
   run<256>("conv layout", {160, 2880, 512, 0}, d);
   run<32>("conv layout", {160, 2880, 512, 0}, d);
+  run_tile<4, 0>(d); run_tile<2, 0>(d); run_tile<4, 1>(d); run_tile<2, 1>(d); run_tile<4, 2>(d); run_tile<2, 2>(d);
+  run_tile<1, 0>(d); run_tile<8, 0>(d);
   return 0;
 }
