@@ -1318,6 +1318,22 @@ int dunet_finalize(float* out_volume, const int32_t v[3], int32_t channels, cons
   return 0;
 }
 
+int dunet_dice_counts(const uint8_t* pred, const void* label, int32_t label_is_float, int32_t channels, int64_t voxels,
+                      uint64_t* counts, void* stream) {
+  if (!pred || !label || !counts || channels < 1 || voxels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)channels * 3 * sizeof(uint64_t), st));
+  const dim3 grid(grid_for(voxels, 256, 148 * 8 / std::max(1, std::min(channels, 8))), channels);
+  if (label_is_float)
+    dice_counts_kernel<float><<<grid, 256, 0, st>>>(pred, static_cast<const float*>(label), (long long)voxels,
+                                                    reinterpret_cast<unsigned long long*>(counts));
+  else
+    dice_counts_kernel<uint8_t><<<grid, 256, 0, st>>>(pred, static_cast<const uint8_t*>(label), (long long)voxels,
+                                                      reinterpret_cast<unsigned long long*>(counts));
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t c1, const float* weight, int32_t cout,
                        float* out, int32_t B, const int32_t dims[3], int32_t use_ref, void* stream) {
   if (!src0 || !weight || !out || !dims || c0 < 1 || cout < 1 || B < 1) return fail(DUNET_E_INVALID, "bad argument");

@@ -868,6 +868,38 @@ __global__ void finalize_kernel(float* __restrict__ vol, const int* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-class Dice inputs (reference metric.py:3-49 dice_coeff as used by Tester.validation_step, test.py:143-151):
+// counts[c] = { |pred_c & label_c|, |pred_c|, |label_c| } as exact 64-bit integers.  pred: uint8 {0,1} [C][vox] (the
+// binary volume finalize_kernel writes); label: uint8 or fp32 one-hot [C][vox], non-zero = foreground.
+// grid = (blocks, C); integer atomics -> order-independent, exact.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename LabelT>
+__global__ void __launch_bounds__(256) dice_counts_kernel(const uint8_t* __restrict__ pred, const LabelT* __restrict__ label,
+                                                          long long vox, unsigned long long* __restrict__ counts) {
+  const int c = blockIdx.y;
+  const uint8_t* p = pred + (long long)c * vox;
+  const LabelT* l = label + (long long)c * vox;
+  unsigned int inter = 0, np = 0, nl = 0;  // < 2^32 per thread: vox / threads is far below that
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < vox; v += (long long)gridDim.x * blockDim.x) {
+    const bool a = p[v] != 0, b = l[v] != LabelT(0);
+    inter += (a && b) ? 1u : 0u;
+    np += a ? 1u : 0u;
+    nl += b ? 1u : 0u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    inter += __shfl_xor_sync(0xffffffffu, inter, o);
+    np += __shfl_xor_sync(0xffffffffu, np, o);
+    nl += __shfl_xor_sync(0xffffffffu, nl, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(counts + c * 3 + 0, (unsigned long long)inter);
+    atomicAdd(counts + c * 3 + 1, (unsigned long long)np);
+    atomicAdd(counts + c * 3 + 2, (unsigned long long)nl);
+  }
+}
+
 __global__ void fill_zero_kernel(float4* p, long long n4) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
     p[i] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -139,6 +139,14 @@ int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channel
                    const int32_t* counts_h, const int32_t* counts_w, uint8_t* binary, uint8_t* argmax_labels,
                    void* stream);
 
+/* replaces: the per-class reductions of dice_coeff (metric.py:3-49) as Tester.validation_step calls it on the binarised
+ * volume (test.py:143-151).  pred: uint8 {0,1} [channels][voxels] (dunet_finalize's `binary`); label: one-hot
+ * [channels][voxels], uint8 or fp32 (label_is_float), non-zero = foreground.  counts (device, [channels][3] uint64):
+ * { |pred & label|, |pred|, |label| } -- exact integers; the Dice value and the reference's special cases
+ * (pred non-empty & label empty -> 1; both empty -> 0) are host arithmetic on these. */
+int dunet_dice_counts(const uint8_t* pred, const void* label, int32_t label_is_float, int32_t channels, int64_t voxels,
+                      uint64_t* counts, void* stream);
+
 /* Stand-alone operator (also the unit-test seam of the tensor-core kernel): y = conv3d(cat([src0, src1]), weight),
  * 3x3x3, stride 1, zero padding 1, no bias.  fp32 NCDHW in/out, bf16 operands + fp32 accumulation inside.
  * use_ref_kernel: 0 = production tcgen05 kernels, 1 = CUDA-core debug kernel, 2 = generic tcgen05 kernel only,

@@ -378,3 +378,39 @@ def test_cout64_kernel_block_size_variants_agree():
     b = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=2, debug_flags=_lib.DUNET_FLAG_TC64_CB64)(
         image=image, pred_type="ddim_sample", noise=noise)
     assert rel_l2(a, b) < BF16_TOL
+
+
+def test_engine_dropin_dice_matches_oracle(tmp_path):
+    """EngineB200 (Tester / Engine.infer mirror): checkpoint round trip through torch.save({'model': ...}), window
+    driver + binarisation, and GPU Dice counts == the oracle metric on the same binary volumes (exact integers)."""
+    from oracle import oracle_metric
+
+    cout, S, vol = 3, 32, (40, 48, 32)
+    src = _build(cout, S, SMALL)
+    ckpt = tmp_path / "final_model.pt"
+    torch.save({"model": {k: v.cpu() for k, v in src.state_dict().items()}}, ckpt)
+    torch.manual_seed(123)  # different init: the checkpoint must overwrite it
+    m = pkg.DiffUNetB200(in_channels=1, out_channels=cout, image_size=S, spatial_size=S, features=SMALL)
+    e = pkg.EngineB200(m, class_names={0: "bg", 1: "liver", 2: "spleen"}, sw_batch_size=2, overlap=0.25)
+    e.load_checkpoint(str(ckpt))
+    for k, v in e.model.state_dict().items():
+        assert torch.equal(v.cpu(), src.state_dict()[k].cpu()), k
+    image = seeded_image((1, 1) + vol)
+    torch.manual_seed(9)
+    label = (torch.rand(1, cout, *vol) > 0.6).float()
+    label[:, 2] = 0  # an empty class: exercises the "prediction non-empty, label empty -> 1" rule
+    n_win = len(pkg.window_starts(vol, (S, S, S), 0.25))
+    noise = seeded_noise((n_win, cout, S, S, S)).cuda()
+    nf = lambda w, b: noise[w:w + b]
+    img, outputs, labels = e.infer({"image": image, "label": label}, noise_fn=nf)
+    assert outputs.shape == label.shape and set(outputs.unique().tolist()) <= {0.0, 1.0}
+    ref_out, ref_lab = pkg.infer_volume(src, image.cuda(), sw_batch_size=2, overlap=0.25, noise_fn=nf)
+    assert torch.equal(outputs, ref_lab)  # same binarisation as infer_volume's torch sigmoid > 0.5
+    mean = e.validation_step({"image": image, "label": label}, noise_fn=nf)
+    exp = oracle_metric.per_class_dice(outputs.cpu(), label)
+    assert list(e.dices[-1].values()) == pytest.approx(exp, abs=1e-12)
+    assert mean == pytest.approx(sum(exp) / len(exp), abs=1e-12)
+    counts = pkg.dice_counts(outputs[0].to(torch.uint8), label[0].cuda())
+    for c in range(cout):
+        o, l = outputs[0, c].cpu().bool(), label[0, c].bool()
+        assert counts[c].tolist() == [int((o & l).sum()), int(o.sum()), int(l.sum())]
