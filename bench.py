@@ -154,11 +154,11 @@ def run_b200(args):
 
     torch.manual_seed(0)
     model = pkg.DiffUNetB200(in_channels=1, out_channels=CLASSES, image_size=ROI[1], spatial_size=ROI[0], features=FEATURES,
-                             batch_max=args.sw_batch).to(dev).eval()
+                             batch_max=args.sw_batch, precision=args.precision).to(dev).eval()
     torch.manual_seed(1)
     host_vol = torch.rand(1, 1, *VOLUME).pin_memory()
     dev_vol = host_vol.to(dev)
-    starts = pkg.window_starts(VOLUME, ROI, OVERLAP)
+    starts = pkg.window_starts(VOLUME, ROI, args.overlap)
     n_win = len(starts)
     lo, hi = pkg.shard_range(n_win, rank, world)
     gen = torch.Generator(device=dev)
@@ -167,7 +167,7 @@ def run_b200(args):
 
     def one_volume(volume_dev):
         """the hot path for this rank's shard of windows, then the single NCCL exchange + finalize on rank 0"""
-        buf = StitchBuffers(CLASSES, VOLUME, ROI, OVERLAP, dev)
+        buf = StitchBuffers(CLASSES, VOLUME, ROI, args.overlap, dev)
         for g in range(lo, hi, args.sw_batch):
             grp = starts[g:min(g + args.sw_batch, hi)]
             batch = crop_windows(volume_dev[0], grp, ROI)
@@ -235,8 +235,8 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "features": list(FEATURES), "classes": CLASSES, "sw_batch": args.sw_batch,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class split operands)", "data": "synthetic",
+            "config": {"workload": WORKLOAD if args.overlap == OVERLAP else WORKLOAD.replace("overlap 0.25 (98 windows)", f"overlap {args.overlap} ({n_win} windows)"), "features": list(FEATURES), "classes": CLASSES, "sw_batch": args.sw_batch,
                        "windows_per_step": n_win, "windows_this_rank": hi - lo, "volumes_per_s": value / n_win,
                        "l2": "inputs larger than L2 (each window streams > 1 GB of activations; no flush needed)",
                        "algorithmic_tflop_per_window": GFLOP_PER_WINDOW / 1e3,
@@ -291,6 +291,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sw-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", type=float, default=OVERLAP, help="0.25 = test.py:30 default (98 windows); 0.8 = cfg/btcv, cfg/msd (2645 windows)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
