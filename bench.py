@@ -209,14 +209,27 @@ def run_b200(args):
         _lib.check(lib.dunet_profile_read_all(fam_ms, fam_n, fam_b))
         _lib.check(lib.dunet_profile_enable(0))
         # ---------------- end-to-end leg: host volume in, host labels out, every step ----------------
+        # Both copies of every step are inside the timed region.  They run on a side stream so that the D2H of volume i's
+        # labels overlaps the windows of volume i + 1 (two pinned label buffers); the last D2H is waited for before the
+        # closing event.
         barrier()
+        copy_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        host_labels2 = [host_labels, torch.empty_like(host_labels).pin_memory()] if rank == 0 else None
+        main = torch.cuda.current_stream()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(args.steps):
-            v = host_vol.to(dev, non_blocking=True)          # H2D of the step's input from pinned memory
+        for it in range(args.steps):
+            with torch.cuda.stream(copy_stream):
+                v = host_vol.to(dev, non_blocking=True)      # H2D of the step's input from pinned memory
+            main.wait_stream(copy_stream)
+            v.record_stream(main)
             lab = one_volume(v)
             if rank == 0:
-                host_labels.copy_(lab, non_blocking=True)    # D2H of the step's result (binary label volume)
+                d2h_stream.wait_stream(main)
+                with torch.cuda.stream(d2h_stream):
+                    host_labels2[it % 2].copy_(lab, non_blocking=True)  # D2H of the step's result (binary label volume)
+                lab.record_stream(d2h_stream)
+        main.wait_stream(d2h_stream)
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
