@@ -57,12 +57,20 @@ struct ConvTc {
   static constexpr int B_LBO = N_TILE * 16;
   static constexpr int B_SBO = 128;
   static constexpr int PLANES = ZT + 2 * HALO;
-  static constexpr int A_SLOTS = MODE == MODE_CONV3 ? 8 : 2 * PLANES;  // transposed conv: small ring -> 2 CTAs per SM
-  static constexpr int W_SLOTS = (32768 / W_UNIT_BYTES) < 2 ? 2 : ((32768 / W_UNIT_BYTES) > 8 ? 8 : (32768 / W_UNIT_BYTES));
+  // Ring sizes.  Deep U-Net levels are WEIGHT-STREAMING bound: every work item reads 27 weight tiles (16 KB each for
+  // 64 x 128) that feed only ZT * CB_CH/16 MMAs, and a bulk copy takes ~2.5k clocks under load, so a 2-slot ring
+  // delivered 13 B/clk/SM where the MMAs want 32 (measured with tools/deep_timeline.py: 31k clocks per item against
+  // 13.8k of MMA time).  The plane ring keeps one block + 1-2 planes of look-ahead, everything else goes to weights.
+  static constexpr int A_SLOTS = MODE == MODE_CONV3 ? (ZT <= 2 ? PLANES + 2 : PLANES + 1) : 2 * PLANES;
+  static constexpr int RED_BYTES_ = 4 * N_TILE * 2 * 4;
+  static constexpr int W_FIT = (232448 - 1024 - 512 - RED_BYTES_ - A_SLOTS * PLANE_BYTES) / W_UNIT_BYTES;
+  static constexpr int W_SLOTS = MODE == MODE_CONV3 ? (W_FIT < 2 ? 2 : (W_FIT > 8 ? 8 : W_FIT))
+                                                    : ((32768 / W_UNIT_BYTES) < 2 ? 2 : ((32768 / W_UNIT_BYTES) > 8 ? 8 : (32768 / W_UNIT_BYTES)));
   static constexpr int TMEM_COLS = (ZT * N_TILE <= 32) ? 32 : (ZT * N_TILE <= 64) ? 64 : (ZT * N_TILE <= 128) ? 128
                                    : (ZT * N_TILE <= 256) ? 256 : 512;
   static constexpr int RED_BYTES = 4 * N_TILE * 2 * 4;      // epilogue statistics exchange between the 4 warps
-  static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + RED_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + RED_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert(16 * A_SLOTS + 16 * W_SLOTS + 40 <= 512, "barrier block");
   static_assert(ZT * N_TILE <= 512, "accumulators exceed TMEM");
   static_assert(A_SLOTS >= PLANES, "ring must hold one input-channel block");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -209,6 +217,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 1] = clock64();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -260,7 +269,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
     // of the low descriptor word ever changes).
     if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE);
-      static_assert((Cfg::W_SLOTS & (Cfg::W_SLOTS - 1)) == 0, "W_SLOTS must be a power of two");
       const uint64_t a_desc0 = make_smem_desc(a_smem, Cfg::A_LBO, Cfg::A_SBO);
       const uint64_t b_desc0 = make_smem_desc(w_smem, Cfg::B_LBO, Cfg::B_SBO);
       const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
@@ -284,7 +292,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
           // one weight tap (tz compile-time, tyx run-time): ZT slabs x CB_CH/16 k-steps
           auto tap = [&](auto tzc, int tyx) {
             constexpr int TZI = decltype(tzc)::value;
-            const int ws = w & (Cfg::W_SLOTS - 1);
+            const int ws = w % Cfg::W_SLOTS;
             mbar_wait(w_full + 8 * ws, (w / Cfg::W_SLOTS) & 1);
             tc_fence_after();
             if (tyx == 0) {  // planes first read in this tz phase: all ZT for tz = 0, one more for each later phase
@@ -294,6 +302,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
                 tc_fence_after();
               }
             }
+            if (a.dbg && w == 0) a.dbg[blockIdx.x * 8 + 3] = clock64();  // first operands have arrived
             const uint32_t tap16 = (tyx / 3) * Cfg::HX + (tyx % 3);  // tap offset in 16-byte units
             const uint32_t bl_u = b_lo0 + ws * (Cfg::W_UNIT_BYTES >> 4);
             const uint32_t acc0 = (first_cb && TZI == 0 && tyx == 0) ? 0u : 1u;  // very first MMA of a slab overwrites
@@ -347,6 +356,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
       const int buf = li % NBUF, use = li / NBUF;
       mbar_wait(acc_full + 8 * buf, use & 1);
       tc_fence_after();
+      if (a.dbg && li == 0 && threadIdx.x == 3 * 32) a.dbg[blockIdx.x * 8 + 4] = clock64();  // first accumulators complete
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
 #pragma unroll 1
       for (int j = 0; j < N_TILE / 16; ++j) {
@@ -424,6 +434,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
       }
     }
   }
+  if (a.dbg && threadIdx.x == 3 * 32) { a.dbg[blockIdx.x * 8 + 5] = clock64(); a.dbg[blockIdx.x * 8 + 6] = (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x; }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();

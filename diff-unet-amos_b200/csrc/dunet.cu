@@ -446,6 +446,7 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
 
 // ------------------------------------------------------------------------------------------------ layer launchers
 static long long* g_conv_dbg = nullptr;  // optional per-CTA timeline buffer (tools only)
+static int g_conv_dbg_count = 0;
 static int g_num_sms = 0;
 
 static int ensure_num_sms() {
@@ -586,7 +587,11 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
   a.cout = c.coutp; a.D = D; a.H = H; a.W = W;
   a.tiles_x = g.tiles_x; a.tiles_y = g.tiles_y; a.tiles_z = g.tiles_z; a.n_tiles = c.n_tiles; a.batch = B;
   a.ksplit = want_split;
-  a.dbg = g_conv_dbg;
+  {  // tools: stamp only the DUNET_DBG_LAUNCH-th generic conv launch since the buffer was set (default: every launch)
+    static const int target = [] { const char* e = getenv("DUNET_DBG_LAUNCH"); return e ? atoi(e) : -1; }();
+    a.dbg = (g_conv_dbg && (target < 0 || g_conv_dbg_count == target)) ? g_conv_dbg : nullptr;
+    if (g_conv_dbg) ++g_conv_dbg_count;
+  }
   if (a.ksplit > 1) a.out_partial = splitk;
   else a.stats = partial;
   int rc;
@@ -720,7 +725,7 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
     memset(&b, 0, sizeof b);
     b.w = d.packed_tc; b.out = out.hi; b.bias = d.bias; b.chunks_in = d.cinp / 8; b.cout = d.coutp; b.D = D; b.H = H; b.W = W;
     b.tiles_x = (W + CONV_TX - 1) / CONV_TX; b.tiles_y = (H + CONV_TY - 1) / CONV_TY; b.tiles_z = (D + 1) / 2;
-    b.n_tiles = 8 * d.coutp / 128; b.batch = B; b.dbg = g_conv_dbg;
+    b.n_tiles = 8 * d.coutp / 128; b.batch = B; b.dbg = getenv("DUNET_DBG_DECONV") ? g_conv_dbg : nullptr;
     TRY(ensure_num_sms());
     const long long tiles = (long long)b.tiles_x * b.tiles_y * b.tiles_z * B;
     const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
@@ -1437,6 +1442,7 @@ int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, con
 
 int dunet_debug_set_conv_timeline(int64_t* dev_buffer) {
   g_conv_dbg = reinterpret_cast<long long*>(dev_buffer);
+  g_conv_dbg_count = 0;
   return 0;
 }
 
