@@ -154,7 +154,8 @@ def run_b200(args):
 
     torch.manual_seed(0)
     model = pkg.DiffUNetB200(in_channels=1, out_channels=CLASSES, image_size=ROI[1], spatial_size=ROI[0], features=FEATURES,
-                             batch_max=args.sw_batch, precision=args.precision).to(dev).eval()
+                             batch_max=args.sw_batch, precision=args.precision,
+                             dual_stream=bool(args.dual_stream)).to(dev).eval()
     torch.manual_seed(1)
     host_vol = torch.rand(1, 1, *VOLUME).pin_memory()
     dev_vol = host_vol.to(dev)
@@ -251,6 +252,7 @@ def run_b200(args):
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class split operands)", "data": "synthetic",
             "config": {"workload": WORKLOAD if args.overlap == OVERLAP else WORKLOAD.replace("overlap 0.25 (98 windows)", f"overlap {args.overlap} ({n_win} windows)"), "features": list(FEATURES), "classes": CLASSES, "sw_batch": args.sw_batch,
                        "windows_per_step": n_win, "windows_this_rank": hi - lo, "volumes_per_s": value / n_win,
+                       "dual_stream": "e2e leg only (half batches on two internal streams; off while per-kernel profiling is on)" if args.dual_stream else "off",
                        "l2": "inputs larger than L2 (each window streams > 1 GB of activations; no flush needed)",
                        "algorithmic_tflop_per_window": GFLOP_PER_WINDOW / 1e3,
                        "whole_path_tflops": value * GFLOP_PER_WINDOW / 1e3,
@@ -306,6 +308,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", type=float, default=OVERLAP, help="0.25 = test.py:30 default (98 windows); 0.8 = cfg/btcv, cfg/msd (2645 windows)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"])
+    ap.add_argument("--dual-stream", type=int, default=1, help="DUNET_FLAG_DUAL_STREAM: two half batches on two internal streams (the product default; "
+                    "inactive in the profiled device-resident leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

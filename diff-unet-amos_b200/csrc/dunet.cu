@@ -1260,7 +1260,7 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t per_step_stride = (size_t)B * p->C * p->V[0];
-  const bool dual = B >= 2 && run_encoder && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on;
+  const bool dual = B >= 4 && run_encoder && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on;
   if (!dual)
     return ddim_sample_impl(p, image, noise, acc_out, per_step_logits, per_step_stride, final_x, B, run_encoder, out_scale,
                             out_accumulate, ws, st);

@@ -308,7 +308,7 @@ class DiffUNetB200(nn.Module):
     def __init__(self, spatial_dims: int = 3, in_channels: int = 3, out_channels: int = 1, image_size=96,
                  spatial_size=96, features: Sequence[int] = DEFAULT_FEATURES, dropout: float = 0.2,
                  timesteps: int = 1000, mode: str = "train", *, num_steps: int = 10, batch_max: int = 4,
-                 debug_flags: int = 0, precision: str = "bf16"):
+                 debug_flags: int = 0, precision: str = "bf16", dual_stream: bool = True):
         super().__init__()
         if spatial_dims != 3:
             raise NotImplementedError("only spatial_dims == 3")
@@ -328,6 +328,8 @@ class DiffUNetB200(nn.Module):
         self.num_steps, self.batch_max, self.debug_flags = int(num_steps), int(batch_max), int(debug_flags)
         if precision == "fp32x3":
             self.debug_flags |= _lib.DUNET_FLAG_FP32X3
+        if dual_stream:  # batches of >= 4 windows: two half batches on two internal streams (bit-identical results)
+            self.debug_flags |= _lib.DUNET_FLAG_DUAL_STREAM
         self.timesteps = timesteps
         self.schedule = DdimSchedule.build(self.num_steps, timesteps)
         holder = _Node()

@@ -41,9 +41,11 @@ enum {
 
 #define DUNET_FLAG_GENERIC_CONV 4u /* debug: route Cout = 64 convs through the generic tcgen05 kernel (no z-stacking) */
 
-#define DUNET_FLAG_DUAL_STREAM 8u /* experimental: run the two halves of a window batch on two internal streams (measured:
-                                    +3 % at batch 4, large loss at batch 2 -- the persistent conv kernels use a static tile
-                                    schedule and do not share SMs gracefully; off by default) */
+#define DUNET_FLAG_DUAL_STREAM 8u /* batches of >= 4 windows run as two half batches on two internal streams (forked from /
+                                    joined into the caller's stream with events, no host synchronisation): the HBM-bound
+                                    kernels of one half overlap the tensor-bound convolutions of the other.  Measured +3 %
+                                    at batch 4 and 8; results are bit-identical (batching is transparent).  Not used while
+                                    dunet_profile_enable(1) is active (per-kernel timings would overlap) */
 
 #define DUNET_FLAG_FP32X3 16u /* fp32-class precision mode ("fp32x3"): every activation and weight is a
                                  hi + lo pair of bf16 tensors and each product is formed as hi*hi + lo*hi + hi*lo on the
