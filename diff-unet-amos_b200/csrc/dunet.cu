@@ -329,6 +329,10 @@ struct dunet_plan {
   float* temb_table = nullptr;
   int temb_row = 0, temb_off[9];
   bool committed = false;
+  // layout the embeddings currently held in a workspace were written with: (batch, dual-stream halves or not).  A later
+  // dunet_ddim_sample(run_encoder = 0) must read them back through the same layout.
+  int emb_B = 0;
+  bool emb_dual = false;
   std::vector<void*> owned;
   // two internal streams: the two halves of a window batch run out of phase so that the HBM-bound kernels of one half
   // (normalise, final/DDIM, transposed conv) overlap the tensor-core-bound convolutions of the other
@@ -1163,6 +1167,7 @@ int dunet_workspace_bytes(const dunet_plan* p, int32_t batch, size_t* out) {
 int dunet_encode(dunet_plan* p, const float* image, int32_t B, void* workspace, void* stream) {
   TRY(check_call(p, B, workspace));
   if (!image || !aligned16(image)) return fail(DUNET_E_INVALID, "image must be a 16-byte aligned device pointer");
+  p->emb_B = B; p->emb_dual = false;
   return encode_impl(p, image, B, static_cast<uint8_t*>(workspace), ws_layout(p, B), static_cast<cudaStream_t>(stream));
 }
 
@@ -1180,6 +1185,7 @@ int dunet_get_embedding(dunet_plan* p, int32_t level, float* out, int32_t B, voi
 int dunet_set_embedding(dunet_plan* p, int32_t level, const float* in, int32_t B, void* workspace, void* stream) {
   TRY(check_call(p, B, workspace));
   if (level < 0 || level > 4 || !in) return fail(DUNET_E_INVALID, "bad level / NULL in");
+  p->emb_B = B; p->emb_dual = false;
   const WsLayout L = ws_layout(p, B);
   return launch_pack(p, in, p->fr[level], nullptr, 0, ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B),
                      p->fp[level], p->V[level], B, static_cast<cudaStream_t>(stream));
@@ -1260,7 +1266,9 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t per_step_stride = (size_t)B * p->C * p->V[0];
-  const bool dual = B >= 4 && run_encoder && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on;
+  const bool dual = run_encoder ? (B >= 4 && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on)
+                                : (p->emb_dual && p->emb_B == B);
+  if (run_encoder) { p->emb_B = B; p->emb_dual = dual; }
   if (!dual)
     return ddim_sample_impl(p, image, noise, acc_out, per_step_logits, per_step_stride, final_x, B, run_encoder, out_scale,
                             out_accumulate, ws, st);
