@@ -414,3 +414,53 @@ def test_engine_dropin_dice_matches_oracle(tmp_path):
     for c in range(cout):
         o, l = outputs[0, c].cpu().bool(), label[0, c].bool()
         assert counts[c].tolist() == [int((o & l).sum()), int(o.sum()), int(l.sum())]
+
+
+def test_non_cubic_window_vs_oracle():
+    """spatial_size != image_size (engine.py:169 builds the window as (spatial_size, image_size, image_size)) and a
+    non-square in-plane size: every level has D != H != W."""
+    cout, patch = 2, (32, 48, 64)
+    torch.manual_seed(0)
+    m = pkg.DiffUNetB200(in_channels=1, out_channels=cout, image_size=patch[1:], spatial_size=patch[0], features=SMALL).cuda().eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    image, noise = seeded_image((1, 1) + patch), seeded_noise((1, cout) + patch)
+    with torch.no_grad():
+        out = m(image=image.cuda(), pred_type="ddim_sample", noise=noise.cuda())
+        e = oracle_model.encoder_forward(sd, image)
+        ref = oracle_ddim.ddim_sample_window(lambda x, t: oracle_model.denoiser_forward(sd, x, t, image, e), noise)
+    assert rel_l2(out.cpu(), ref["sample_return"]) < BF16_TOL
+
+
+def test_volume_smaller_than_roi_is_padded_and_cropped():
+    """MONAI pads a volume that is smaller than the roi symmetrically (floor on the low side) and crops the result back;
+    bit-exact against the restated driver with an fp32 predictor both sides evaluate identically."""
+    image = torch.arange(20 * 40 * 36, dtype=torch.float32).reshape(1, 1, 20, 40, 36) / 1000.0
+    pred = lambda b, **kw: torch.cat([b * 2.0, b + 1.0], 1)
+    ref = oracle_sliding.sliding_window_inference(image, (32, 32, 32), 2, lambda b, window_indices=None: pred(b), 0.25)
+    got = pkg.sliding_window_inference(image.cuda(), (32, 32, 32), 2, pred, 0.25)
+    assert got.shape == ref.shape and torch.equal(got.cpu(), ref)
+
+
+def test_error_behaviour_matches_the_reference_seams():
+    """diffusion.py:54,62-63: unknown pred_type -> NotImplementedError; plus the B200 path's own loud failures: CPU
+    tensors, wrong window shape, batch above batch_max, and C-ABI argument checks (negative code + message)."""
+    m = _build(2, 32, SMALL, batch_max=2)
+    img = seeded_image((1, 1, 32, 32, 32))
+    with pytest.raises(NotImplementedError):
+        m(image=img.cuda(), pred_type="no_such_type")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(image=img, pred_type="ddim_sample")
+    with pytest.raises(ValueError):
+        m(image=seeded_image((1, 1, 32, 32, 48)).cuda(), pred_type="ddim_sample")
+    with pytest.raises(ValueError, match="batch_max"):
+        m(image=seeded_image((3, 1, 32, 32, 32)).cuda(), pred_type="ddim_sample")
+    lib = _lib.load()
+    assert lib.dunet_workspace_bytes(None, 1, ctypes.byref(ctypes.c_size_t())) == -1  # DUNET_E_INVALID
+    assert b"NULL" in lib.dunet_last_error()
+    cfg = _lib.DunetCfg()
+    cfg.num_classes, cfg.in_channels, cfg.batch_max, cfg.num_steps, cfg.flags = 2, 1, 1, 10, 0
+    cfg.patch = (ctypes.c_int32 * 3)(16, 32, 32)  # 16^3 fails in the reference too (SURVEY 8c)
+    cfg.features = (ctypes.c_int32 * 6)(*SMALL)
+    plan = ctypes.c_void_p()
+    assert lib.dunet_plan_create(ctypes.byref(plan), ctypes.byref(cfg)) == -1
+    assert b">= 32" in lib.dunet_last_error()
