@@ -2,10 +2,10 @@
 from ._lib import DunetError, load as load_library
 from .dist import infer_volume_distributed, my_window_range, reduce_partial_volume
 from .engine import EngineB200, dice_counts, dice_from_counts
-from .inference import StitchBuffers, infer_volume, sliding_window_inference
+from .inference import StitchBuffers, infer_volume, scale_intensity_range, sliding_window_inference
 from .model import DEFAULT_FEATURES, DiffUNetB200
 from .schedule import DdimSchedule
-from .windows import axis_counts, scan_intervals, shard_range, window_starts
+from .windows import axis_counts, gaussian_importance_map, scan_intervals, shard_range, window_starts
 
 
 def model_hub(model_name: str, **kwargs):
@@ -16,6 +16,6 @@ def model_hub(model_name: str, **kwargs):
     raise NotImplementedError(f"No such model : {model_name}")
 
 
-__all__ = ["DiffUNetB200", "EngineB200", "dice_counts", "dice_from_counts", "DEFAULT_FEATURES", "DdimSchedule", "DunetError", "StitchBuffers", "axis_counts",
+__all__ = ["DiffUNetB200", "EngineB200", "gaussian_importance_map", "scale_intensity_range", "dice_counts", "dice_from_counts", "DEFAULT_FEATURES", "DdimSchedule", "DunetError", "StitchBuffers", "axis_counts",
            "infer_volume", "infer_volume_distributed", "load_library", "my_window_range", "reduce_partial_volume", "model_hub", "scan_intervals", "shard_range", "sliding_window_inference",
            "window_starts"]

@@ -1331,6 +1331,36 @@ int dunet_finalize(float* out_volume, const int32_t v[3], int32_t channels, cons
   return 0;
 }
 
+int dunet_stitch_add_weighted(float* out_volume, float* count_volume, const int32_t v[3], int32_t channels, const float* patch,
+                              const float* weights, const int32_t pd[3], const int32_t s[3], void* stream) {
+  if (!out_volume || !count_volume || !patch || !weights || !v || !pd || !s || channels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  TRY(check_box(v, pd, s));
+  stitch_add_weighted_kernel<<<grid_for((long long)channels * pd[0] * pd[1] * pd[2], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out_volume, count_volume, patch, weights, channels, v[0], v[1], v[2], pd[0], pd[1], pd[2], s[0], s[1], s[2]);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_finalize_weighted(float* out_volume, const float* count_volume, const int32_t v[3], int32_t channels, uint8_t* binary,
+                            uint8_t* argmax_labels, void* stream) {
+  if (!out_volume || !count_volume || !v || channels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  const long long vv = (long long)v[0] * v[1] * v[2];
+  finalize_weighted_kernel<<<grid_for(vv, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out_volume, count_volume, binary,
+                                                                                            argmax_labels, channels, vv);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_scale_intensity(const float* in, float* out, int64_t n, float a_min, float a_max, float b_min, float b_max, int32_t clip,
+                          void* stream) {
+  if (!in || !out || n < 1) return fail(DUNET_E_INVALID, "bad argument");
+  if (!(a_max > a_min)) return fail(DUNET_E_INVALID, "a_max must exceed a_min");
+  scale_intensity_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, (long long)n, a_min, a_max, b_min,
+                                                                                       b_max, clip);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int dunet_dice_counts(const uint8_t* pred, const void* label, int32_t label_is_float, int32_t channels, int64_t voxels,
                       uint64_t* counts, void* stream) {
   if (!pred || !label || !counts || channels < 1 || voxels < 1) return fail(DUNET_E_INVALID, "bad argument");

@@ -832,6 +832,60 @@ __global__ void stitch_add_kernel(float* __restrict__ vol, const float* __restri
   }
 }
 
+// Weighted variant for MONAI's mode="gaussian" blend (not used by the reference's own call, engine.py:173-177):
+//   out[slices] += w * pred ; count[slices] += w      with w the clamped gaussian importance map of the window.
+// Multiply and add are kept separate (no FMA contraction) so the fp32 result matches torch's `importance_map * pred` then `+=`.
+__global__ void stitch_add_weighted_kernel(float* __restrict__ vol, float* __restrict__ cnt, const float* __restrict__ patch,
+                                           const float* __restrict__ w, int C, int VD, int VH, int VW, int PD, int PH, int PW,
+                                           int sz, int sy, int sx) {
+  const long long pv = (long long)PD * PH * PW;
+  const long long total = (long long)C * pv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % pv;
+    const int x = (int)(v % PW), y = (int)((v / PW) % PH), z = (int)(v / ((long long)PW * PH));
+    const int c = (int)(i / pv);
+    const long long o = ((long long)(sz + z) * VH + sy + y) * VW + sx + x;
+    const long long oc = (long long)c * VD * VH * VW + o;
+    vol[oc] = __fadd_rn(vol[oc], __fmul_rn(w[v], patch[i]));
+    if (c == 0) cnt[o] = __fadd_rn(cnt[o], w[v]);
+  }
+}
+
+// out /= count_map (fp32 volume), then the same binarisation / argmax as finalize_kernel
+__global__ void finalize_weighted_kernel(float* __restrict__ vol, const float* __restrict__ cnt, uint8_t* __restrict__ binary,
+                                         uint8_t* __restrict__ argmax, int C, long long vv) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < vv; v += (long long)gridDim.x * blockDim.x) {
+    const float cn = cnt[v];
+    float best = -INFINITY;
+    int bi = 0;
+    for (int c = 0; c < C; ++c) {
+      const float o = vol[c * vv + v] / cn;
+      vol[c * vv + v] = o;
+      if (binary) binary[c * vv + v] = (1.f / (1.f + expf(-o)) > 0.5f) ? 1 : 0;
+      if (o > best) {
+        best = o;
+        bi = c;
+      }
+    }
+    if (argmax) argmax[v] = (uint8_t)bi;
+  }
+}
+
+// MONAI ScaleIntensityRange (reference val/test transform, utils.py:167-170: a_min=-175, a_max=250, b_min=0, b_max=1, clip):
+//   y = (x - a_min) / (a_max - a_min) ; y = y * (b_max - b_min) + b_min ; clip to [b_min, b_max]
+// same op order in fp32, no FMA contraction -> bit-exact with the torch/numpy evaluation.
+__global__ void scale_intensity_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float a_min,
+                                       float a_max, float b_min, float b_max, int clip) {
+  const float den = __fsub_rn(a_max, a_min), span = __fsub_rn(b_max, b_min);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float y = __fdiv_rn(__fsub_rn(in[i], a_min), den);
+    y = __fadd_rn(__fmul_rn(y, span), b_min);
+    if (clip) y = fminf(fmaxf(y, b_min), b_max);
+    out[i] = y;
+  }
+}
+
 // crop a window out of the (padded) input volume: [1][VD][VH][VW] -> [PD][PH][PW]
 __global__ void crop_window_kernel(const float* __restrict__ vol, float* __restrict__ patch, int VD, int VH, int VW,
                                    int PD, int PH, int PW, int sz, int sy, int sx) {

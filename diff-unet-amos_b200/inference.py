@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .windows import axis_counts, window_starts
+from .windows import axis_counts, gaussian_importance_map, window_starts
 
 
 def _ptr(t):
@@ -27,25 +27,58 @@ def _stream():
 
 
 class StitchBuffers:
-    """Output accumulator of one volume: fp32 [C, D, H, W] sums + per-axis integer coverage counts."""
+    """Output accumulator of one volume: fp32 [C, D, H, W] sums + coverage: per-axis integer counts (constant blend, the
+    count map is their outer product) or an accumulated fp32 weight volume (gaussian blend)."""
 
-    def __init__(self, channels: int, vol: Sequence[int], roi: Sequence[int], overlap: float, device):
+    def __init__(self, channels: int, vol: Sequence[int], roi: Sequence[int], overlap: float, device, mode: str = "constant",
+                 sigma_scale: float = 0.125):
         self.vol = tuple(int(v) for v in vol)
         self.roi = tuple(int(r) for r in roi)
         self.channels = channels
+        self.mode = mode
         self.out = torch.zeros((channels,) + self.vol, dtype=torch.float32, device=device)
-        self.counts = [torch.from_numpy(c).to(device) for c in axis_counts(self.vol, self.roi, overlap)]
+        if mode == "constant":
+            self.counts = [torch.from_numpy(c).to(device) for c in axis_counts(self.vol, self.roi, overlap)]
+        elif mode == "gaussian":
+            self.weights = gaussian_importance_map(self.roi, sigma_scale).to(device).contiguous()
+            self.count_vol = torch.zeros(self.vol, dtype=torch.float32, device=device)
+        else:
+            raise NotImplementedError(f"blend mode {mode!r}: only 'constant' (the reference's) and 'gaussian' exist")
 
     def add(self, patch: torch.Tensor, start) -> None:
-        _lib.check(_lib.load().dunet_stitch_add(_ptr(self.out), _lib.i32x3(self.vol), self.channels, _ptr(patch),
-                                               _lib.i32x3(self.roi), _lib.i32x3(start), _stream()))
+        lib = _lib.load()
+        if self.mode == "constant":
+            _lib.check(lib.dunet_stitch_add(_ptr(self.out), _lib.i32x3(self.vol), self.channels, _ptr(patch),
+                                            _lib.i32x3(self.roi), _lib.i32x3(start), _stream()))
+        else:
+            _lib.check(lib.dunet_stitch_add_weighted(_ptr(self.out), _ptr(self.count_vol), _lib.i32x3(self.vol), self.channels,
+                                                     _ptr(patch), _ptr(self.weights), _lib.i32x3(self.roi), _lib.i32x3(start),
+                                                     _stream()))
 
     def finalize(self, binary: bool = False, argmax: bool = False):
         b = torch.empty((self.channels,) + self.vol, dtype=torch.uint8, device=self.out.device) if binary else None
         a = torch.empty(self.vol, dtype=torch.uint8, device=self.out.device) if argmax else None
-        _lib.check(_lib.load().dunet_finalize(_ptr(self.out), _lib.i32x3(self.vol), self.channels, _ptr(self.counts[0]),
-                                             _ptr(self.counts[1]), _ptr(self.counts[2]), _ptr(b), _ptr(a), _stream()))
+        lib = _lib.load()
+        if self.mode == "constant":
+            _lib.check(lib.dunet_finalize(_ptr(self.out), _lib.i32x3(self.vol), self.channels, _ptr(self.counts[0]),
+                                          _ptr(self.counts[1]), _ptr(self.counts[2]), _ptr(b), _ptr(a), _stream()))
+        else:
+            _lib.check(lib.dunet_finalize_weighted(_ptr(self.out), _ptr(self.count_vol), _lib.i32x3(self.vol), self.channels,
+                                                   _ptr(b), _ptr(a), _stream()))
         return self.out, b, a
+
+
+def scale_intensity_range(image: torch.Tensor, a_min: float = -175.0, a_max: float = 250.0, b_min: float = 0.0,
+                          b_max: float = 1.0, clip: bool = True) -> torch.Tensor:
+    """``ScaleIntensityRanged`` of the reference's val/test transforms (utils.py:167-170) as a GPU pre-pass."""
+    if not image.is_cuda:
+        raise RuntimeError("scale_intensity_range runs on the GPU only (no CPU fallback)")
+    x = image.float().contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().dunet_scale_intensity(_ptr(x), _ptr(out), x.numel(), a_min, a_max, b_min, b_max, 1 if clip else 0,
+                                                     _stream()))
+    return out
 
 
 def _pad_to_roi(inputs: torch.Tensor, roi) -> Tuple[torch.Tensor, list]:
@@ -70,15 +103,17 @@ def crop_windows(volume: torch.Tensor, starts, roi) -> torch.Tensor:
 
 
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable[..., torch.Tensor],
-                             overlap: float = 0.25, mode: str = "constant", window_range: Optional[Tuple[int, int]] = None,
-                             finalize: bool = True, out_channels: Optional[int] = None, **kwargs):
-    """Constant-blend sliding window on the GPU.  ``predictor(window_batch, **kwargs)`` -> [b, C, *roi].
+                             overlap: float = 0.25, mode: str = "constant", sigma_scale: float = 0.125,
+                             window_range: Optional[Tuple[int, int]] = None, finalize: bool = True,
+                             out_channels: Optional[int] = None, **kwargs):
+    """Sliding window on the GPU, ``mode`` "constant" (what the reference uses) or "gaussian" (MONAI's other blend).
+    ``predictor(window_batch, **kwargs)`` -> [b, C, *roi].
 
     ``window_range=(lo, hi)`` restricts the run to a contiguous shard of the window list (multi-GPU); with
     ``finalize=False`` the un-normalised StitchBuffers is returned instead of the blended volume.
     """
-    if mode != "constant":
-        raise NotImplementedError("only the blend mode the reference uses (constant) is implemented")
+    if mode not in ("constant", "gaussian"):
+        raise NotImplementedError(f"blend mode {mode!r}: only 'constant' (the reference's) and 'gaussian' exist")
     if not inputs.is_cuda:
         raise RuntimeError("sliding_window_inference runs on the GPU only (no CPU fallback)")
     if inputs.shape[1] != 1:
@@ -103,13 +138,13 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
                 if pred.dtype != torch.float32 or not pred.is_contiguous():
                     pred = pred.float().contiguous()
                 if buf is None:
-                    buf = StitchBuffers(pred.shape[1], vol, roi, overlap, inputs.device)
+                    buf = StitchBuffers(pred.shape[1], vol, roi, overlap, inputs.device, mode, sigma_scale)
                 for j, s in enumerate(grp):
                     buf.add(pred[j], s)
             if buf is None:  # empty shard (more ranks than windows): contribute zeros to the reduction
                 if out_channels is None:
                     raise ValueError("empty window range: pass out_channels")
-                buf = StitchBuffers(out_channels, vol, roi, overlap, inputs.device)
+                buf = StitchBuffers(out_channels, vol, roi, overlap, inputs.device, mode, sigma_scale)
             outs.append(buf)
     if not finalize:
         return outs

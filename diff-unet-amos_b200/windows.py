@@ -55,6 +55,22 @@ def axis_counts(image_size: Sequence[int], roi: Sequence[int], overlap: float) -
     return out
 
 
+def gaussian_importance_map(roi: Sequence[int], sigma_scale: float = 0.125, floor: float = 1e-3):
+    """MONAI ``compute_importance_map(roi, mode="gaussian", sigma_scale)`` followed by the clamp sliding_window_inference
+    applies (``min_non_zero = max(map.min(), 1e-3)``): a separable product of 1-D gaussians centred on the window,
+    sigma_d = sigma_scale * roi_d, built in fp32 in the same op order (monai/data/utils.py, monai/inferers/utils.py >= 1.2).
+    Host logic (a [roi] tensor built once per volume); fp32 torch CPU ops."""
+    import torch
+
+    imp = None
+    for i, n in enumerate(roi):
+        x = torch.arange(start=-(n - 1) / 2.0, end=(n - 1) / 2.0 + 1, dtype=torch.float32)
+        x = torch.exp(x ** 2 / (-2 * (n * sigma_scale) ** 2))
+        imp = x if imp is None else imp.unsqueeze(-1) * x[(None,) * i]
+    lo = max(float(imp.min()), floor)
+    return torch.clamp(imp, min=lo)
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [lo, hi) share of ``n_items`` for ``rank``; the first ``n_items % world`` ranks get one extra."""
     base, extra = divmod(n_items, world)

@@ -141,6 +141,21 @@ int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channel
                    const int32_t* counts_h, const int32_t* counts_w, uint8_t* binary, uint8_t* argmax_labels,
                    void* stream);
 
+/* MONAI blend mode "gaussian" (the reference's own call uses the default constant blend): out[slices] += w * pred
+ * and count[slices] += w with `weights` the [pd0, pd1, pd2] fp32 importance map of a window; dunet_finalize_weighted divides
+ * by the accumulated fp32 count volume [D, H, W] and binarises like dunet_finalize. */
+int dunet_stitch_add_weighted(float* out_volume, float* count_volume, const int32_t vol_dims[3], int32_t channels,
+                              const float* patch, const float* weights, const int32_t patch_dims[3], const int32_t start[3],
+                              void* stream);
+int dunet_finalize_weighted(float* out_volume, const float* count_volume, const int32_t vol_dims[3], int32_t channels,
+                            uint8_t* binary, uint8_t* argmax_labels, void* stream);
+
+/* replaces: monai.transforms.ScaleIntensityRanged(a_min=-175, a_max=250, b_min=0, b_max=1, clip=True), the intensity step
+ * of the reference's val/test transforms (utils.py:167-170, 185-187), as a GPU pre-pass feeding the window driver
+ * (SURVEY 8f-3).  y = (x - a_min) / (a_max - a_min) * (b_max - b_min) + b_min, optionally clipped; in == out allowed. */
+int dunet_scale_intensity(const float* in, float* out, int64_t n, float a_min, float a_max, float b_min, float b_max,
+                          int32_t clip, void* stream);
+
 /* replaces: the per-class reductions of dice_coeff (metric.py:3-49) as Tester.validation_step calls it on the binarised
  * volume (test.py:143-151).  pred: uint8 {0,1} [channels][voxels] (dunet_finalize's `binary`); label: one-hot
  * [channels][voxels], uint8 or fp32 (label_is_float), non-zero = foreground.  counts (device, [channels][3] uint64):

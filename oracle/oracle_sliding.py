@@ -67,9 +67,32 @@ def count_map(image_size: Sequence[int], roi: Sequence[int], grid: np.ndarray) -
     return cnt
 
 
+def importance_map(roi: Sequence[int], mode: str = "constant", sigma_scale: float = 0.125) -> torch.Tensor:
+    """monai/data/utils.py ``compute_importance_map`` (constant: ones; gaussian: separable product of 1-D gaussians,
+    sigma_d = sigma_scale * roi_d) followed by the clamp of monai/inferers/utils.py (>= 1.2):
+    ``min_non_zero = max(map.min(), 1e-3); map = clamp(map, min=min_non_zero)``.  Not exercised by the reference
+    (engine.py:173-177 uses the default mode); restated for the gaussian-blend extension, parity unpinned."""
+    if mode == "constant":
+        return torch.ones(tuple(roi), dtype=torch.float32)
+    imp = None
+    for i, n in enumerate(roi):
+        x = torch.arange(start=-(n - 1) / 2.0, end=(n - 1) / 2.0 + 1, dtype=torch.float32)
+        x = torch.exp(x ** 2 / (-2 * (n * sigma_scale) ** 2))
+        imp = x if imp is None else imp.unsqueeze(-1) * x[(None,) * i]
+    return torch.clamp(imp, min=max(float(imp.min()), 1e-3))
+
+
+def scale_intensity_range(x: torch.Tensor, a_min=-175.0, a_max=250.0, b_min=0.0, b_max=1.0, clip=True) -> torch.Tensor:
+    """monai.transforms.ScaleIntensityRange as the reference configures it (utils.py:167-170)."""
+    y = (x - a_min) / (a_max - a_min)
+    y = y * (b_max - b_min) + b_min
+    return torch.clamp(y, b_min, b_max) if clip else y
+
+
 def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_batch_size: int,
-                             predictor: Callable[..., torch.Tensor], overlap: float = 0.25, **kwargs) -> torch.Tensor:
-    """Constant-blend sliding window.  ``predictor(window_batch, window_indices=..., **kwargs)`` -> [b, C, *roi].
+                             predictor: Callable[..., torch.Tensor], overlap: float = 0.25, mode: str = "constant",
+                             sigma_scale: float = 0.125, **kwargs) -> torch.Tensor:
+    """Sliding window, constant blend (the reference's) or gaussian blend.  ``predictor(window_batch, window_indices=..., **kwargs)`` -> [b, C, *roi].
 
     ``window_indices`` (flat indices n*num_win + w of the windows in the batch) is an oracle-side addition so the
     predictor can pick the explicit per-window noise; MONAI itself forwards only ``**kwargs``.
@@ -89,6 +112,7 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
     total = num_win * batch
     out = None
     cnt = torch.zeros((1, 1) + size, dtype=torch.float32)
+    imp = importance_map(roi, mode, sigma_scale)
     for g in range(0, total, sw_batch_size):
         idxs = list(range(g, min(g + sw_batch_size, total)))
         crops = []
@@ -100,9 +124,12 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
             out = torch.zeros((batch, pred.shape[1]) + size, dtype=torch.float32)
         for j, idx in enumerate(idxs):
             n, s = idx // num_win, grid[idx % num_win]
-            out[n, :, s[0]:s[0] + roi[0], s[1]:s[1] + roi[1], s[2]:s[2] + roi[2]] += pred[j]
+            if mode == "constant":
+                out[n, :, s[0]:s[0] + roi[0], s[1]:s[1] + roi[1], s[2]:s[2] + roi[2]] += pred[j]
+            else:
+                out[n, :, s[0]:s[0] + roi[0], s[1]:s[1] + roi[1], s[2]:s[2] + roi[2]] += imp * pred[j]
             if n == 0:
-                cnt[0, 0, s[0]:s[0] + roi[0], s[1]:s[1] + roi[1], s[2]:s[2] + roi[2]] += 1.0
+                cnt[0, 0, s[0]:s[0] + roi[0], s[1]:s[1] + roi[1], s[2]:s[2] + roi[2]] += imp
     out = out / cnt
     if any(pad):  # crop the padding back off (pad list is ordered last dim first)
         sl = [slice(None), slice(None)]

@@ -464,3 +464,17 @@ def test_error_behaviour_matches_the_reference_seams():
     plan = ctypes.c_void_p()
     assert lib.dunet_plan_create(ctypes.byref(plan), ctypes.byref(cfg)) == -1
     assert b">= 32" in lib.dunet_last_error()
+
+
+def test_gaussian_blend_and_intensity_prepass_bit_exact():
+    """Extensions next to the path: ScaleIntensityRanged as a GPU pre-pass and MONAI's gaussian blend,
+    both bit-exact against the oracle restatement (same fp32 op order, no FMA contraction)."""
+    torch.manual_seed(11)
+    hu = torch.randn(1, 1, 40, 48, 36) * 400.0
+    got = pkg.scale_intensity_range(hu.cuda())
+    assert torch.equal(got.cpu(), oracle_sliding.scale_intensity_range(hu))
+    image = got.cpu()
+    pred = lambda b, **kw: torch.cat([b * 2.0 + 1.0, b - 0.5, b * b], 1)
+    ref = oracle_sliding.sliding_window_inference(image, (32, 32, 32), 4, lambda b, window_indices=None: pred(b), 0.25, mode="gaussian")
+    out = pkg.sliding_window_inference(image.cuda(), (32, 32, 32), 4, pred, 0.25, mode="gaussian")
+    assert torch.equal(out.cpu(), ref)

@@ -57,3 +57,27 @@ def test_volume_matches_reference_driven_golden():
     assert rel_l2(out, g["stitched"]) < 1e-4
     lab = oracle_sliding.engine_infer_labels(out).numpy().astype(np.uint8)
     assert (lab == g["labels"]).mean() > 0.9999
+
+
+def test_gaussian_importance_map_known_answers():
+    """MONAI gaussian blend (extension): centre weight exp(-0.5 (0.5/sigma)^2)^3, corner clamped to 1e-3,
+    symmetric; a constant predictor is reproduced exactly up to rounding; product host logic == oracle."""
+    import diff_unet_amos_b200 as pkg
+
+    imp = oracle_sliding.importance_map((96, 96, 96), "gaussian", 0.125)
+    c = float(np.exp(np.float32(0.5) ** 2 / np.float32(-2 * 12.0 ** 2)))
+    assert abs(float(imp[47, 47, 47]) - c ** 3) < 1e-6
+    assert float(imp.min()) == np.float32(1e-3) and float(imp[0, 0, 0]) == np.float32(1e-3)
+    assert torch.equal(imp, imp.flip(0)) and torch.allclose(imp, imp.permute(1, 2, 0), rtol=1e-6)  # (gz*gy)*gx: order matters bitwise
+    assert torch.equal(pkg.gaussian_importance_map((96, 96, 96), 0.125), imp)
+    assert torch.equal(pkg.gaussian_importance_map((32, 48, 64), 0.125), oracle_sliding.importance_map((32, 48, 64), "gaussian"))
+    img = torch.rand(1, 1, 40, 48, 36)
+    out = oracle_sliding.sliding_window_inference(img, (32, 32, 32), 2, lambda b, window_indices=None: torch.full_like(b, 3.0),
+                                                  0.25, mode="gaussian")
+    assert torch.allclose(out, torch.full_like(out, 3.0), rtol=1e-6)
+
+
+def test_scale_intensity_range_known_answers():
+    x = torch.tensor([-1000.0, -175.0, 37.5, 250.0, 3000.0])
+    y = oracle_sliding.scale_intensity_range(x)
+    assert y.tolist() == [0.0, 0.0, 0.5, 1.0, 1.0]
