@@ -154,7 +154,7 @@ def run_b200(args):
 
     torch.manual_seed(0)
     model = pkg.DiffUNetB200(in_channels=1, out_channels=CLASSES, image_size=ROI[1], spatial_size=ROI[0], features=FEATURES,
-                             batch_max=args.sw_batch, precision=args.precision,
+                             batch_max=args.sw_batch + 1, precision=args.precision,
                              dual_stream=bool(args.dual_stream)).to(dev).eval()
     torch.manual_seed(1)
     host_vol = torch.rand(1, 1, *VOLUME).pin_memory()
@@ -165,19 +165,35 @@ def run_b200(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(2 + rank)
     host_labels = torch.empty((CLASSES,) + VOLUME, dtype=torch.uint8).pin_memory() if rank == 0 else None
+    # second pinned result buffer for the overlapped D2H of the e2e leg -- allocated here: cudaHostAlloc of 671 MB takes
+    # ~0.5 s and must not sit between the barrier and the timed region of rank 0 (the other ranks would wait for it)
+    host_labels2 = [host_labels, torch.empty((CLASSES,) + VOLUME, dtype=torch.uint8).pin_memory()] if rank == 0 else None
+
+    # window batches of this rank: sw_batch windows each; a single left-over window joins the last batch (13 = 4 + 4 + 5)
+    # instead of running alone at batch-1 efficiency
+    bounds = list(range(lo, hi, args.sw_batch)) + [hi]
+    if len(bounds) > 2 and bounds[-1] - bounds[-2] == 1:
+        del bounds[-2]
+    scatter = world > 1 and CLASSES % world == 0
 
     def one_volume(volume_dev):
-        """the hot path for this rank's shard of windows, then the single NCCL exchange + finalize on rank 0"""
+        """the hot path for this rank's shard of windows, then the NCCL exchange (reduce-scatter of the stitched logits by
+        channel, local divide + binarise, gather of the uint8 labels on rank 0)"""
         buf = StitchBuffers(CLASSES, VOLUME, ROI, args.overlap, dev)
-        for g in range(lo, hi, args.sw_batch):
-            grp = starts[g:min(g + args.sw_batch, hi)]
+        for g0, g1 in zip(bounds[:-1], bounds[1:]):
+            grp = starts[g0:g1]
             batch = crop_windows(volume_dev[0], grp, ROI)
             noise = torch.randn((len(grp), CLASSES) + ROI, device=dev, generator=gen)  # gaussian_diffusion.py:693
             pred = model(image=batch, pred_type="ddim_sample", noise=noise)
             for j, s in enumerate(grp):
                 buf.add(pred[j], s)
+        if scatter:
+            mine = StitchBuffers.__new__(StitchBuffers)
+            mine.vol, mine.roi, mine.mode, mine.counts, mine.channels = buf.vol, buf.roi, buf.mode, buf.counts, CLASSES // world
+            mine.out = pkg.reduce_scatter_channels(buf.out)      # sum of the partial volumes, my channels only
+            return pkg.gather_channel_chunks(mine.finalize(binary=True)[1], dst=0)
         if world > 1:
-            dist.reduce(buf.out, dst=0)  # stitched-logits gather: sum of disjoint-or-overlapping partial volumes
+            dist.reduce(buf.out, dst=0)
         if rank == 0:
             return buf.finalize(binary=True)[1]
         return None
@@ -215,7 +231,6 @@ def run_b200(args):
         # closing event.
         barrier()
         copy_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        host_labels2 = [host_labels, torch.empty_like(host_labels).pin_memory()] if rank == 0 else None
         main = torch.cuda.current_stream()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()

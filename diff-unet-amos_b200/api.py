@@ -1,6 +1,6 @@
 """Public surface of the B200 Diff-UNet inference package."""
 from ._lib import DunetError, load as load_library
-from .dist import infer_volume_distributed, my_window_range, reduce_partial_volume
+from .dist import gather_channel_chunks, infer_volume_distributed, my_window_range, reduce_partial_volume, reduce_scatter_channels
 from .engine import EngineB200, dice_counts, dice_from_counts
 from .inference import StitchBuffers, infer_volume, scale_intensity_range, sliding_window_inference
 from .model import DEFAULT_FEATURES, DiffUNetB200
@@ -16,6 +16,6 @@ def model_hub(model_name: str, **kwargs):
     raise NotImplementedError(f"No such model : {model_name}")
 
 
-__all__ = ["DiffUNetB200", "EngineB200", "gaussian_importance_map", "scale_intensity_range", "dice_counts", "dice_from_counts", "DEFAULT_FEATURES", "DdimSchedule", "DunetError", "StitchBuffers", "axis_counts",
+__all__ = ["DiffUNetB200", "EngineB200", "gather_channel_chunks", "reduce_scatter_channels", "gaussian_importance_map", "scale_intensity_range", "dice_counts", "dice_from_counts", "DEFAULT_FEATURES", "DdimSchedule", "DunetError", "StitchBuffers", "axis_counts",
            "infer_volume", "infer_volume_distributed", "load_library", "my_window_range", "reduce_partial_volume", "model_hub", "scan_intervals", "shard_range", "sliding_window_inference",
            "window_starts"]
