@@ -382,7 +382,6 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
     const int tz4 = (p->D[lvl] + CONV_ZT - 1) / CONV_ZT;
     const int items4 = g.tiles_x * g.tiles_y * tz4 * c.n_tiles * std::max(1, std::min(c.ncb(), 4));
     g.zt = (items4 < 64 && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
-    if (getenv("DUNET_EXP_ZT2") && c.n_tile == 128) g.zt = 2;
   }
   g.tiles_z = (p->D[lvl] + g.zt - 1) / g.zt;
   g.tiles = g.tiles_x * g.tiles_y * g.tiles_z;
