@@ -336,8 +336,8 @@ struct dunet_plan {
   std::vector<void*> owned;
   // two internal streams: the two halves of a window batch run out of phase so that the HBM-bound kernels of one half
   // (normalise, final/DDIM, transposed conv) overlap the tensor-core-bound convolutions of the other
-  cudaStream_t half_stream[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaStream_t half_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 static int dev_alloc(dunet_plan* p, void** out, size_t bytes) {
@@ -763,6 +763,12 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
   return launch_conv_tc<64, 128, 2, MODE_DECONV2>(t, a, st);
 }
 
+// number of sub-batches a batch of B windows is split into in dual-stream mode (experiments: DUNET_NSTREAMS = 2..4)
+static int n_substreams(int B) {
+  static const int ns = [] { const char* e = getenv("DUNET_NSTREAMS"); const int v = e ? atoi(e) : 2; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
+  return std::min(ns, B);
+}
+
 static int check_call(const dunet_plan* p, int B, const void* ws) {
   if (!p) return fail(DUNET_E_INVALID, "plan is NULL");
   if (!p->committed) return fail(DUNET_E_STATE, "plan not committed (dunet_plan_commit)");
@@ -1017,7 +1023,7 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
 void dunet_plan_destroy(dunet_plan* p) {
   if (!p) return;
   for (void* q : p->owned) cudaFree(q);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 4; ++i) {
     if (p->half_stream[i]) cudaStreamDestroy(p->half_stream[i]);
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
   }
@@ -1158,7 +1164,8 @@ int dunet_workspace_bytes(const dunet_plan* p, int32_t batch, size_t* out) {
   if (!p || !out) return fail(DUNET_E_INVALID, "NULL argument");
   if (batch < 1 || batch > p->cfg.batch_max) return fail(DUNET_E_INVALID, "batch %d outside [1, %d]", batch, p->cfg.batch_max);
   const size_t single = ws_layout(p, batch).total;
-  const size_t halves = batch >= 2 ? 2 * ws_layout(p, (batch + 1) / 2).total : 0;
+  const int ns = n_substreams(batch);
+  const size_t halves = batch >= 2 ? ns * ws_layout(p, (batch + ns - 1) / ns).total : 0;
   *out = std::max(single, halves);
   return 0;
 }
@@ -1273,25 +1280,29 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
                             out_accumulate, ws, st);
   // ---- two half batches on two internal streams (fork from / join into the caller's stream; no host synchronisation)
   if (!p->half_stream[0]) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       CUDA_TRY(cudaStreamCreateWithFlags(&p->half_stream[i], cudaStreamNonBlocking));
       CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   }
-  const int B0 = (B + 1) / 2;
+  const int ns = n_substreams(B);
+  const int B0 = (B + ns - 1) / ns;
   const size_t half_ws = ws_layout(p, B0).total;
   CUDA_TRY(cudaEventRecord(p->ev_fork, st));
-  for (int h = 0; h < 2; ++h) {
-    const int b0 = h * B0, nb = h ? B - B0 : B0;
+  int used = 0;
+  for (int h = 0; h < ns; ++h) {
+    const int b0 = h * B0, nb = std::min(B0, B - b0);
+    if (nb <= 0) break;
     const size_t img_off = (size_t)b0 * p->cfg.in_channels * p->V[0], st_off = (size_t)b0 * p->C * p->V[0];
     CUDA_TRY(cudaStreamWaitEvent(p->half_stream[h], p->ev_fork, 0));
     TRY(ddim_sample_impl(p, image + img_off, noise + st_off, acc_out + st_off, per_step_logits ? per_step_logits + st_off : nullptr,
                          per_step_stride, final_x ? final_x + st_off : nullptr, nb, run_encoder, out_scale, out_accumulate,
                          ws + h * half_ws, p->half_stream[h]));
     CUDA_TRY(cudaEventRecord(p->ev_join[h], p->half_stream[h]));
+    ++used;
   }
-  for (int h = 0; h < 2; ++h) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[h], 0));
+  for (int h = 0; h < used; ++h) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[h], 0));
   return 0;
 }
 

@@ -141,7 +141,8 @@ class _Runtime:
         self.plan = None
         self.device = None
         self.weights_sig = None
-        self.workspaces: Dict[int, torch.Tensor] = {}
+        self.workspaces: Dict[str, torch.Tensor] = {}
+        self.ws_batch = None   # batch size of the last call that used the workspace
         self.emb_token = None  # identity of the embeddings currently held in the workspace
 
     def close(self):
@@ -189,16 +190,25 @@ class _Runtime:
         return self.plan
 
     def workspace(self, batch: int) -> torch.Tensor:
-        ws = self.workspaces.get(batch)
+        """ONE workspace, sized for the largest batch (any smaller batch lays itself out inside it), so alternating batch
+        sizes (the last, shorter window group of every volume) never re-allocate.  The embeddings it holds are tied to
+        the batch size they were written with: a change of batch size invalidates them."""
+        ws = self.workspaces.get("max")
         if ws is None:
-            nbytes = ctypes.c_size_t()
-            _lib.check(_lib.load().dunet_workspace_bytes(self.plan, batch, ctypes.byref(nbytes)))
-            self.workspaces.clear()  # one live workspace: embeddings are tied to it
+            lib = _lib.load()
+            need = 0
+            for b in range(1, self.owner.batch_max + 1):
+                nbytes = ctypes.c_size_t()
+                _lib.check(lib.dunet_workspace_bytes(self.plan, b, ctypes.byref(nbytes)))
+                need = max(need, nbytes.value)
+            buf = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            off = (-buf.data_ptr()) % 256
+            ws = buf[off:off + need]
+            self.workspaces["max"] = ws
+            self.ws_batch = None
+        if self.ws_batch != batch:
+            self.ws_batch = batch
             self.emb_token = None
-            ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
-            off = (-ws.data_ptr()) % 256
-            ws = ws[off:off + nbytes.value]
-            self.workspaces[batch] = ws
         return ws
 
 
