@@ -281,7 +281,8 @@ def run_b200(args):
                          "peak_source": peaks["source"] + ", sustained cuBLAS bf16",
                          "launches": int(conv_n.value), "avg_launch_ms": conv_ms.value / max(conv_n.value, 1),
                          "conv_share_of_step": conv_ms.value / ms,
-                         "traffic": 227.1e6, "traffic_note": "ncu --set full, conv3d_tc64<64,4> 64->64 @96^3 batch 1: dram read 113.5 MB + write <= 113.6 MB per launch = the algorithmic bytes (profiles/r1_ncu_full_conv3d_tc64.txt)"},
+                         "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
+                         "traffic": 864.9e6, "traffic_note": "ncu --set full, conv3d_tc64_kernel<32,4,0> 64->64 @96^3, 4 windows per launch: dram read 453.4 MB + write 411.5 MB (algorithmic 4 x 113.2 MB each way; part of the output is still in L2 at kernel end), tensor pipe active 79 % of elapsed (profiles/r1_ncu_full_conv3d_tc64_batch4_v2.txt)"},
             "roofline_hbm": {name: {"bound": "hbm", "achieved": fam_b[i] / fam_ms[i] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": fam_b[i] / fam_ms[i] / 1e6 / peaks["hbm_gbs"], "launches": int(fam_n[i]),
                                     "share_of_step": fam_ms[i] / ms}
