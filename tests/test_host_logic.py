@@ -104,3 +104,29 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert lib.dunet_version() == 100
     assert ctypes.sizeof(_lib.DunetCfg) == 4 * 14
+
+
+def test_product_fails_loudly_without_a_gpu():
+    """No CPU fallback anywhere on the product path: without a CUDA device plan creation returns a negative code with a
+    message (nothing throws across the ABI), compute calls on CPU tensors raise, and nothing under the package imports
+    oracle/."""
+    if torch.cuda.is_available():
+        pytest.skip("this is the no-GPU behaviour test")
+    lib = _lib.load()
+    cfg = _lib.DunetCfg()
+    cfg.num_classes, cfg.in_channels, cfg.batch_max, cfg.num_steps, cfg.flags = 2, 1, 1, 10, 0
+    cfg.patch = (ctypes.c_int32 * 3)(32, 32, 32)
+    cfg.features = (ctypes.c_int32 * 6)(*SMALL)
+    plan = ctypes.c_void_p()
+    assert lib.dunet_plan_create(ctypes.byref(plan), ctypes.byref(cfg)) < 0
+    assert len(lib.dunet_last_error()) > 0
+    m = pkg.DiffUNetB200(in_channels=1, out_channels=2, image_size=32, spatial_size=32, features=SMALL)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(image=torch.rand(1, 1, 32, 32, 32), pred_type="ddim_sample")
+    with pytest.raises(RuntimeError, match="GPU only"):
+        pkg.sliding_window_inference(torch.rand(1, 1, 40, 40, 40), (32, 32, 32), 1, lambda b: b)
+    pkg_dir = os.path.join(ROOT, "diff-unet-amos_b200")
+    for fn in os.listdir(pkg_dir):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg_dir, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
