@@ -954,9 +954,4 @@ __global__ void __launch_bounds__(256) dice_counts_kernel(const uint8_t* __restr
   }
 }
 
-__global__ void fill_zero_kernel(float4* p, long long n4) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
-    p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
 }  // namespace dunet

@@ -61,6 +61,11 @@ enum {
 #define DUNET_FLAG_TC64_CB64 64u /* debug / A-B timing: the Cout = 64 kernel walks 64-channel blocks with a 7-slot plane ring
                                    instead of 32-channel blocks with a 13-slot ring */
 
+/* Environment switches read once by the library (debugging / A-B timing only; none changes results):
+ *   DUNET_NO_PDL=1      launch without programmatic stream serialization
+ *   DUNET_NSTREAMS=2..4 number of sub-batches / internal streams used by DUNET_FLAG_DUAL_STREAM (default 2; 3 and 4 measured slower)
+ *   DUNET_DBG_LAUNCH=k, DUNET_DBG_DECONV=1   which launch writes the per-CTA timeline (dunet_debug_set_conv_timeline) */
+
 typedef struct dunet_plan dunet_plan;
 
 /* Mirrors DiffUNet.__init__(spatial_dims=3, in_channels, out_channels, image_size, spatial_size, features, ...)
