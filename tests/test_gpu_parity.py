@@ -478,3 +478,18 @@ def test_gaussian_blend_and_intensity_prepass_bit_exact():
     ref = oracle_sliding.sliding_window_inference(image, (32, 32, 32), 4, lambda b, window_indices=None: pred(b), 0.25, mode="gaussian")
     out = pkg.sliding_window_inference(image.cuda(), (32, 32, 32), 4, pred, 0.25, mode="gaussian")
     assert torch.equal(out.cpu(), ref)
+
+
+def test_wide_feature_variant_64_128_256_512_1024():
+    """BASELINE config 1 names the 64-128-256-512-1024(+64) width (19.1 TFLOP / patch): every level except the
+    first then runs on the generic N = 128 kernel, with up to 1024 + 512 concatenated input channels."""
+    cout, S, feats = 3, 32, (64, 128, 256, 512, 1024, 64)
+    m = _build(cout, S, feats, batch_max=2)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    image, noise = seeded_image((2, 1, S, S, S)).cuda(), seeded_noise((2, cout, S, S, S)).cuda()
+    with torch.no_grad():
+        out = m(image=image, pred_type="ddim_sample", noise=noise)
+        ref = _oracle_window_gpu(sd, image[1:2], noise[1:2], 10)
+    err = rel_l2(out[1:2].cpu(), ref.cpu())
+    print(f"wide features: rel-l2 {err:.4f}")
+    assert err < BF16_TOL

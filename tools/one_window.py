@@ -20,9 +20,10 @@ ap.add_argument("--prof", action="store_true")
 ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--dump", action="store_true")
 ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"])
+ap.add_argument("--features", default="64,64,128,256,512,64")
 a = ap.parse_args()
 torch.manual_seed(0)
-m = pkg.DiffUNetB200(in_channels=1, out_channels=a.C, image_size=a.S, spatial_size=a.S, batch_max=a.batch, num_steps=a.ddim, debug_flags=a.flags, precision=a.precision).cuda().eval()
+m = pkg.DiffUNetB200(in_channels=1, out_channels=a.C, image_size=a.S, spatial_size=a.S, batch_max=a.batch, num_steps=a.ddim, features=tuple(int(v) for v in a.features.split(",")), debug_flags=a.flags, precision=a.precision).cuda().eval()
 image = torch.rand(a.batch, 1, a.S, a.S, a.S, device="cuda")
 noise = torch.randn(a.batch, a.C, a.S, a.S, a.S, device="cuda")
 with torch.no_grad():
