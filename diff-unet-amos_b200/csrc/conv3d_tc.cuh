@@ -402,7 +402,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
             }
           } else {
             if (ok) {
-              const int tap = gcol / a.cout, co = gcol % a.cout;
+              // column order (dz, dy, 64-channel block, dx, co % 64), see deconv2_tc.cuh / pack_deconv_tc_w_kernel
+              const int nblk = a.cout / 64, nt128 = gcol >> 7, within = gcol & 127;
+              const int dzdy = nt128 / nblk, tap = dzdy * 2 + (within >> 6), co = (nt128 - dzdy * nblk) * 64 + (within & 63);
               const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
               const long long ovox = in_vox * 8;
               const long long o = ((long long)n * out_chunks + co / 8) * ovox + ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;

@@ -5,8 +5,8 @@
 // matters is that the epilogue (TMEM -> +bias -> bf16 -> 16-byte stores) never waits for loads or MMAs.  One CTA per SM
 // walks a static list of (8x16xZT input tile, 128-column block) units; the input planes of a tile are loaded once and
 // reused by all its column blocks, weights stream through a small ring, accumulators are double-buffered in TMEM.
-// Column order is (dz, dy, dx, co): with Cout = 64 one 128-column block holds the dx = 0 and dx = 1 taps, so a thread
-// writes 32 contiguous bytes per channel chunk and a warp writes whole 256-byte runs.
+// Column order is (dz, dy, 64-channel block, dx, co % 64): every 128-column block holds the dx = 0 and dx = 1 taps of the
+// same 64 output channels, so a thread writes 32 contiguous bytes per channel chunk and a warp writes whole 256-byte runs.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -34,7 +34,7 @@ struct DeconvTc {
 };
 
 struct DeconvTcArgs {
-  const __nv_bfloat16* w;  // packed [n_tile][cin block][8 k chunks][128][8], column = tap * cout + co
+  const __nv_bfloat16* w;  // packed [n_tile][cin block][8 k chunks][128][8], n_tile = (dz*2+dy) * (cout/64) + co/64, column = dx*64 + co%64
   __nv_bfloat16* out;      // C8-planar, cout channels, 2D x 2H x 2W
   const float* bias;       // [cout]
   int chunks_in;           // Cin / 8
@@ -173,18 +173,19 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
         mbar_wait(acc_full + 8 * buf, use & 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::ACC_COLS;
-        if (a.cout == 64) {
-          // One 128-column block = [dx = 0 | dx = 1] x 64 channels of the tap pair (dz, dy) = (nt >> 1, nt & 1).  The two
-          // x-taps of a voxel are adjacent 16-byte slots of the output row, so the values are exchanged between lanes
-          // (shuffles) until every store instruction writes whole contiguous 128-byte runs instead of half sectors.
-          const int dz = nt >> 1, dy = nt & 1;
+        {
+          // One 128-column block = [dx = 0 | dx = 1] x 64 channels (block cblk) of the tap pair (dz, dy).  The two x-taps
+          // of a voxel are adjacent 16-byte slots of the output row, so the values are exchanged between lanes (shuffles)
+          // until every store instruction writes whole contiguous 128-byte runs instead of half sectors.
+          const int nblk = a.cout / 64, dzdy = nt / nblk, cblk = nt - dzdy * nblk;
+          const int dz = dzdy >> 1, dy = dzdy & 1;
           const int yrow = tiy * CONV_TY + (r >> 3);
           const int oy = 2 * yrow + dy;
 #pragma unroll 1
           for (int jp = 0; jp < 4; ++jp) {
             float bl[8], bh[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { bl[i] = __ldg(a.bias + jp * 16 + i); bh[i] = __ldg(a.bias + jp * 16 + 8 + i); }
+            for (int i = 0; i < 8; ++i) { bl[i] = __ldg(a.bias + cblk * 64 + jp * 16 + i); bh[i] = __ldg(a.bias + cblk * 64 + jp * 16 + 8 + i); }
 #pragma unroll
             for (int s = 0; s < ZT; ++s) {
               const int z = z0 + s;
@@ -218,7 +219,7 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
                   e1.z = __shfl_sync(0xffffffffu, d1.z, src); e1.w = __shfl_sync(0xffffffffu, d1.w, src);
                   const uint4 val = (lane & 1) ? e1 : e0;
                   if (ok) {
-                    uint4* dst = reinterpret_cast<uint4*>(a.out) + ((long long)n * out_chunks + jp * 2 + c) * ovox +
+                    uint4* dst = reinterpret_cast<uint4*>(a.out) + ((long long)n * out_chunks + cblk * 8 + jp * 2 + c) * ovox +
                                  ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;
                     *dst = val;
                   }
@@ -226,31 +227,6 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
               }
             }
           }
-        } else {
-#pragma unroll 1
-        for (int j = 0; j < Cfg::N_TILE / 16; ++j) {
-          const int gcol = nt * Cfg::N_TILE + j * 16;
-          const int tap = gcol / a.cout, co = gcol % a.cout;
-          float bl[8], bh[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { bl[i] = __ldg(a.bias + co + i); bh[i] = __ldg(a.bias + co + 8 + i); }
-#pragma unroll
-          for (int s = 0; s < ZT; ++s) {
-            const int z = z0 + s;
-            float v[16];
-            tmem_ld16(acc + s * Cfg::N_TILE + j * 16, v);
-            if (xy_ok && z < a.D) {
-              const int oz = 2 * z + (tap >> 2), oy = 2 * y + ((tap >> 1) & 1), ox = 2 * x + (tap & 1);
-              BF8* dst = reinterpret_cast<BF8*>(a.out) + ((long long)n * out_chunks + co / 8) * ovox +
-                         ((long long)oz * (2 * a.H) + oy) * (2 * a.W) + ox;
-              float lo[8], hi[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { lo[i] = v[i] + bl[i]; hi[i] = v[8 + i] + bh[i]; }
-              dst[0] = float_to_bf8(lo);
-              dst[ovox] = float_to_bf8(hi);
-            }
-          }
-        }
         }
         tc_fence_before();
         __syncwarp();

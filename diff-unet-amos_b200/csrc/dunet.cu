@@ -217,7 +217,7 @@ __global__ void pack_deconv_w_kernel(const float* __restrict__ w, bf16* __restri
   }
 }
 // transposed-conv weights fp32 [cinr][coutr][8] -> tensor-core B operand bf16 [n_tile][cin block][k chunk][128][8] where
-// GEMM column = tap * coutp + cout  (tap = dz*4 + dy*2 + dx)
+// 128-column block nt = (dz*2 + dy) * (coutp/64) + cout/64, column inside it = dx * 64 + cout % 64  (tap = dz*4 + dy*2 + dx)
 __global__ void pack_deconv_tc_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cinr, int coutr, int cinp,
                                         int coutp, int parts) {
   const int n_tile = 128, kch = 8, ncb1 = cinp / 64, ncb = ncb1 * parts, n_tiles = 8 * coutp / n_tile;
@@ -231,7 +231,8 @@ __global__ void pack_deconv_tc_w_kernel(const float* __restrict__ w, bf16* __res
     const int cbg = (int)(t % ncb); t /= ncb;
     const int nt = (int)t;
     const int cb = cbg % ncb1, part = parts == 1 ? 0 : cbg / ncb1;
-    const int gcol = nt * n_tile + col, tap = gcol / coutp, co = gcol % coutp;
+    const int nblk = coutp / 64, dzdy = nt / nblk;
+    const int tap = dzdy * 2 + col / 64, co = (nt - dzdy * nblk) * 64 + col % 64;
     const int ci = cb * 64 + k * 8 + j;
     float v = 0.f;
     if (ci < cinr && co < coutr) v = w[((long long)ci * coutr + co) * 8 + tap];
