@@ -1273,7 +1273,8 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t per_step_stride = (size_t)B * p->C * p->V[0];
-  const bool dual = run_encoder ? (B >= 4 && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on)
+  static const int dual_min = [] { const char* e = getenv("DUNET_DUAL_MIN"); return e ? atoi(e) : 4; }();
+  const bool dual = run_encoder ? (B >= dual_min && B >= 2 && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on)
                                 : (p->emb_dual && p->emb_B == B);
   if (run_encoder) { p->emb_B = B; p->emb_dual = dual; }
   if (!dual)
