@@ -493,3 +493,32 @@ def test_wide_feature_variant_64_128_256_512_1024():
     err = rel_l2(out[1:2].cpu(), ref.cpu())
     print(f"wide features: rel-l2 {err:.4f}")
     assert err < BF16_TOL
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32x3"])
+def test_workspace_and_output_guards_stay_untouched(precision):
+    """No kernel writes outside the caller-owned buffers: the workspace and the output live inside larger allocations
+    whose guard regions (1 MiB each side, pattern 0xA5) must be intact after a whole DDIM call (default features at 32^3:
+    tc64, generic, split-K, transposed-conv and final kernels all run; batch 3 exercises ragged tile schedules)."""
+    cout, S, B, G = 3, 32, 3, 1 << 20
+    m = _build(cout, S, oracle_model.DEFAULT_FEATURES, batch_max=B, num_steps=2, precision=precision)
+    rt = m._rt
+    rt.ensure(torch.device("cuda", torch.cuda.current_device()))
+    need = 0
+    for b in range(1, B + 1):
+        n = ctypes.c_size_t()
+        _lib.check(_lib.load().dunet_workspace_bytes(rt.plan, b, ctypes.byref(n)))
+        need = max(need, n.value)
+    big = torch.full((need + 2 * G + 512,), 0xA5, dtype=torch.uint8, device="cuda")
+    off = G + (-(big.data_ptr() + G)) % 256
+    rt.workspaces["max"] = big[off:off + need]
+    rt.ws_batch = None
+    image, noise = seeded_image((B, 1, S, S, S)).cuda(), seeded_noise((B, cout, S, S, S)).cuda()
+    n_out = B * cout * S ** 3
+    obig = torch.full((n_out + 2 * G // 4,), float("nan"), device="cuda")
+    acc = obig[G // 4:G // 4 + n_out].view(B, cout, S, S, S)
+    res = m._run_ddim(image, noise, run_encoder=True, want_final=False, acc=acc)
+    torch.cuda.synchronize()
+    assert res["acc"].data_ptr() == acc.data_ptr() and torch.isfinite(acc).all()
+    assert bool((big[:off] == 0xA5).all()) and bool((big[off + need:] == 0xA5).all())
+    assert bool(torch.isnan(obig[:G // 4]).all()) and bool(torch.isnan(obig[G // 4 + n_out:]).all())
