@@ -17,7 +17,7 @@ DUNET_FLAG_KEEP_FP32_WEIGHTS = 2
 DUNET_FLAG_GENERIC_CONV = 4
 DUNET_FLAG_DUAL_STREAM = 8
 DUNET_FLAG_FP32X3 = 16
-DUNET_FLAG_FUSED_NORM = 32
+DUNET_FLAG_NO_FUSED_NORM = 32
 DUNET_FLAG_TC64_CB64 = 64
 
 

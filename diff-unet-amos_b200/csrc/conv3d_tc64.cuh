@@ -11,11 +11,13 @@
 //   * PERSISTENT CTAs (one per SM) walk a static list of 8x16xZT output tiles; the plane/weight rings run ahead across
 //     tile boundaries and the accumulators are double-buffered in TMEM (2 x ZT x 64 columns), so the epilogue of tile i
 //     (TMEM -> bf16 -> HBM, InstanceNorm statistics) overlaps the MMAs of tile i+1.
-//   * FUSE (second conv of a TwoConv, bf16 mode): the input is the RAW output of the previous conv; four extra warps
+//   * FUSE (second conv of a TwoConv, bf16 mode): the input is the RAW output of the previous conv; eight extra warps
 //     apply that conv's InstanceNorm + LeakyReLU (+ time-embedding bias) to every halo plane IN SHARED MEMORY between
 //     the TMA arrival and the MMAs (out-of-volume halo voxels stay the zeros TMA wrote: the padding of the normalised
 //     tensor).  The normalised intermediate never exists in HBM: one full read + write pass per TwoConv disappears.
-//     Same fp32 formulas as norm_act_kernel, so the result is bit-identical to the unfused path.
+//     Same fp32 formulas as norm_act_kernel, so the result is bit-identical to the unfused path.  The transform warps
+//     are instruction-latency bound (one dependent stream per scheduler): with four of them the conv lost what the
+//     saved pass gained (690 vs 532 + 157 us), with eight it takes 558 us.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -46,7 +48,9 @@ struct ConvTc64 {
   static constexpr int TMEM_COLS = 512;
   static constexpr int RED_BYTES = 4 * 128 * 4;
   static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + RED_BYTES + 1024 + 512;
-  static constexpr int THREADS_FUSED = CONV_THREADS + 4 * 32;  // + 4 transform warps
+  static constexpr int XFORM_WARPS = 8;  // FUSE: the transform warps are instruction-latency bound (one dependent stream per
+                                         // scheduler), more warps hide it
+  static constexpr int THREADS_FUSED = CONV_THREADS + XFORM_WARPS * 32;
   static_assert(2 * ACC_COLS <= 512, "double-buffered accumulators exceed TMEM");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -104,7 +108,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   const int tiles_per_n = a.tiles_x * a.tiles_y * a.tiles_z;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); mbar_init(a_ready + 8 * i, 4); }
+    for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); mbar_init(a_ready + 8 * i, Cfg::XFORM_WARPS); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
     fence_mbar_init();
@@ -246,7 +250,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     // =============================== in-place normalise of arriving halo planes ===============================
     // thread = (8-channel chunk of the block, 1 of LPC lanes walking that chunk's 18 x 10 halo positions): its 8 scales /
     // shifts / biases are reloaded (L1 hits) when the (sample, block) changes
-    constexpr int LPC = 128 / Cfg::KCH;  // lanes per chunk: 16 (64-channel blocks) or 32 (32-channel blocks)
+    constexpr int LPC = Cfg::XFORM_WARPS * 32 / Cfg::KCH;  // lanes per chunk
     constexpr int NPOS = Cfg::HY * Cfg::HX;  // 180 halo positions of one chunk plane
     constexpr int NV = (NPOS + LPC - 1) / LPC;  // vectors per thread per plane (6 or 12)
     const int tt = threadIdx.x - 7 * 32, chunk = tt / LPC, l0 = tt % LPC;

@@ -524,8 +524,7 @@ struct FuseIn {
 
 // can conv `c` at level `lvl` take its input through the normalise-on-load path of the Cout = 64 kernel?
 static bool conv_can_fuse_input(const dunet_plan* p, const ConvW& c, int lvl, int B) {
-  if (!(p->cfg.flags & DUNET_FLAG_FUSED_NORM)) return false;  // opt-in: measured slower, see include/dunet.h
-  if (p->cfg.flags & (DUNET_FLAG_REF_CONV | DUNET_FLAG_GENERIC_CONV | DUNET_FLAG_FP32X3)) return false;
+  if (p->cfg.flags & (DUNET_FLAG_REF_CONV | DUNET_FLAG_GENERIC_CONV | DUNET_FLAG_FP32X3 | DUNET_FLAG_NO_FUSED_NORM)) return false;
   if (c.parts != 1 || c.coutp != 64 || c.nb1 != 0 || !c.packed64) return false;
   const ConvGeom g = conv_geom(p, c, lvl, B);
   return g.ksplit == 1 && g.zt == CONV_ZT;

@@ -52,11 +52,12 @@ enum {
                                  same tcgen05 kernels (3x the MMA work, 2x the activation traffic, fp32 accumulation and
                                  fp32 elementwise math as in bf16 mode).  Meets north_star's 1e-4 / 99.9 % argmax gates */
 
-#define DUNET_FLAG_FUSED_NORM 32u /* experimental, off by default: the second conv of a TwoConv (Cout = 64 kernel) normalises
-                                    the first conv's raw output ON LOAD, in shared memory, instead of reading the tensor
-                                    norm_act_kernel materialises.  Bit-identical results (tested); measured SLOWER on B200
-                                    (64->64 @96^3 x4: 690 us vs 532 + 158 us): tcgen05.mma operand fetch already uses the
-                                    whole 128 B/clk shared-memory bandwidth, so the extra in-place pass stalls the MMAs */
+#define DUNET_FLAG_NO_FUSED_NORM 32u /* debug / A-B timing: materialise the normalised intermediate of every TwoConv with
+                                       norm_act_kernel.  By default the second conv of a TwoConv (Cout = 64 kernel, bf16
+                                       mode) normalises the first conv's raw output ON LOAD: eight extra warps rewrite each
+                                       TMA-loaded halo plane in shared memory (InstanceNorm + LeakyReLU + time bias) before
+                                       the MMAs read it, so that tensor never exists in HBM.  Bit-identical results (tested);
+                                       64->64 @96^3 x4: 558 us instead of 532 + 157 us */
 
 #define DUNET_FLAG_TC64_CB64 64u /* debug / A-B timing: the Cout = 64 kernel walks 64-channel blocks with a 7-slot plane ring
                                    instead of 32-channel blocks with a 13-slot ring */

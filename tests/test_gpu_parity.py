@@ -358,13 +358,13 @@ def test_fp32x3_batching_is_transparent():
 
 
 def test_normalise_on_load_is_bit_identical():
-    """DUNET_FLAG_FUSED_NORM (experimental): the second conv of a TwoConv normalises its input on load in shared memory
-    (conv3d_tc64 FUSE) instead of reading the tensor norm_act_kernel materialises.  Same fp32 formulas, same bf16
-    rounding points -> the whole DDIM window must agree bit for bit with the default path."""
+    """Default: the second conv of a TwoConv normalises its input on load in shared memory (conv3d_tc64 FUSE) instead of
+    reading a tensor norm_act_kernel materialised (DUNET_FLAG_NO_FUSED_NORM).  Same fp32 formulas, same bf16 rounding
+    points -> the whole DDIM window must agree bit for bit."""
     cout, S = 3, 64
     image, noise = seeded_image((2, 1, S, S, S)).cuda(), seeded_noise((2, cout, S, S, S)).cuda()
     a = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=3)(image=image, pred_type="ddim_sample", noise=noise)
-    b = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=3, debug_flags=_lib.DUNET_FLAG_FUSED_NORM)(
+    b = _build(cout, S, oracle_model.DEFAULT_FEATURES, num_steps=3, debug_flags=_lib.DUNET_FLAG_NO_FUSED_NORM)(
         image=image, pred_type="ddim_sample", noise=noise)
     assert torch.equal(a, b)
 
