@@ -677,7 +677,7 @@ static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src
     // output to ws.mid (ws.raw is still being read) -- callers get the buffer through *raw_out.
     float* affine = reinterpret_cast<float*>(ws + L.affine);
     const int planes = B * (t.a.coutp / 8);
-    TRY(prof_begin(PROF_NORM, st));
+    TRY(prof_begin(PROF_OTHER, st));
     launch_k(in_affine_kernel, dim3(planes), dim3(256), 0, st, (const float*)partial, nseg, (const float*)t.a.gamma,
              (const float*)t.a.beta, t.a.coutp / 8, (double)p->V[lvl], 1e-5f, affine);
     LAUNCH_CHECK();
