@@ -286,9 +286,9 @@ def run_b200(args):
             "roofline_hbm": {name: {"bound": "hbm", "achieved": fam_b[i] / fam_ms[i] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": fam_b[i] / fam_ms[i] / 1e6 / peaks["hbm_gbs"], "launches": int(fam_n[i]),
                                     "share_of_step": fam_ms[i] / ms}
-                             for i, name in ((1, "normalise (IN+LeakyReLU+bias+residual+pool)"), (2, "final 1x1 conv + DDIM update + accumulate"),
-                                             (3, "transposed conv k2s2")) if fam_ms[i] > 0},
-            "kernel_time_share": {n: fam_ms[i] / ms for i, n in enumerate(["conv3x3x3", "normalise", "final_ddim", "deconv", "splitk_reduce"])},
+                             for i, name in ((1, "normalise (IN+LeakyReLU+bias+residual+pool), launches >= 64 MB"), (2, "final 1x1 conv + DDIM update + accumulate"),
+                                             (3, "transposed conv k2s2"), (6, "normalise, launches < 64 MB (launch-latency bound)")) if fam_ms[i] > 0},
+            "kernel_time_share": {n: fam_ms[i] / ms for i, n in enumerate(["conv3x3x3", "normalise_large", "final_ddim", "deconv", "splitk_reduce", "affine_map", "normalise_small"])},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

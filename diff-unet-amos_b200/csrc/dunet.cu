@@ -58,7 +58,7 @@ static int fail(int code, const char* fmt, ...) {
 
 // ---- optional live profiling of the conv launches (bench.py roofline) ----
 struct ProfRec { cudaEvent_t a, b; int tag; };
-enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_TAGS = 8 };
+enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_NORM_SMALL = 6, PROF_TAGS = 8 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;       // event pool, reused across enable() calls
 static size_t g_prof_used = 0;
@@ -633,9 +633,13 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
   // ~4 resident blocks per SM in total, each streaming a long contiguous range of one 8-channel plane (the
   // statistics prologue is paid once per block)
   const int per_plane = std::max(1, (148 * 8 + planes - 1) / planes);
-  if (g_prof_on)  // one bf16 read + one bf16 write per element (+ read of the residual, + 1/8 write of the pooled tensor)
-    g_prof_bytes[PROF_NORM] += (prec ? 2.0 : 1.0) * B * c.coutp * (double)p->V[lvl] * (4.0 + (add.hi ? 2.0 : 0.0) + (pooled.hi ? 0.25 : 0.0));
-  TRY(prof_begin(PROF_NORM, st));
+  // one bf16 read + one bf16 write per element (+ read of the residual, + 1/8 write of the pooled tensor); launches that move
+  // less than 64 MB are launch-latency bound and are reported as their own family so that the HBM roofline of the large
+  // ones stays readable
+  const double nbytes = (prec ? 2.0 : 1.0) * B * c.coutp * (double)p->V[lvl] * (4.0 + (add.hi ? 2.0 : 0.0) + (pooled.hi ? 0.25 : 0.0));
+  const int ptag = nbytes >= 64e6 ? PROF_NORM : PROF_NORM_SMALL;
+  if (g_prof_on) g_prof_bytes[ptag] += nbytes;
+  TRY(prof_begin(ptag, st));
   if (pooled.hi) {
     const dim3 grid(grid_for(p->V[lvl] / 4, NORM_THREADS, per_plane), planes);
     if (prec) {

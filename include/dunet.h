@@ -194,7 +194,8 @@ int dunet_debug_set_conv_timeline(int64_t* dev_buffer);
  * kernel time (ms), number of conv launches, and their ALGORITHMIC flops 2*B*V*Cout*27*Cin (real channels only). */
 int dunet_profile_enable(int32_t on);
 int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_flops);
-/* per kernel family [8]: 0 conv3x3x3, 1 normalise, 2 final+DDIM, 3 transposed conv, 4 split-K reduce, 5 other.
+/* per kernel family [8]: 0 conv3x3x3, 1 normalise (launches moving >= 64 MB), 2 final+DDIM, 3 transposed conv, 4 split-K reduce,
+ * 5 other (affine-map kernel), 6 normalise launches below 64 MB (launch-latency bound).
  * bytes_by_tag (nullable): ALGORITHMIC HBM bytes of the bandwidth-bound families (normalise: 4 B/element (+2 residual,
  * +0.25 pooled); final+DDIM: per voxel 2F + 16C (+2C re-pack); transposed conv: 2(Cin + 8 Cout) per input voxel). */
 int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag);

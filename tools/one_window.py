@@ -49,7 +49,7 @@ if a.prof:
     msb = (ctypes.c_double * 8)(); cnt = (ctypes.c_uint64 * 8)(); byt = (ctypes.c_double * 8)()
     _lib.check(lib.dunet_profile_read_all(msb, cnt, byt))
     lib.dunet_profile_enable(0)
-    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "other"]
+    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "affine-map", "norm-small", "-"]
     tot = sum(msb)
     print("in-situ CUDA-event time per kernel family (one call, batch %d):" % a.batch)
     for i, nme in enumerate(names):
