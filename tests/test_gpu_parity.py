@@ -258,7 +258,7 @@ def test_config5_msd_128cube_ddim25():
     assert float(out.min()) >= -25.0 and float(out.max()) <= 25.0
 
 
-@pytest.mark.parametrize("cout", [15, 13, 1])
+@pytest.mark.parametrize("cout", [15, 13, 1, 20, 31])
 def test_odd_class_counts(cout):
     """include_background:false gives 15 / 13 output channels (cfg/amos/classes.yaml, engine.py:58-59): channel padding
     of the packed input, the final conv tiles and the state layout must not leak."""
