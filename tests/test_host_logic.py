@@ -130,3 +130,31 @@ def test_product_fails_loudly_without_a_gpu():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg_dir, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_window_grid_property_random_shapes():
+    """Property test (hypothesis): for random volumes / windows / overlaps the product's integer grid equals the restated
+    MONAI driver's, every voxel is covered, the last window ends at the border, and the count map is the outer product of
+    the per-axis counts."""
+    from hypothesis import given, settings, strategies as st
+
+    dim = st.integers(min_value=1, max_value=6).map(lambda k: 16 * k)
+
+    @settings(max_examples=60, deadline=None)
+    @given(roi=st.tuples(dim, dim, dim), extra=st.tuples(st.integers(0, 70), st.integers(0, 70), st.integers(0, 70)),
+           ov=st.sampled_from([0.0, 0.1, 0.25, 0.5, 0.8, 0.9]))
+    def check(roi, extra, ov):
+        vol = tuple(r + e for r, e in zip(roi, extra))
+        ours = windows.window_starts(vol, roi, ov)
+        ref = oracle_sliding.window_grid(vol, roi, ov)
+        assert np.array_equal(ours, ref)
+        cnt = oracle_sliding.count_map(vol, roi, ref)
+        assert cnt.min() >= 1
+        cd, ch, cw = windows.axis_counts(vol, roi, ov)
+        assert np.array_equal(cd[:, None, None] * ch[None, :, None] * cw[None, None, :], cnt)
+        assert all(int(ours[:, d].max()) + roi[d] == vol[d] for d in range(3))
+        for world in (2, 3, 8):
+            spans = [windows.shard_range(len(ours), r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == len(ours) and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+    check()
