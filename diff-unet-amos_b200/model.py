@@ -449,6 +449,18 @@ class DiffUNetB200(nn.Module):
         ``ensemble=R`` (BASELINE config 4; not in the reference) averages the summed outputs of R independent noise
         draws; the encoder runs once."""
         image = _f32c(image, "image")
+        if image.dim() == 5 and image.shape[0] > self.batch_max:
+            # more windows than the plan's batch_max (the reference accepts any sw_batch_size and loops at batch 1,
+            # diffusion.py:88-89): process them in chunks -- results are identical, batching is transparent
+            B = image.shape[0]
+            if noise is not None:
+                noise = _f32c(noise, "noise")
+                noise = noise.unsqueeze(0) if noise.dim() == 5 else noise
+            outs = []
+            for lo in range(0, B, self.batch_max):
+                hi = min(lo + self.batch_max, B)
+                outs.append(self.ddim_sample(image[lo:hi], None if noise is None else noise[:, lo:hi].contiguous(), ensemble))
+            return torch.cat(outs)
         self._check_image(image)
         B = image.shape[0]
         shape = (B, self.num_classes) + self.patch

@@ -453,7 +453,12 @@ def test_error_behaviour_matches_the_reference_seams():
     with pytest.raises(ValueError):
         m(image=seeded_image((1, 1, 32, 32, 48)).cuda(), pred_type="ddim_sample")
     with pytest.raises(ValueError, match="batch_max"):
-        m(image=seeded_image((3, 1, 32, 32, 32)).cuda(), pred_type="ddim_sample")
+        m.embed_model(seeded_image((3, 1, 32, 32, 32)).cuda())
+    # ... but ddim_sample accepts any number of windows (the reference takes any sw_batch_size): chunks of batch_max
+    img3, nz3 = seeded_image((3, 1, 32, 32, 32)).cuda(), seeded_noise((3, 2, 32, 32, 32)).cuda()
+    out3 = m(image=img3, pred_type="ddim_sample", noise=nz3)
+    assert out3.shape == nz3.shape
+    assert torch.equal(out3[2:3], m(image=img3[2:3], pred_type="ddim_sample", noise=nz3[2:3]))
     lib = _lib.load()
     assert lib.dunet_workspace_bytes(None, 1, ctypes.byref(ctypes.c_size_t())) == -1  # DUNET_E_INVALID
     assert b"NULL" in lib.dunet_last_error()
