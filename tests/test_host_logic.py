@@ -158,3 +158,21 @@ def test_window_grid_property_random_shapes():
             assert spans[0][0] == 0 and spans[-1][1] == len(ours) and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
 
     check()
+
+
+def test_bench_reference_arm_prints_one_valid_json_line():
+    """`bench.py --impl reference` (the reference's CPU path = oracle port on the host cores) prints exactly one JSON line
+    with the contract's keys; this is the only bench leg that may run without a GPU."""
+    import subprocess
+    import sys
+
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "patches/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
