@@ -19,6 +19,8 @@ DUNET_FLAG_DUAL_STREAM = 8
 DUNET_FLAG_FP32X3 = 16
 DUNET_FLAG_NO_FUSED_NORM = 32
 DUNET_FLAG_TC64_CB64 = 64
+DUNET_FLAG_FP16 = 128
+DUNET_FLAG_PLAIN_ENCODER = 256
 
 
 class DunetCfg(ctypes.Structure):
@@ -52,22 +54,26 @@ SIGNATURES = {
     "dunet_encode": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "dunet_get_embedding": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
     "dunet_set_embedding": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
-    "dunet_denoise_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p]),
+    "dunet_denoise_step": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_void_p, c_int32, c_void_p, c_void_p]),
     "dunet_ddim_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32, c_void_p, c_void_p]),
     "dunet_crop_window": (c_int32, [c_void_p, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    "dunet_crop_windows": (c_int32, [c_void_p, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p]),
+    "dunet_infer_windows": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p, c_uint64, POINTER(c_int64),
+                                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dunet_stitch_add": (c_int32, [c_void_p, POINTER(c_int32), c_int32, c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "dunet_finalize": (c_int32, [c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dunet_stitch_add_weighted": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "dunet_finalize_weighted": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_void_p]),
     "dunet_scale_intensity": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32, c_void_p]),
+    "dunet_q_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_uint64, c_int64, c_void_p]),
     "dunet_dice_counts": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "dunet_op_conv3x3x3": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, POINTER(c_int32), c_int32, c_void_p]),
     "dunet_op_deconv2x2x2": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int32, POINTER(c_int32), c_int32, c_void_p]),
     "dunet_debug_set_conv_timeline": (c_int32, [c_void_p]),
-    "dunet_profile_enable": (c_int32, [c_int32]),
-    "dunet_profile_read": (c_int32, [POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double)]),
-    "dunet_profile_read_all": (c_int32, [POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double)]),
-    "dunet_profile_dump": (c_int32, [POINTER(ctypes.c_double), POINTER(c_int32), c_int32, POINTER(c_int32)]),
+    "dunet_profile_enable": (c_int32, [c_void_p, c_int32]),
+    "dunet_profile_read": (c_int32, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double)]),
+    "dunet_profile_read_all": (c_int32, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double)]),
+    "dunet_profile_dump": (c_int32, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int32), c_int32, POINTER(c_int32)]),
     "dunet_debug_barrier_timeouts": (c_int32, [POINTER(c_uint32)]),
     "dunet_launch_count": (c_uint64, []),
 }

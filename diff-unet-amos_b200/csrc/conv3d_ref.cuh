@@ -9,6 +9,7 @@
 
 namespace dunet {
 
+template <bool HF>
 __global__ void __launch_bounds__(128) conv3d_ref_kernel(const __nv_bfloat16* __restrict__ src0, int c0, int chunks0,
                                                          const __nv_bfloat16* __restrict__ src1, int c1, int chunks1,
                                                          const float* __restrict__ w /*[cout][c0+c1][27]*/,
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(128) conv3d_ref_kernel(const __nv_bfloat16* __
             const BF8* sp = second ? reinterpret_cast<const BF8*>(src1) + ((long long)n * chunks1 + (ci - c0) / 8) * vox
                                    : reinterpret_cast<const BF8*>(src0) + ((long long)n * chunks0 + ci / 8) * vox;
             float xi[8];
-            bf8_to_float(sp[sv], xi);
+            bf8_to_float<HF>(sp[sv], xi);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               if (ci + k < cin) {
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(128) conv3d_ref_kernel(const __nv_bfloat16* __
                 for (int j = 0; j < 8; ++j) {
                   if (oc * 8 + j >= cout) continue;
                   const float wv =
-                      __bfloat162float(__float2bfloat16_rn(w[((long long)(oc * 8 + j) * cin + (rot ? (ci + k + 1) % c0 : ci + k)) * 27 + tap]));
+                      round_16<HF>(w[((long long)(oc * 8 + j) * cin + (rot ? (ci + k + 1) % c0 : ci + k)) * 27 + tap]);
                   acc[j] = fmaf(xi[k], wv, acc[j]);
                 }
               }
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(128) conv3d_ref_kernel(const __nv_bfloat16* __
         }
       }
     }
-    reinterpret_cast<BF8*>(out)[((long long)n * out_chunks + oc) * vox + v] = float_to_bf8(acc);
+    reinterpret_cast<BF8*>(out)[((long long)n * out_chunks + oc) * vox + v] = float_to_bf8<HF>(acc);
   }
 }
 

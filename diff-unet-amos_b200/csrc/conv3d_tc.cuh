@@ -172,7 +172,7 @@ __device__ __forceinline__ ConvItem conv_item(const ConvTcArgs& a, int item) {
 // PERSISTENT: gridDim.x <= #SMs CTAs walk the work items round-robin; the plane / weight rings run ahead across items
 // and, when 2 * ZT * N_TILE <= 512, the accumulators are double-buffered in TMEM so the epilogue of one item overlaps
 // the MMAs of the next.  Statistics rows are per spatial tile, so results do not depend on the item -> CTA assignment.
-template <int CB_CH, int N_TILE, int ZT, int MODE>
+template <int CB_CH, int N_TILE, int ZT, int MODE, bool H>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                  const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, ConvTcArgs a) {
@@ -268,7 +268,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
     // specialised on tz at compile time and all descriptor arithmetic is 32-bit (only the 14-bit start-address field
     // of the low descriptor word ever changes).
     if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE);
+      constexpr uint32_t idesc = make_idesc_16(128, N_TILE, H);
       const uint64_t a_desc0 = make_smem_desc(a_smem, Cfg::A_LBO, Cfg::A_SBO);
       const uint64_t b_desc0 = make_smem_desc(w_smem, Cfg::B_LBO, Cfg::B_SBO);
       const uint32_t a_lo0 = (uint32_t)a_desc0, a_hi = (uint32_t)(a_desc0 >> 32);
@@ -387,8 +387,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
                 float c0[8], c1[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { c0[i] = v[i]; c1[i] = v[8 + i]; }
-                store_split(a.out, a.out_lo, o, c0);
-                store_split(a.out, a.out_lo, o + in_vox, c1);
+                store_split<H>(a.out, a.out_lo, o, c0);
+                store_split<H>(a.out, a.out_lo, o + in_vox, c1);
               }
               if (do_stats) {
                 const float m = ok ? 1.f : 0.f;
@@ -411,8 +411,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
               float c0[8], c1[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) { c0[i] = v[i] + a.bias[co + i]; c1[i] = v[8 + i] + a.bias[co + 8 + i]; }
-              store_split(a.out, a.out_lo, o, c0);
-              store_split(a.out, a.out_lo, o + ovox, c1);
+              store_split<H>(a.out, a.out_lo, o, c0);
+              store_split<H>(a.out, a.out_lo, o + ovox, c1);
             }
           }
         }

@@ -67,6 +67,7 @@ struct ConvTc64Args {
   // [n * 8 + chunk][16] = scale[8], shift[8] (in_affine_kernel); bias added after the activation [64] or nullptr
   const float* in_affine;
   const float* in_bias;
+  int in_bias_n_stride;    // floats between the bias rows of consecutive samples (0: one row for the whole batch)
   float slope;
 };
 
@@ -83,7 +84,7 @@ __device__ __forceinline__ void for_each_tile(int tiles_per_n, int batch, F&& f)
   }
 }
 
-template <int CB_CH, int ZT, bool FUSE>
+template <int CB_CH, int ZT, bool FUSE, bool H>
 __global__ void __launch_bounds__(FUSE ? ConvTc64<CB_CH, ZT>::THREADS_FUSED : CONV_THREADS, 1)
 conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                    const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, ConvTc64Args a) {
@@ -224,10 +225,10 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
 #pragma unroll
                   for (int i = 0; i < nblk; ++i) {
                     const int sl = slab_lo + i, tz = p - sl;
-                    umma_bf16_lh(acc + sl * 64, al, a_hi, bl + i * 64, b_hi, make_idesc_bf16(128, 64), tz != 0 ? 1u : 0u);
+                    umma_bf16_lh(acc + sl * 64, al, a_hi, bl + i * 64, b_hi, make_idesc_16(128, 64, H), tz != 0 ? 1u : 0u);
                   }
                 } else {
-                  umma_bf16_lh(acc + slab_lo * 64, al, a_hi, bl, b_hi, make_idesc_bf16(128, 64 * nblk), 1u);
+                  umma_bf16_lh(acc + slab_lo * 64, al, a_hi, bl, b_hi, make_idesc_16(128, 64 * nblk, H), 1u);
                 }
               }
               if constexpr (KIND == 2) umma_commit(a_empty + pl_bar[p]);  // last reader of this plane for this block
@@ -286,7 +287,7 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
           sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
           sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bi[j] = a.in_bias ? __ldg(a.in_bias + gch * 8 + j) : 0.f;
+          for (int j = 0; j < 8; ++j) bi[j] = a.in_bias ? __ldg(a.in_bias + (long long)n * a.in_bias_n_stride + gch * 8 + j) : 0.f;
         }
         for (int p = 0; p < Cfg::PLANES; ++p, ++u) {
           const int slot = u % Cfg::A_SLOTS;
@@ -305,9 +306,9 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
               for (int j = 0; j < G; ++j)
                 if (j0 + j < NV && (mask >> (j0 + j) & 1u)) {
                   float f[8];
-                  bf8_to_float(v[j], f);
+                  bf8_to_float<H>(v[j], f);
                   norm_apply(f, sc, sh, bi, a.slope);
-                  *reinterpret_cast<BF8*>(pl + (j0 + j) * (LPC * 16)) = float_to_bf8(f);
+                  *reinterpret_cast<BF8*>(pl + (j0 + j) * (LPC * 16)) = float_to_bf8<H>(f);
                 }
             }
           }
@@ -371,8 +372,8 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
             float c0[8], c1[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { c0[i] = v[i]; c1[i] = v[8 + i]; }
-            store_split(a.out, a.out_lo, o, c0);
-            store_split(a.out, a.out_lo, o + vox, c1);
+            store_split<H>(a.out, a.out_lo, o, c0);
+            store_split<H>(a.out, a.out_lo, o + vox, c1);
           }
           if (a.stats) {
             const float m = ok ? 1.f : 0.f;

@@ -44,7 +44,7 @@ struct DeconvTcArgs {
   long long* dbg;          // optional timeline: per CTA 64 slots
 };
 
-template <int NCB, int ZT>
+template <int NCB, int ZT, bool H>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
   using Cfg = DeconvTc<NCB, ZT>;
@@ -116,7 +116,7 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
   } else if (warp == 2) {
     // =============================== MMA issuer ===============================
     if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::N_TILE);
+      constexpr uint32_t idesc = make_idesc_16(128, Cfg::N_TILE, H);
       const uint64_t a_desc0 = make_smem_desc(a_smem, Cfg::A_LBO, Cfg::A_SBO);
       const uint64_t b_desc0 = make_smem_desc(w_smem, Cfg::B_LBO, Cfg::B_SBO);
       int u0 = 0, w = 0, unit = 0;
@@ -197,10 +197,10 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
                 float lo[8], hi[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { lo[i] = v0[i] + bl[i]; hi[i] = v0[8 + i] + bh[i]; }
-                pk[0][0] = float_to_bf8(lo); pk[0][1] = float_to_bf8(hi);
+                pk[0][0] = float_to_bf8<H>(lo); pk[0][1] = float_to_bf8<H>(hi);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { lo[i] = v1[i] + bl[i]; hi[i] = v1[8 + i] + bh[i]; }
-                pk[1][0] = float_to_bf8(lo); pk[1][1] = float_to_bf8(hi);
+                pk[1][0] = float_to_bf8<H>(lo); pk[1][1] = float_to_bf8<H>(hi);
               }
               const int oz = 2 * z + dz;
 #pragma unroll

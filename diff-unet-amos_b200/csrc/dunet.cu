@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -56,33 +58,40 @@ static int fail(int code, const char* fmt, ...) {
     if (r__ != 0) return r__; \
   } while (0)
 
-// ---- optional live profiling of the conv launches (bench.py roofline) ----
+// ---- optional live profiling of the launches of ONE plan (bench.py roofline): CUDA events around every launch ----
 struct ProfRec { cudaEvent_t a, b; int tag; };
-enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_NORM_SMALL = 6, PROF_TAGS = 8 };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;       // event pool, reused across enable() calls
-static size_t g_prof_used = 0;
-static double g_prof_flops = 0.0;
-static double g_prof_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // ALGORITHMIC HBM bytes per kernel family (see dunet_profile_read_all)
-
-static int prof_begin(int tag, cudaStream_t st) {
-  if (!g_prof_on) return 0;
-  if (g_prof_used == g_prof.size()) {
+enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_NORM_SMALL = 6, PROF_GLUE = 7, PROF_TAGS = 8 };
+struct Prof {
+  bool on = false;
+  std::vector<ProfRec> recs;       // event pool, reused across enable() calls
+  size_t used = 0;
+  double flops = 0.0;
+  double bytes[PROF_TAGS] = {0, 0, 0, 0, 0, 0, 0, 0};  // ALGORITHMIC HBM bytes per kernel family (see dunet_profile_read_all)
+};
+struct dunet_plan;
+static Prof* prof_of(const dunet_plan* p);
+static int prof_begin_(Prof* pr, int tag, cudaStream_t st) {
+  if (!pr || !pr->on) return 0;
+  if (pr->used == pr->recs.size()) {
     ProfRec rec;
     CUDA_TRY(cudaEventCreate(&rec.a));
     CUDA_TRY(cudaEventCreate(&rec.b));
-    g_prof.push_back(rec);
+    pr->recs.push_back(rec);
   }
-  g_prof[g_prof_used].tag = tag;
-  CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].a, st));
+  pr->recs[pr->used].tag = tag;
+  CUDA_TRY(cudaEventRecord(pr->recs[pr->used].a, st));
   return 0;
 }
-static int prof_end(cudaStream_t st) {
-  if (!g_prof_on) return 0;
-  CUDA_TRY(cudaEventRecord(g_prof[g_prof_used].b, st));
-  ++g_prof_used;
+static int prof_end_(Prof* pr, cudaStream_t st) {
+  if (!pr || !pr->on) return 0;
+  CUDA_TRY(cudaEventRecord(pr->recs[pr->used].b, st));
+  ++pr->used;
   return 0;
 }
+// the launchers below all have the plan in scope as `p`
+#define prof_begin(tag, st) prof_begin_(prof_of(p), tag, st)
+#define prof_end(st) prof_end_(prof_of(p), st)
+#define PROF_ON (prof_of(p)->on)
 
 // Launch with programmatic stream serialization (see pdl_sync() in ptx.cuh): only for kernels that call pdl_sync().
 // DUNET_NO_PDL=1 in the environment falls back to plain stream order (debugging / A-B timing).
@@ -146,12 +155,16 @@ static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, in
 // conv weights fp32 [coutr][cinr][27] -> bf16 [n_tile][cin block][tap][k chunk][N_TILE][8]   (see conv3d_tc.cuh)
 // fp32x3 mode (parts == 3): the block list is [W.hi | W.hi | W.lo] (ncb = 3 x the logical blocks), matching the activation
 // segments [A.hi | A.lo | A.hi] of ConvSegs.
-__device__ __forceinline__ bf16 weight_part(float v, int part) {
+__device__ __forceinline__ bf16 weight_part(float v, int part, int fp16) {
+  if (fp16) {  // fp16 storage behind the 16-bit pointer type (DUNET_FLAG_FP16; never combined with the hi/lo split)
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const bf16*>(&h);
+  }
   const bf16 hi = __float2bfloat16_rn(v);
   return part < 2 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles, int rot, int parts) {
+                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles, int rot, int parts, int fp16) {
   const int kch = cb_ch / 8;
   const int ncb1 = ncb / parts;
   const long long total = (long long)n_tiles * ncb * 27 * kch * n_tile * 8;
@@ -172,13 +185,13 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
-    out[i] = weight_part(v, part);
+    out[i] = weight_part(v, part, fp16);
   }
 }
 // conv weights for the Cout = 64 z-stacked kernel (conv3d_tc64.cuh): bf16 [cin block][ty*3+tx][k chunk][192][8] with
 // row = (2 - tz) * 64 + cout
 __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                     int c0p, int c1r, int cb_ch, int ncb, int rot, int parts) {
+                                     int c0p, int c1r, int cb_ch, int ncb, int rot, int parts, int fp16) {
   const int kch = cb_ch / 8;
   const int ncb1 = ncb / parts;
   const long long total = (long long)ncb * 9 * kch * 192 * 8;
@@ -199,12 +212,12 @@ __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restri
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
-    out[i] = weight_part(v, part);
+    out[i] = weight_part(v, part, fp16);
   }
 }
 // transposed-conv weights fp32 [cinr][coutr][8] -> bf16 [tap][cinp][coutp]
 __global__ void pack_deconv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cinr, int coutr, int cinp,
-                                     int coutp) {
+                                     int coutp, int fp16) {
   const long long total = 8LL * cinp * coutp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -213,13 +226,13 @@ __global__ void pack_deconv_w_kernel(const float* __restrict__ w, bf16* __restri
     const int tap = (int)(i / ((long long)coutp * cinp));
     float v = 0.f;
     if (ci < cinr && co < coutr) v = w[((long long)ci * coutr + co) * 8 + tap];
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = weight_part(v, 0, fp16);
   }
 }
 // transposed-conv weights fp32 [cinr][coutr][8] -> tensor-core B operand bf16 [n_tile][cin block][k chunk][128][8] where
 // 128-column block nt = (dz*2 + dy) * (coutp/64) + cout/64, column inside it = dx * 64 + cout % 64  (tap = dz*4 + dy*2 + dx)
 __global__ void pack_deconv_tc_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cinr, int coutr, int cinp,
-                                        int coutp, int parts) {
+                                        int coutp, int parts, int fp16) {
   const int n_tile = 128, kch = 8, ncb1 = cinp / 64, ncb = ncb1 * parts, n_tiles = 8 * coutp / n_tile;
   const long long total = (long long)n_tiles * ncb * kch * n_tile * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -236,7 +249,7 @@ __global__ void pack_deconv_tc_w_kernel(const float* __restrict__ w, bf16* __res
     const int ci = cb * 64 + k * 8 + j;
     float v = 0.f;
     if (ci < cinr && co < coutr) v = w[((long long)ci * coutr + co) * 8 + tap];
-    out[i] = weight_part(v, part);
+    out[i] = weight_part(v, part, fp16);
   }
 }
 // copy `n` floats into a zero-padded buffer of n_pad floats, optionally strided rows: dst[r][0..cols_pad) <- src[r][0..cols)
@@ -304,7 +317,7 @@ struct Slot {
 };
 
 struct WsLayout {
-  size_t in_pack, raw, mid, partial, ss, splitk, affine, x_t, acc, total;
+  size_t in_pack, raw, mid, partial, ss, splitk, affine, x_t, acc, image, total;
   size_t emb[5], epool[5], x[5], dpool[5], up[5], u[5];
 };
 
@@ -339,7 +352,19 @@ struct dunet_plan {
   // (normalise, final/DDIM, transposed conv) overlap the tensor-core-bound convolutions of the other
   cudaStream_t half_stream[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  int num_sms = 0;
+  mutable Prof prof;  // per-plan launch profiler (dunet_profile_*)
+  // timesteps passed to dunet_denoise_step that are not one shared schedule entry (training-style calls, per-sample t):
+  // a [batch_max][temb_row] bias table built per call; the timesteps are staged through a small ring of pinned host
+  // slots (an event per slot says when its copy has been consumed) -- all allocated in dunet_plan_commit
+  static constexpr int T_RING = 8;
+  int* h_t = nullptr;          // pinned [T_RING][batch_max]
+  int* d_t = nullptr;          // device [batch_max]
+  float* temb_scratch = nullptr;  // device [batch_max][temb_row]
+  cudaEvent_t t_ev[T_RING] = {};
+  int t_slot = 0;
 };
+static Prof* prof_of(const dunet_plan* p) { return &p->prof; }
 
 static int dev_alloc(dunet_plan* p, void** out, size_t bytes) {
   CUDA_TRY(cudaMalloc(out, bytes ? bytes : 16));
@@ -400,25 +425,51 @@ static int stats_nseg(long long vox) {
 }
 
 static inline bool is_prec(const dunet_plan* p) { return (p->cfg.flags & DUNET_FLAG_FP32X3) != 0; }
+static inline bool is_fp16(const dunet_plan* p) { return (p->cfg.flags & DUNET_FLAG_FP16) != 0; }
+// dispatch a statement templated on the 16-bit storage format: DUNET_FMT(is_fp16(p), f<..., HF>(args))
+#define DUNET_FMT(cond, ...)                               \
+  do {                                                     \
+    if (cond) { constexpr bool HF = true; __VA_ARGS__; }   \
+    else { constexpr bool HF = false; __VA_ARGS__; }       \
+  } while (0)
+// a per-channel bias row (time-embedding projection), optionally one row per sample (n_stride floats apart)
+struct BiasRef {
+  const float* p = nullptr;
+  int n_stride = 0;
+  BiasRef at(int off) const { BiasRef r; r.p = p ? p + off : nullptr; r.n_stride = n_stride; return r; }
+};
 // activation of `ch` (padded) channels at U-Net level `lvl`, batch B, stored at workspace offset `off`: in fp32x3 mode the
 // low part follows the high part
-static inline Act ws_act(const dunet_plan* p, uint8_t* ws, size_t off, int ch, int lvl, int B) {
+static inline Act ws_act_x(const dunet_plan* p, uint8_t* ws, size_t off, int ch, int lvl, int B, bool prec) {
   Act a;
   a.hi = reinterpret_cast<bf16*>(ws + off);
-  a.lo = is_prec(p) ? a.hi + (size_t)B * ch * (size_t)p->V[lvl] : nullptr;
+  a.lo = prec ? a.hi + (size_t)B * ch * (size_t)p->V[lvl] : nullptr;
   return a;
 }
+static inline Act ws_act(const dunet_plan* p, uint8_t* ws, size_t off, int ch, int lvl, int B) {
+  return ws_act_x(p, ws, off, ch, lvl, B, is_prec(p));
+}
+// The ENCODER runs in split precision in fp32x3 mode and ALSO in fp16 mode: its feature maps are added into the denoiser
+// at every level of every DDIM step, so its rounding error is the one error source that repeats identically N times
+// (measured on a 96^3 window: 2/3 of the fp16 error variance; argmax agreement 99.90 % -> 99.94 % with an exact encoder).
+// It is 2.6 % of the FLOPs, so 3x its MMAs costs ~5 %.  DUNET_FLAG_PLAIN_ENCODER switches this off (A-B measurements).
+static inline bool enc_prec(const dunet_plan* p) {
+  return is_prec(p) || (is_fp16(p) && !(p->cfg.flags & DUNET_FLAG_PLAIN_ENCODER));
+}
+// 16-bit storage format of a tensor: fp16 in fp16 mode unless it is (part of) a split hi/lo bf16 pair
+static inline bool fmt_h(const dunet_plan* p, bool prec) { return is_fp16(p) && !prec; }
 
 static WsLayout ws_layout(const dunet_plan* p, int B) {
   WsLayout L;
   size_t off = 0;
-  const size_t pm = is_prec(p) ? 2 : 1;
+  const size_t pm = is_prec(p) ? 2 : 1, pme = enc_prec(p) ? 2 : 1;  // denoiser / encoder tensors: 1 or 2 (hi + lo) parts
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  auto act = [&](int ch, int lvl) -> size_t { return (size_t)(pm * (size_t)B * ch * (size_t)p->V[lvl] * sizeof(bf16)); };
-  L.in_pack = take(act(p->in_pad, 0));
+  auto act_m = [&](int ch, int lvl, size_t m) -> size_t { return (size_t)(m * (size_t)B * ch * (size_t)p->V[lvl] * sizeof(bf16)); };
+  auto act = [&](int ch, int lvl) -> size_t { return act_m(ch, lvl, pm); };
+  L.in_pack = take(act_m(p->in_pad, 0, std::max(pm, pme)));
   size_t raw_max = 0, part_max = 0, ss_max = 0, split_max = 0;
   auto upd = [&](const ConvW& c, int lvl) {
-    raw_max = std::max(raw_max, act(c.coutp, lvl));
+    raw_max = std::max(raw_max, act_m(c.coutp, lvl, c.parts == 3 ? 2 : 1));
     const ConvGeom g = conv_geom(p, c, lvl, B);
     const size_t planes = (size_t)B * (c.coutp / 8);
     part_max = std::max(part_max, planes * std::max(g.tiles, 160) * 16 * sizeof(float));  // rows: tiles, reduction segments (<= 128) or persistent CTAs (<= #SMs)
@@ -436,10 +487,11 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
   const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);  // voxel-major DDIM state, classes padded to the MMA column tiles
   L.x_t = take((size_t)B * CP * p->V[0] * sizeof(float));
   L.acc = take((size_t)B * CP * p->V[0] * sizeof(float));
+  L.image = take((size_t)B * p->cfg.in_channels * p->V[0] * sizeof(float));  // cropped windows (dunet_infer_windows)
   for (int l = 0; l < 5; ++l) {
-    L.emb[l] = take(act(p->fp[l], l));
+    L.emb[l] = take(act_m(p->fp[l], l, pme));
     L.x[l] = take(act(p->fp[l], l));
-    L.epool[l] = l ? take(act(p->fp[l - 1], l)) : 0;
+    L.epool[l] = l ? take(act_m(p->fp[l - 1], l, pme)) : 0;
     L.dpool[l] = l ? take(act(p->fp[l - 1], l)) : 0;
     L.up[l] = l ? take(act(p->upp[l], l - 1)) : 0;
     L.u[l] = l ? take(act(p->uoutp[l], l - 1)) : 0;
@@ -449,32 +501,57 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
 }
 
 // ------------------------------------------------------------------------------------------------ layer launchers
-static long long* g_conv_dbg = nullptr;  // optional per-CTA timeline buffer (tools only)
+// optional per-CTA timeline buffer of the generic conv / transposed conv kernels (tools only; process-global by design:
+// dunet_debug_set_conv_timeline is a debugging hook, see include/dunet.h)
+static long long* g_conv_dbg = nullptr;
 static int g_conv_dbg_count = 0;
-static int g_num_sms = 0;
 
-static int ensure_num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+// every tcgen05 kernel instantiation that exists: X(kernel, dynamic shared memory bytes)
+#define DUNET_TC_KERNELS_H(X, H)                                                                  \
+  X((conv3d_tc_kernel<32, 64, CONV_ZT, MODE_CONV3, H>), (ConvTc<32, 64, CONV_ZT, MODE_CONV3>::SMEM_BYTES))     \
+  X((conv3d_tc_kernel<32, 128, CONV_ZT, MODE_CONV3, H>), (ConvTc<32, 128, CONV_ZT, MODE_CONV3>::SMEM_BYTES))   \
+  X((conv3d_tc_kernel<64, 64, 2, MODE_CONV3, H>), (ConvTc<64, 64, 2, MODE_CONV3>::SMEM_BYTES))                 \
+  X((conv3d_tc_kernel<64, 128, 2, MODE_CONV3, H>), (ConvTc<64, 128, 2, MODE_CONV3>::SMEM_BYTES))               \
+  X((conv3d_tc_kernel<64, 64, CONV_ZT, MODE_CONV3, H>), (ConvTc<64, 64, CONV_ZT, MODE_CONV3>::SMEM_BYTES))     \
+  X((conv3d_tc_kernel<64, 128, CONV_ZT, MODE_CONV3, H>), (ConvTc<64, 128, CONV_ZT, MODE_CONV3>::SMEM_BYTES))   \
+  X((conv3d_tc_kernel<64, 128, 2, MODE_DECONV2, H>), (ConvTc<64, 128, 2, MODE_DECONV2>::SMEM_BYTES))           \
+  X((conv3d_tc64_kernel<32, CONV_ZT, false, H>), (ConvTc64<32, CONV_ZT>::SMEM_BYTES))                          \
+  X((conv3d_tc64_kernel<32, CONV_ZT, true, H>), (ConvTc64<32, CONV_ZT>::SMEM_BYTES))                           \
+  X((conv3d_tc64_kernel<64, CONV_ZT, false, H>), (ConvTc64<64, CONV_ZT>::SMEM_BYTES))                          \
+  X((conv3d_tc64_kernel<64, CONV_ZT, true, H>), (ConvTc64<64, CONV_ZT>::SMEM_BYTES))                           \
+  X((deconv2_tc_kernel<1, 2, H>), (DeconvTc<1, 2>::SMEM_BYTES))                                                \
+  X((deconv2_tc_kernel<2, 2, H>), (DeconvTc<2, 2>::SMEM_BYTES))
+
+// Per-DEVICE one-time setup (the dynamic shared memory opt-in of a kernel is a per-device attribute): keyed by device
+// id, mutex-protected.  Called from dunet_plan_create and the standalone dunet_op_* entry points, never on the per-step
+// path.  Returns the SM count of the current device.
+static std::mutex g_dev_mu;
+static std::unordered_map<int, int> g_dev_sms;
+static int dev_prepare(int* sms_out) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  auto it = g_dev_sms.find(dev);
+  if (it == g_dev_sms.end()) {
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+#define DUNET_SET_SMEM(K, BYTES) CUDA_TRY(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES));
+    DUNET_TC_KERNELS_H(DUNET_SET_SMEM, false)
+    DUNET_TC_KERNELS_H(DUNET_SET_SMEM, true)
+#undef DUNET_SET_SMEM
+    it = g_dev_sms.emplace(dev, sms).first;
   }
+  if (sms_out) *sms_out = it->second;
   return 0;
 }
 
-template <int CB_CH, int N_TILE, int ZT, int MODE>
-static int launch_conv_tc(const CUtensorMap (&t)[4], const ConvTcArgs& a, cudaStream_t st) {
+template <int CB_CH, int N_TILE, int ZT, int MODE, bool H>
+static int launch_conv_tc(const dunet_plan* p, const CUtensorMap (&t)[4], const ConvTcArgs& a, cudaStream_t st) {
   using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
-  static bool attr_set = false;
-  auto kern = conv3d_tc_kernel<CB_CH, N_TILE, ZT, MODE>;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  auto kern = conv3d_tc_kernel<CB_CH, N_TILE, ZT, MODE, H>;
   const long long items = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
-  TRY(ensure_num_sms());
   // persistent: one CTA per SM (each may own all 512 TMEM columns) walking the work items round-robin
-  const long long grid = std::min<long long>(items, (long long)g_num_sms);
+  const long long grid = std::min<long long>(items, (long long)p->num_sms);
   TRY(prof_begin(MODE == MODE_CONV3 ? PROF_CONV : PROF_DECONV, st));
   launch_k(kern, dim3((unsigned)grid), dim3(CONV_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
@@ -482,18 +559,12 @@ static int launch_conv_tc(const CUtensorMap (&t)[4], const ConvTcArgs& a, cudaSt
   return 0;
 }
 
-template <int CB_CH, bool FUSE>
-static int launch_conv_tc64(const CUtensorMap (&t)[4], const ConvTc64Args& a, unsigned* grid_out, cudaStream_t st) {
+template <int CB_CH, bool FUSE, bool H>
+static int launch_conv_tc64(const dunet_plan* p, const CUtensorMap (&t)[4], const ConvTc64Args& a, unsigned* grid_out, cudaStream_t st) {
   using Cfg = ConvTc64<CB_CH, CONV_ZT>;
-  static bool attr_set = false;
-  auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT, FUSE>;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
-  TRY(ensure_num_sms());
+  auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT, FUSE, H>;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.batch;
-  const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
+  const unsigned grid = (unsigned)std::min<long long>(tiles, p->num_sms);
   *grid_out = grid;
   TRY(prof_begin(PROF_CONV, st));
   launch_k(kern, dim3(grid), dim3(FUSE ? Cfg::THREADS_FUSED : CONV_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
@@ -519,7 +590,7 @@ static ConvSegs make_segs(int nb0, int chunks0, int nb1, int chunks1, bool prec)
 // LeakyReLU(x * scale + shift) + bias (in_affine_kernel output + optional time-embedding bias row)
 struct FuseIn {
   const float* affine = nullptr;
-  const float* bias = nullptr;
+  BiasRef bias;
 };
 
 // can conv `c` at level `lvl` take its input through the normalise-on-load path of the Cout = 64 kernel?
@@ -542,18 +613,18 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     if (!c.w32) return fail(DUNET_E_STATE, "DUNET_FLAG_REF_CONV needs DUNET_FLAG_KEEP_FP32_WEIGHTS");
     // the debug kernel writes only the chunks holding real output channels; padded chunks must still be zero
     CUDA_TRY(cudaMemsetAsync(out.hi, 0, (size_t)B * c.coutp * p->V[lvl] * sizeof(bf16), st));
-    conv3d_ref_kernel<<<grid_for((long long)B * ((c.coutr + 7) / 8) * p->V[lvl], 128, 148 * 64), 128, 0, st>>>(
-        src0.hi, c.c0r, c.c0p / 8, src1.hi, c.c1r, c.c1p / 8, c.w32, out.hi, c.coutr, c.coutp / 8, D, H, W, B, c.rot);
+    DUNET_FMT(fmt_h(p, prec), conv3d_ref_kernel<HF><<<grid_for((long long)B * ((c.coutr + 7) / 8) * p->V[lvl], 128, 148 * 64), 128, 0, st>>>(
+        src0.hi, c.c0r, c.c0p / 8, src1.hi, c.c1r, c.c1p / 8, c.w32, out.hi, c.coutr, c.coutp / 8, D, H, W, B, c.rot));
     LAUNCH_CHECK();
     if (partial) {
       const int nseg = stats_nseg(p->V[lvl]);
-      in_stats_kernel<<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(out.hi, partial, p->V[lvl], nseg);
+      DUNET_FMT(fmt_h(p, prec), in_stats_kernel<HF><<<dim3(nseg, planes), STATS_THREADS, 0, st>>>(out.hi, partial, p->V[lvl], nseg));
       LAUNCH_CHECK();
       *nseg_out = nseg;
     }
     return 0;
   }
-  if (g_prof_on) g_prof_flops += 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
+  if (PROF_ON) prof_of(p)->flops += 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
   const ConvGeom g = conv_geom(p, c, lvl, B);
   const int want_split = (splitk && partial) ? g.ksplit : 1;
   const bool use64 = c.packed64 && want_split == 1 && g.zt == CONV_ZT && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV);
@@ -575,10 +646,10 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     unsigned grid = 0;
     if (fuse) {
       if (c.nb1 != 0 || prec) return fail(DUNET_E_STATE, "normalise-on-load needs a single bf16 source");
-      b.in_affine = fuse->affine; b.in_bias = fuse->bias; b.slope = 0.1f;
-      TRY(cb == 32 ? (launch_conv_tc64<32, true>(t, b, &grid, st)) : (launch_conv_tc64<64, true>(t, b, &grid, st)));
+      b.in_affine = fuse->affine; b.in_bias = fuse->bias.p; b.in_bias_n_stride = fuse->bias.n_stride; b.slope = 0.1f;
+      DUNET_FMT(fmt_h(p, prec), TRY(cb == 32 ? (launch_conv_tc64<32, true, HF>(p, t, b, &grid, st)) : (launch_conv_tc64<64, true, HF>(p, t, b, &grid, st))));
     } else {
-      TRY(cb == 32 ? (launch_conv_tc64<32, false>(t, b, &grid, st)) : (launch_conv_tc64<64, false>(t, b, &grid, st)));
+      DUNET_FMT(fmt_h(p, prec), TRY(cb == 32 ? (launch_conv_tc64<32, false, HF>(p, t, b, &grid, st)) : (launch_conv_tc64<64, false, HF>(p, t, b, &grid, st))));
     }
     if (partial) *nseg_out = (int)grid;  // one statistics row per persistent CTA and sample
     return 0;
@@ -597,20 +668,22 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
   }
   if (a.ksplit > 1) a.out_partial = splitk;
   else a.stats = partial;
-  int rc;
-  if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3>(t, a, st);
-  else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3>(t, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 64 && g.zt == 2) rc = launch_conv_tc<64, 64, 2, MODE_CONV3>(t, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 128 && g.zt == 2) rc = launch_conv_tc<64, 128, 2, MODE_CONV3>(t, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3>(t, a, st);
-  else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3>(t, a, st);
-  else return fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
+  int rc = 0;
+  DUNET_FMT(fmt_h(p, prec), {
+    if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
+    else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
+    else if (c.cb_ch == 64 && c.n_tile == 64 && g.zt == 2) rc = launch_conv_tc<64, 64, 2, MODE_CONV3, HF>(p, t, a, st);
+    else if (c.cb_ch == 64 && c.n_tile == 128 && g.zt == 2) rc = launch_conv_tc<64, 128, 2, MODE_CONV3, HF>(p, t, a, st);
+    else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
+    else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
+    else rc = fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
+  });
   TRY(rc);
   if (a.ksplit > 1) {
     const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
     TRY(prof_begin(PROF_SPLITK, st));
-    launch_k(splitk_reduce_stats_kernel, dim3(nseg, planes), dim3(STATS_THREADS), 0, st, (const float*)splitk, a.ksplit,
-             (long long)B * c.coutp * p->V[lvl], out.hi, out.lo, partial, (long long)p->V[lvl], nseg);
+    DUNET_FMT(fmt_h(p, prec), launch_k(splitk_reduce_stats_kernel<HF>, dim3(nseg, planes), dim3(STATS_THREADS), 0, st, (const float*)splitk, a.ksplit,
+             (long long)B * c.coutp * p->V[lvl], out.hi, out.lo, partial, (long long)p->V[lvl], nseg));
     LAUNCH_CHECK();
     TRY(prof_end(st));
     *nseg_out = nseg;
@@ -621,12 +694,12 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
 }
 
 // statistics (reduced in the kernel prologue) -> fused normalise/activation(/bias/add/pool)
-static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* partial, int nseg, const float* bias, Act add,
+static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* partial, int nseg, BiasRef bias, Act add,
                     Act out, Act pooled, int lvl, int B, cudaStream_t st) {
   const int planes = B * (c.coutp / 8);
   const bool prec = raw.lo != nullptr;
   NormActArgs a;
-  a.raw = raw.hi; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias; a.add = add.hi;
+  a.raw = raw.hi; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias.p; a.bias_n_stride = bias.n_stride; a.add = add.hi;
   a.out = out.hi; a.pooled = pooled.hi; a.raw_lo = raw.lo; a.add_lo = add.lo; a.out_lo = out.lo; a.pooled_lo = pooled.lo;
   a.chunks = c.coutp / 8; a.D = p->D[lvl]; a.H = p->H[lvl]; a.W = p->W[lvl];
   a.eps = 1e-5f; a.slope = 0.1f;
@@ -636,29 +709,35 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
   // one bf16 read + one bf16 write per element (+ read of the residual, + 1/8 write of the pooled tensor); launches that move
   // less than 64 MB are launch-latency bound and are reported as their own family so that the HBM roofline of the large
   // ones stays readable
-  const double nbytes = (prec ? 2.0 : 1.0) * B * c.coutp * (double)p->V[lvl] * (4.0 + (add.hi ? 2.0 : 0.0) + (pooled.hi ? 0.25 : 0.0));
+  const double nbytes = (prec ? 2.0 : 1.0) * B * c.coutp * (double)p->V[lvl] * (4.0 + (add.hi ? (add.lo && !prec ? 4.0 : 2.0) : 0.0) + (pooled.hi ? 0.25 : 0.0));
   const int ptag = nbytes >= 64e6 ? PROF_NORM : PROF_NORM_SMALL;
-  if (g_prof_on) g_prof_bytes[ptag] += nbytes;
+  if (PROF_ON) prof_of(p)->bytes[ptag] += nbytes;
   TRY(prof_begin(ptag, st));
+  const int mode = prec ? MODE_FP32X3 : (is_fp16(p) ? MODE_FP16 : MODE_BF16);
+  if (prec && add.hi && !add.lo) return fail(DUNET_E_STATE, "fp32x3 normalise needs a hi + lo residual");
+  if (mode == MODE_BF16 && add.lo) return fail(DUNET_E_STATE, "bf16 normalise cannot take a hi + lo residual");
+#define DUNET_NORM(KERN, GRID)                                                                     \
+  do {                                                                                             \
+    if (mode == MODE_FP32X3) {                                                                     \
+      if (add.hi) launch_k(KERN<1, MODE_FP32X3>, GRID, dim3(NORM_THREADS), 0, st, a);              \
+      else launch_k(KERN<0, MODE_FP32X3>, GRID, dim3(NORM_THREADS), 0, st, a);                     \
+    } else if (mode == MODE_FP16) {                                                                \
+      if (add.hi && add.lo) launch_k(KERN<2, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);      \
+      else if (add.hi) launch_k(KERN<1, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);           \
+      else launch_k(KERN<0, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);                       \
+    } else {                                                                                       \
+      if (add.hi) launch_k(KERN<1, MODE_BF16>, GRID, dim3(NORM_THREADS), 0, st, a);                \
+      else launch_k(KERN<0, MODE_BF16>, GRID, dim3(NORM_THREADS), 0, st, a);                       \
+    }                                                                                              \
+  } while (0)
   if (pooled.hi) {
     const dim3 grid(grid_for(p->V[lvl] / 4, NORM_THREADS, per_plane), planes);
-    if (prec) {
-      if (add.hi) launch_k(norm_act_pool_kernel<true, true>, grid, dim3(NORM_THREADS), 0, st, a);
-      else launch_k(norm_act_pool_kernel<false, true>, grid, dim3(NORM_THREADS), 0, st, a);
-    } else {
-      if (add.hi) launch_k(norm_act_pool_kernel<true, false>, grid, dim3(NORM_THREADS), 0, st, a);
-      else launch_k(norm_act_pool_kernel<false, false>, grid, dim3(NORM_THREADS), 0, st, a);
-    }
+    DUNET_NORM(norm_act_pool_kernel, grid);
   } else {
     const dim3 grid(grid_for(p->V[lvl], NORM_THREADS * (prec ? 2 : 4), per_plane), planes);
-    if (prec) {
-      if (add.hi) launch_k(norm_act_kernel<true, true>, grid, dim3(NORM_THREADS), 0, st, a);
-      else launch_k(norm_act_kernel<false, true>, grid, dim3(NORM_THREADS), 0, st, a);
-    } else {
-      if (add.hi) launch_k(norm_act_kernel<true, false>, grid, dim3(NORM_THREADS), 0, st, a);
-      else launch_k(norm_act_kernel<false, false>, grid, dim3(NORM_THREADS), 0, st, a);
-    }
+    DUNET_NORM(norm_act_kernel, grid);
   }
+#undef DUNET_NORM
   LAUNCH_CHECK();
   TRY(prof_end(st));
   return 0;
@@ -667,11 +746,12 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
 // conv -> IN -> LReLU (+temb bias) -> conv -> IN -> LReLU (+add, +pool).  With `defer_last_norm` the second normalise
 // pass is left to the consumer (the final 1x1 conv kernel applies it on the fly): the raw output stays in ws.raw and
 // *nseg_out describes its statistics rows in ws.partial.
-static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src1, const float* temb_bias, Act add, Act out,
+static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src1, BiasRef temb_bias, Act add, Act out,
                        Act pooled, int lvl, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
                        bool defer_last_norm = false, int* nseg_out = nullptr, Act* raw_out = nullptr) {
-  const Act raw_a = ws_act(p, ws, L.raw, t.a.coutp, lvl, B), mid = ws_act(p, ws, L.mid, t.a.coutp, lvl, B);
-  const Act raw_b = ws_act(p, ws, L.raw, t.b.coutp, lvl, B);
+  const bool tp = t.a.parts == 3;  // this block runs in split precision (hi + lo tensors)
+  const Act raw_a = ws_act_x(p, ws, L.raw, t.a.coutp, lvl, B, tp), mid = ws_act_x(p, ws, L.mid, t.a.coutp, lvl, B, tp);
+  const Act raw_b = ws_act_x(p, ws, L.raw, t.b.coutp, lvl, B, tp);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
   float* splitk = reinterpret_cast<float*>(ws + L.splitk);
   int nseg = 0;
@@ -688,14 +768,14 @@ static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src
     TRY(prof_end(st));
     FuseIn f;
     f.affine = affine; f.bias = temb_bias;
-    const Act raw_b2 = ws_act(p, ws, L.mid, t.b.coutp, lvl, B);
+    const Act raw_b2 = ws_act_x(p, ws, L.mid, t.b.coutp, lvl, B, tp);
     TRY(run_conv(p, t.b, raw_a, Act(), raw_b2, partial, splitk, &nseg, lvl, B, st, &f));
     if (raw_out) *raw_out = raw_b2;
     if (defer_last_norm) {
       *nseg_out = nseg;
       return 0;
     }
-    TRY(run_norm(p, t.b, raw_b2, partial, nseg, nullptr, add, out, pooled, lvl, B, st));
+    TRY(run_norm(p, t.b, raw_b2, partial, nseg, BiasRef(), add, out, pooled, lvl, B, st));
     return 0;
   }
   if (raw_out) *raw_out = raw_b;
@@ -705,7 +785,7 @@ static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src
     *nseg_out = nseg;
     return 0;
   }
-  TRY(run_norm(p, t.b, raw_b, partial, nseg, nullptr, add, out, pooled, lvl, B, st));
+  TRY(run_norm(p, t.b, raw_b, partial, nseg, BiasRef(), add, out, pooled, lvl, B, st));
   return 0;
 }
 
@@ -714,8 +794,8 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
   if (p->cfg.flags & DUNET_FLAG_REF_CONV) {  // CUDA-core debug kernel
     if (prec) return fail(DUNET_E_UNSUPPORTED, "DUNET_FLAG_REF_CONV and DUNET_FLAG_FP32X3 are mutually exclusive");
     const long long total = (long long)B * (d.coutp / 8) * 8 * p->V[lvl_in];
-    deconv2_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in.hi, d.cinp, d.packed, d.bias, out.hi, d.coutp, p->D[lvl_in],
-                                                                    p->H[lvl_in], p->W[lvl_in], B);
+    DUNET_FMT(fmt_h(p, prec), deconv2_kernel<HF><<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(in.hi, d.cinp, d.packed, d.bias, out.hi, d.coutp,
+                                                                                         p->D[lvl_in], p->H[lvl_in], p->W[lvl_in], B));
     LAUNCH_CHECK();
     return 0;
   }
@@ -733,19 +813,12 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
     b.w = d.packed_tc; b.out = out.hi; b.bias = d.bias; b.chunks_in = d.cinp / 8; b.cout = d.coutp; b.D = D; b.H = H; b.W = W;
     b.tiles_x = (W + CONV_TX - 1) / CONV_TX; b.tiles_y = (H + CONV_TY - 1) / CONV_TY; b.tiles_z = (D + 1) / 2;
     b.n_tiles = 8 * d.coutp / 128; b.batch = B; b.dbg = getenv("DUNET_DBG_DECONV") ? g_conv_dbg : nullptr;
-    TRY(ensure_num_sms());
     const long long tiles = (long long)b.tiles_x * b.tiles_y * b.tiles_z * B;
-    const unsigned grid = (unsigned)std::min<long long>(tiles, g_num_sms);
-    static bool attr1 = false, attr2 = false;
-    if (g_prof_on) g_prof_bytes[PROF_DECONV] += (double)B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
+    const unsigned grid = (unsigned)std::min<long long>(tiles, p->num_sms);
+    if (PROF_ON) prof_of(p)->bytes[PROF_DECONV] += (double)B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
     TRY(prof_begin(PROF_DECONV, st));
-    if (d.cinp == 64) {
-      if (!attr1) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<1, 2>::SMEM_BYTES)); attr1 = true; }
-      launch_k(deconv2_tc_kernel<1, 2>, dim3(grid), dim3(CONV_THREADS), DeconvTc<1, 2>::SMEM_BYTES, st, t[0], b);
-    } else {
-      if (!attr2) { CUDA_TRY(cudaFuncSetAttribute(deconv2_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DeconvTc<2, 2>::SMEM_BYTES)); attr2 = true; }
-      launch_k(deconv2_tc_kernel<2, 2>, dim3(grid), dim3(CONV_THREADS), DeconvTc<2, 2>::SMEM_BYTES, st, t[0], b);
-    }
+    if (d.cinp == 64) DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<1, 2, HF>, dim3(grid), dim3(CONV_THREADS), DeconvTc<1, 2>::SMEM_BYTES, st, t[0], b));
+    else DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<2, 2, HF>, dim3(grid), dim3(CONV_THREADS), DeconvTc<2, 2>::SMEM_BYTES, st, t[0], b));
     LAUNCH_CHECK();
     TRY(prof_end(st));
     return 0;
@@ -763,8 +836,10 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
   a.cout = d.coutp; a.D = D; a.H = H; a.W = W;
   a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + 1) / 2;
   a.n_tiles = 8 * d.coutp / 128; a.ksplit = 1; a.batch = B; a.dbg = nullptr;
-  if (g_prof_on) g_prof_bytes[PROF_DECONV] += (prec ? 2.0 : 1.0) * B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
-  return launch_conv_tc<64, 128, 2, MODE_DECONV2>(t, a, st);
+  if (PROF_ON) prof_of(p)->bytes[PROF_DECONV] += (prec ? 2.0 : 1.0) * B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
+  int rc = 0;
+  DUNET_FMT(fmt_h(p, prec), rc = launch_conv_tc<64, 128, 2, MODE_DECONV2, HF>(p, t, a, st));
+  return rc;
 }
 
 // number of sub-batches a batch of B windows is split into in dual-stream mode (experiments: DUNET_NSTREAMS = 2..4)
@@ -783,32 +858,32 @@ static int check_call(const dunet_plan* p, int B, const void* ws) {
 
 static int launch_pack(const dunet_plan* p, const float* src0, int c0, const float* src1, int c1, Act dst, int c_pad,
                        long long vox, int B, cudaStream_t st) {
-  (void)p;
-  launch_k(pack_c8_kernel, dim3(grid_for((long long)B * (c_pad / 8) * vox, 256)), dim3(256), 0, st, src0, c0, src1, c1, dst.hi, dst.lo,
-           c_pad, vox, B);
+  DUNET_FMT(fmt_h(p, dst.lo != nullptr), launch_k(pack_c8_kernel<HF>, dim3(grid_for((long long)B * (c_pad / 8) * vox, 256)), dim3(256), 0, st, src0, c0, src1, c1,
+                                 dst.hi, dst.lo, c_pad, vox, B));
   LAUNCH_CHECK();
   return 0;
 }
 
 static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
-  const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
+  const bool ep = enc_prec(p);
+  const Act in_pack = ws_act_x(p, ws, L.in_pack, p->in_pad, 0, B, ep);
   TRY(launch_pack(p, image, p->cfg.in_channels, nullptr, 0, in_pack, p->in_pad, p->V[0], B, st));
   for (int l = 0; l < 5; ++l) {
-    const Act src = l ? ws_act(p, ws, L.epool[l], p->fp[l - 1], l, B) : in_pack;
-    const Act pooled = l < 4 ? ws_act(p, ws, L.epool[l + 1], p->fp[l], l + 1, B) : Act();
-    TRY(run_twoconv(p, p->enc[l], src, Act(), nullptr, Act(), ws_act(p, ws, L.emb[l], p->fp[l], l, B), pooled, l, B, ws, L, st));
+    const Act src = l ? ws_act_x(p, ws, L.epool[l], p->fp[l - 1], l, B, ep) : in_pack;
+    const Act pooled = l < 4 ? ws_act_x(p, ws, L.epool[l + 1], p->fp[l], l + 1, B, ep) : Act();
+    TRY(run_twoconv(p, p->enc[l], src, Act(), BiasRef(), Act(), ws_act_x(p, ws, L.emb[l], p->fp[l], l, B, ep), pooled, l, B, ws, L, st));
   }
   return 0;
 }
 
 // U-Net body given in_pack = cat([image, x_t]); leaves the RAW output of upcat_1.conv_1 in ws.raw
-static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
+static int unet_body(dunet_plan* p, BiasRef temb_row, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
                      int* last_nseg, Act* last_raw) {
   const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
   for (int l = 0; l < 5; ++l) {
     const Act src = l ? ws_act(p, ws, L.dpool[l], p->fp[l - 1], l, B) : in_pack;
     const Act pooled = l < 4 ? ws_act(p, ws, L.dpool[l + 1], p->fp[l], l + 1, B) : Act();
-    TRY(run_twoconv(p, p->den[l], src, Act(), temb_row + p->temb_off[l], ws_act(p, ws, L.emb[l], p->fp[l], l, B),
+    TRY(run_twoconv(p, p->den[l], src, Act(), temb_row.at(p->temb_off[l]), ws_act_x(p, ws, L.emb[l], p->fp[l], l, B, enc_prec(p)),
                     ws_act(p, ws, L.x[l], p->fp[l], l, B), pooled, l, B, ws, L, st));
   }
   Act prev = ws_act(p, ws, L.x[4], p->fp[4], 4, B);
@@ -816,7 +891,7 @@ static int unet_body(dunet_plan* p, const float* temb_row, int B, uint8_t* ws, c
     const Act up = ws_act(p, ws, L.up[l], p->upp[l], l - 1, B);
     TRY(run_deconv(p, p->dec[l], prev, up, l, B, st));
     const Act u = ws_act(p, ws, L.u[l], p->uoutp[l], l - 1, B);
-    TRY(run_twoconv(p, p->upc[l], ws_act(p, ws, L.x[l - 1], p->fp[l - 1], l - 1, B), up, temb_row + p->temb_off[5 + (4 - l)],
+    TRY(run_twoconv(p, p->upc[l], ws_act(p, ws, L.x[l - 1], p->fp[l - 1], l - 1, B), up, temb_row.at(p->temb_off[5 + (4 - l)]),
                     Act(), u, Act(), l - 1, B, ws, L, st, /*defer_last_norm=*/l == 1, last_nseg, l == 1 ? last_raw : nullptr));
     prev = u;
   }
@@ -853,15 +928,18 @@ static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) 
 #define DUNET_FINAL(NT)                                                                            \
   do {                                                                                             \
     if (prec) {                                                                                    \
-      if (a.F == 64) launch_k(final_ddim_kernel<NT, 4, true>, grid, dim3(FINAL_THREADS), 0, st, a);            \
-      else launch_k(final_ddim_kernel<NT, 8, true>, grid, dim3(FINAL_THREADS), 0, st, a);                      \
+      if (a.F == 64) launch_k(final_ddim_kernel<NT, 4, MODE_FP32X3>, grid, dim3(FINAL_THREADS), 0, st, a);     \
+      else launch_k(final_ddim_kernel<NT, 8, MODE_FP32X3>, grid, dim3(FINAL_THREADS), 0, st, a);               \
+    } else if (is_fp16(p)) {                                                                       \
+      if (a.F == 64) launch_k(final_ddim_kernel<NT, 4, MODE_FP16>, grid, dim3(FINAL_THREADS), 0, st, a);       \
+      else launch_k(final_ddim_kernel<NT, 8, MODE_FP16>, grid, dim3(FINAL_THREADS), 0, st, a);                 \
     } else {                                                                                       \
-      if (a.F == 64) launch_k(final_ddim_kernel<NT, 4, false>, grid, dim3(FINAL_THREADS), 0, st, a);           \
-      else launch_k(final_ddim_kernel<NT, 8, false>, grid, dim3(FINAL_THREADS), 0, st, a);                     \
+      if (a.F == 64) launch_k(final_ddim_kernel<NT, 4, MODE_BF16>, grid, dim3(FINAL_THREADS), 0, st, a);       \
+      else launch_k(final_ddim_kernel<NT, 8, MODE_BF16>, grid, dim3(FINAL_THREADS), 0, st, a);                 \
     }                                                                                              \
   } while (0)
-  if (g_prof_on)  // feature map read once (bf16) + fp32 state x_t and sum(x0) read+written + bf16 re-pack of the next input
-    g_prof_bytes[PROF_FINAL] += (double)a.batch * (double)a.vox * ((prec ? 4.0 : 2.0) * a.F + (a.x_t ? 16.0 * a.C : 0.0) + (a.logits_out ? 4.0 * a.C : 0.0) + (a.next_in ? 2.0 * a.C : 0.0));
+  if (PROF_ON)  // feature map read once (bf16) + fp32 state x_t and sum(x0) read+written + bf16 re-pack of the next input
+    prof_of(p)->bytes[PROF_FINAL] += (double)a.batch * (double)a.vox * ((prec ? 4.0 : 2.0) * a.F + (a.x_t ? 16.0 * a.C : 0.0) + (a.logits_out ? 4.0 * a.C : 0.0) + (a.next_in ? 2.0 * a.C : 0.0));
   TRY(prof_begin(PROF_FINAL, st));
   if (a.C <= 8) DUNET_FINAL(1);
   else if (a.C <= 16) DUNET_FINAL(2);
@@ -879,51 +957,56 @@ int dunet_version(void) { return DUNET_VERSION; }
 const char* dunet_last_error(void) { return g_err.c_str(); }
 uint64_t dunet_launch_count(void) { return g_launches.load(); }
 
-int dunet_profile_enable(int32_t on) {
-  g_prof_used = 0;
-  g_prof_flops = 0.0;
-  for (double& b : g_prof_bytes) b = 0.0;
-  g_prof_on = on != 0;
+int dunet_profile_enable(dunet_plan* p, int32_t on) {
+  if (!p) return fail(DUNET_E_INVALID, "plan is NULL");
+  Prof* pr = prof_of(p);
+  pr->used = 0;
+  pr->flops = 0.0;
+  for (double& b : pr->bytes) b = 0.0;
+  pr->on = on != 0;
   return 0;
 }
 
-int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_flops) {
-  if (!conv_ms || !conv_launches || !conv_flops) return fail(DUNET_E_INVALID, "NULL argument");
+int dunet_profile_read(dunet_plan* p, double* conv_ms, uint64_t* conv_launches, double* conv_flops) {
+  if (!p || !conv_ms || !conv_launches || !conv_flops) return fail(DUNET_E_INVALID, "NULL argument");
+  Prof* pr = prof_of(p);
   double total = 0.0;
   uint64_t n = 0;
-  for (size_t i = 0; i < g_prof_used; ++i) {
-    if (g_prof[i].tag != PROF_CONV) continue;
-    CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
+  for (size_t i = 0; i < pr->used; ++i) {
+    if (pr->recs[i].tag != PROF_CONV) continue;
+    CUDA_TRY(cudaEventSynchronize(pr->recs[i].b));
     float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
+    CUDA_TRY(cudaEventElapsedTime(&ms, pr->recs[i].a, pr->recs[i].b));
     total += ms;
     ++n;
   }
-  *conv_ms = total; *conv_launches = n; *conv_flops = g_prof_flops;
+  *conv_ms = total; *conv_launches = n; *conv_flops = pr->flops;
   return 0;
 }
 
-int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag) {
-  if (!ms_by_tag || !launches_by_tag) return fail(DUNET_E_INVALID, "NULL argument");
-  for (int i = 0; i < PROF_TAGS; ++i) { ms_by_tag[i] = 0.0; launches_by_tag[i] = 0; if (bytes_by_tag) bytes_by_tag[i] = g_prof_bytes[i]; }
-  for (size_t i = 0; i < g_prof_used; ++i) {
-    CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
+int dunet_profile_read_all(dunet_plan* p, double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag) {
+  if (!p || !ms_by_tag || !launches_by_tag) return fail(DUNET_E_INVALID, "NULL argument");
+  Prof* pr = prof_of(p);
+  for (int i = 0; i < PROF_TAGS; ++i) { ms_by_tag[i] = 0.0; launches_by_tag[i] = 0; if (bytes_by_tag) bytes_by_tag[i] = pr->bytes[i]; }
+  for (size_t i = 0; i < pr->used; ++i) {
+    CUDA_TRY(cudaEventSynchronize(pr->recs[i].b));
     float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b));
-    ms_by_tag[g_prof[i].tag] += ms;
-    launches_by_tag[g_prof[i].tag] += 1;
+    CUDA_TRY(cudaEventElapsedTime(&ms, pr->recs[i].a, pr->recs[i].b));
+    ms_by_tag[pr->recs[i].tag] += ms;
+    launches_by_tag[pr->recs[i].tag] += 1;
   }
   return 0;
 }
 
-int dunet_profile_dump(double* ms, int32_t* tags, int32_t capacity, int32_t* count) {
-  if (!ms || !tags || !count) return fail(DUNET_E_INVALID, "NULL argument");
+int dunet_profile_dump(dunet_plan* p, double* ms, int32_t* tags, int32_t capacity, int32_t* count) {
+  if (!p || !ms || !tags || !count) return fail(DUNET_E_INVALID, "NULL argument");
+  Prof* pr = prof_of(p);
   int n = 0;
-  for (size_t i = 0; i < g_prof_used && n < capacity; ++i, ++n) {
-    CUDA_TRY(cudaEventSynchronize(g_prof[i].b));
+  for (size_t i = 0; i < pr->used && n < capacity; ++i, ++n) {
+    CUDA_TRY(cudaEventSynchronize(pr->recs[i].b));
     float t = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
-    ms[n] = t; tags[n] = g_prof[i].tag;
+    CUDA_TRY(cudaEventElapsedTime(&t, pr->recs[i].a, pr->recs[i].b));
+    ms[n] = t; tags[n] = pr->recs[i].tag;
   }
   *count = n;
   return 0;
@@ -958,9 +1041,15 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
 
   if ((cfg->flags & DUNET_FLAG_FP32X3) && (cfg->flags & DUNET_FLAG_REF_CONV))
     return fail(DUNET_E_UNSUPPORTED, "DUNET_FLAG_REF_CONV and DUNET_FLAG_FP32X3 are mutually exclusive");
+  if ((cfg->flags & DUNET_FLAG_FP32X3) && (cfg->flags & DUNET_FLAG_FP16))
+    return fail(DUNET_E_UNSUPPORTED, "DUNET_FLAG_FP16 and DUNET_FLAG_FP32X3 are mutually exclusive (the hi/lo split is bf16)");
+  int sms = 0;
+  TRY(dev_prepare(&sms));  // per-device kernel attributes (shared-memory opt-in), once per device
   dunet_plan* p = new dunet_plan();
   p->cfg = *cfg;
+  p->num_sms = sms;
   const int parts = (cfg->flags & DUNET_FLAG_FP32X3) ? 3 : 1;
+  const int parts_enc = enc_prec(p) ? 3 : 1;
   const int cb64 = (cfg->flags & DUNET_FLAG_TC64_CB64) ? 64 : 32;
   p->C = cfg->num_classes;
   for (int l = 0; l < 5; ++l) {
@@ -978,9 +1067,9 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
   // encoder (no temb), pretrained/basic_unet.py:491-494
   for (int l = 0; l < 5; ++l) {
     TwoConvW& e = p->enc[l];
-    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], parts, cb64);
-    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts, cb64);
-    e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts, cb64);
+    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], parts_enc, cb64);
+    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts_enc, cb64);
+    e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts_enc, cb64);
     TwoConvW& d = p->den[l];
     d.has_temb = true;
     if (l == 0) { d.a.shape(cfg->in_channels + p->C, p->in_pad, 0, 0, p->fr[0], parts, cb64); d.a.rot = 1; }
@@ -1027,6 +1116,9 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
 void dunet_plan_destroy(dunet_plan* p) {
   if (!p) return;
   for (void* q : p->owned) cudaFree(q);
+  if (p->h_t) cudaFreeHost(p->h_t);
+  for (cudaEvent_t e : p->t_ev) if (e) cudaEventDestroy(e);
+  for (ProfRec& r : p->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (int i = 0; i < 4; ++i) {
     if (p->half_stream[i]) cudaStreamDestroy(p->half_stream[i]);
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
@@ -1052,13 +1144,13 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       if (!c->packed) TRY(dev_alloc(p, (void**)&c->packed, c->packed_elems() * sizeof(bf16)));
       const int cinr = c->c0r + c->c1r;
       pack_conv_w_kernel<<<grid_for((long long)c->packed_elems(), 256), 256, 0, st>>>(
-          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->ncb(), c->n_tiles, c->rot, c->parts);
+          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->ncb(), c->n_tiles, c->rot, c->parts, fmt_h(p, c->parts == 3) ? 1 : 0);
       LAUNCH_CHECK();
       if (c->coutp == 64) {
         const size_t n64 = c->packed64_elems();
         if (!c->packed64) TRY(dev_alloc(p, (void**)&c->packed64, n64 * sizeof(bf16)));
         pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(src, c->packed64, c->coutr, cinr, c->c0r, c->c0p,
-                                                                             c->c1r, c->cb64, c->ncb64(), c->rot, c->parts);
+                                                                             c->c1r, c->cb64, c->ncb64(), c->rot, c->parts, fmt_h(p, c->parts == 3) ? 1 : 0);
         LAUNCH_CHECK();
       }
       if (p->cfg.flags & DUNET_FLAG_KEEP_FP32_WEIGHTS) {
@@ -1103,11 +1195,11 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       DeconvW* d = static_cast<DeconvW*>(s.obj);
       const size_t n = 8ull * d->cinp * d->coutp;
       if (!d->packed) TRY(dev_alloc(p, (void**)&d->packed, n * sizeof(bf16)));
-      pack_deconv_w_kernel<<<grid_for((long long)n, 256), 256, 0, st>>>(src, d->packed, d->cinr, d->coutr, d->cinp, d->coutp);
+      pack_deconv_w_kernel<<<grid_for((long long)n, 256), 256, 0, st>>>(src, d->packed, d->cinr, d->coutr, d->cinp, d->coutp, is_fp16(p) ? 1 : 0);
       LAUNCH_CHECK();
       if (!d->packed_tc) TRY(dev_alloc(p, (void**)&d->packed_tc, n * d->parts * sizeof(bf16)));
       pack_deconv_tc_w_kernel<<<grid_for((long long)n * d->parts, 256), 256, 0, st>>>(src, d->packed_tc, d->cinr, d->coutr, d->cinp,
-                                                                                      d->coutp, d->parts);
+                                                                                      d->coutp, d->parts, is_fp16(p) ? 1 : 0);
       LAUNCH_CHECK();
       d->have_w = true;
       break;
@@ -1159,6 +1251,20 @@ int dunet_plan_commit(dunet_plan* p, void* stream) {
   CUDA_TRY(cudaMemsetAsync(p->temb_table, 0, (size_t)(p->n_steps + 1) * p->temb_row * sizeof(float), st));
   CUDA_TRY(cudaMemcpyAsync(p->d_tmap, p->tmap.data(), p->n_steps * sizeof(int), cudaMemcpyHostToDevice, st));
   TRY(launch_temb(p, p->d_tmap, p->n_steps, p->temb_table, st));
+  // everything the per-step entry points need later is created here: "no hidden allocation after commit"
+  if (!p->d_t) {
+    TRY(dev_alloc(p, (void**)&p->d_t, (size_t)p->cfg.batch_max * sizeof(int)));
+    TRY(dev_alloc(p, (void**)&p->temb_scratch, (size_t)p->cfg.batch_max * p->temb_row * sizeof(float)));
+    CUDA_TRY(cudaMallocHost((void**)&p->h_t, (size_t)dunet_plan::T_RING * p->cfg.batch_max * sizeof(int)));
+    for (int i = 0; i < dunet_plan::T_RING; ++i) CUDA_TRY(cudaEventCreateWithFlags(&p->t_ev[i], cudaEventDisableTiming));
+  }
+  if (!p->half_stream[0]) {
+    for (int i = 0; i < 4; ++i) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&p->half_stream[i], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaStreamSynchronize(st));  // host vector above must outlive the copy; commit is a setup-time call
   p->committed = true;
   return 0;
@@ -1185,9 +1291,9 @@ int dunet_get_embedding(dunet_plan* p, int32_t level, float* out, int32_t B, voi
   TRY(check_call(p, B, workspace));
   if (level < 0 || level > 4 || !out) return fail(DUNET_E_INVALID, "bad level / NULL out");
   const WsLayout L = ws_layout(p, B);
-  const Act e = ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B);
-  unpack_c8_kernel<<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      e.hi, e.lo, p->fp[level], out, p->fr[level], p->V[level], B);
+  const Act e = ws_act_x(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B, enc_prec(p));
+  DUNET_FMT(fmt_h(p, e.lo != nullptr), unpack_c8_kernel<HF><<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      e.hi, e.lo, p->fp[level], out, p->fr[level], p->V[level], B));
   LAUNCH_CHECK();
   return 0;
 }
@@ -1197,29 +1303,48 @@ int dunet_set_embedding(dunet_plan* p, int32_t level, const float* in, int32_t B
   if (level < 0 || level > 4 || !in) return fail(DUNET_E_INVALID, "bad level / NULL in");
   p->emb_B = B; p->emb_dual = false;
   const WsLayout L = ws_layout(p, B);
-  return launch_pack(p, in, p->fr[level], nullptr, 0, ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B),
+  return launch_pack(p, in, p->fr[level], nullptr, 0, ws_act_x(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B, enc_prec(p)),
                      p->fp[level], p->V[level], B, static_cast<cudaStream_t>(stream));
 }
 
-int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int32_t t_original, float* logits_out,
+int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, const int32_t* t_original, float* logits_out,
                        int32_t B, void* workspace, void* stream) {
   TRY(check_call(p, B, workspace));
-  if (!x_t || !image || !logits_out) return fail(DUNET_E_INVALID, "NULL tensor argument");
+  if (!x_t || !image || !logits_out || !t_original) return fail(DUNET_E_INVALID, "NULL tensor argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const WsLayout L = ws_layout(p, B);
+  // one timestep shared by the batch and present in the respaced schedule (the inference call): its precomputed row
   int row = -1;
-  for (int i = 0; i < p->n_steps; ++i)
-    if (p->tmap[i] == t_original) row = i;
-  if (row < 0) {  // timestep outside the respaced schedule (training-style call): build its row in the scratch slot
-    row = p->n_steps;
-    CUDA_TRY(cudaMemcpyAsync(p->d_tmap + row, &t_original, sizeof(int), cudaMemcpyHostToDevice, st));
-    TRY(launch_temb(p, p->d_tmap + row, 1, p->temb_table + (size_t)row * p->temb_row, st));
+  bool shared = true;
+  for (int n = 0; n < B; ++n) {
+    if (t_original[n] < 0) return fail(DUNET_E_INVALID, "timestep %d of sample %d is negative", (int)t_original[n], n);
+    shared = shared && t_original[n] == t_original[0];
+  }
+  if (shared)
+    for (int i = 0; i < p->n_steps; ++i)
+      if (p->tmap[i] == t_original[0]) row = i;
+  BiasRef temb;
+  if (row >= 0) {
+    temb.p = p->temb_table + (size_t)row * p->temb_row;
+  } else {
+    // training-style call (models/diffusion/diffusion.py:71-84: `step` is a per-sample tensor of arbitrary timesteps):
+    // build one bias row per sample.  The timesteps travel through a pinned ring slot owned by the plan.
+    const int slot = p->t_slot;
+    p->t_slot = (slot + 1) % dunet_plan::T_RING;
+    CUDA_TRY(cudaEventSynchronize(p->t_ev[slot]));  // the copy that last used this slot has been consumed
+    int* h = p->h_t + (size_t)slot * p->cfg.batch_max;
+    for (int n = 0; n < B; ++n) h[n] = t_original[n];
+    CUDA_TRY(cudaMemcpyAsync(p->d_t, h, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(p->t_ev[slot], st));
+    TRY(launch_temb(p, p->d_t, B, p->temb_scratch, st));
+    temb.p = p->temb_scratch;
+    temb.n_stride = p->temb_row;
   }
   TRY(launch_pack(p, x_t, p->C, image, p->cfg.in_channels, ws_act(p, ws, L.in_pack, p->in_pad, 0, B), p->in_pad, p->V[0], B, st));
   int nseg = 0;
   Act feat;
-  TRY(unet_body(p, p->temb_table + (size_t)row * p->temb_row, B, ws, L, st, &nseg, &feat));
+  TRY(unet_body(p, temb, B, ws, L, st, &nseg, &feat));
   FinalDdimArgs a;
   final_args_common(p, a, ws, L, nseg, B, feat);
   a.image = image; a.logits_out = logits_out;
@@ -1227,27 +1352,49 @@ int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, int3
   return launch_final(p, a, st);
 }
 
-// one batch (or half batch) of windows on one stream, workspace laid out for exactly B windows.
+// where the initial x_T of a batch comes from: the caller's tensor, or the library's counter-based generator
+struct NoiseSrc {
+  const float* given = nullptr;      // [B][C][vox] fp32 or nullptr
+  unsigned long long seed = 0;
+  const int64_t* ids = nullptr;      // host [B]: noise stream id per window (generator only)
+  int draw = 0;                      // ensemble draw index, folded into the stream id
+};
+
+// One batch (or half batch) of windows on one stream, workspace laid out for exactly B windows: encoder (optional), noise
+// initialisation, the N DDIM steps.  Leaves sum_k clamp(x0_k) in ws.acc and the last sample in ws.x_t, both voxel-major.
 // per_step_stride = elements between consecutive steps in per_step_logits (the FULL batch size when halves are used).
-static int ddim_sample_impl(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
-                            size_t per_step_stride, float* final_x, int B, int run_encoder, float out_scale, int out_accumulate,
-                            uint8_t* ws, cudaStream_t st) {
+static int ddim_core(dunet_plan* p, const float* image, const NoiseSrc& nz, int id0, float* per_step_logits, size_t per_step_stride,
+                     int B, int run_encoder, int zero_acc, uint8_t* ws, cudaStream_t st) {
   const WsLayout L = ws_layout(p, B);
   const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);
   float* x_t = reinterpret_cast<float*>(ws + L.x_t);   // voxel-major [B][vox][CP]
   float* acc = reinterpret_cast<float*>(ws + L.acc);
   if (run_encoder) TRY(encode_impl(p, image, B, ws, L, st));
-  const int sgrid = grid_for((long long)B * p->V[0] * (CP / 4), 256, 148 * 8);
-  launch_k(state_to_vm_kernel, dim3(sgrid), dim3(256), 0, st, noise, x_t, p->C, CP, (long long)p->V[0], B);
-  LAUNCH_CHECK();
-  launch_k(state_to_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)nullptr, acc, p->C, CP, (long long)p->V[0], B);
-  LAUNCH_CHECK();
   const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
-  TRY(launch_pack(p, noise, p->C, image, p->cfg.in_channels, in_pack, p->in_pad, p->V[0], B, st));
+  for (int b0 = 0; b0 < B; b0 += INIT_MAX_B) {  // x_t = noise, acc = 0, first conv input = [noise, image] in one pass
+    const int nb = std::min(INIT_MAX_B, B - b0);
+    DdimInitArgs ia;
+    memset(&ia, 0, sizeof ia);
+    ia.noise = nz.given ? nz.given + (size_t)b0 * p->C * p->V[0] : nullptr;
+    ia.image = image + (size_t)b0 * p->V[0];
+    ia.x_t = x_t + (size_t)b0 * p->V[0] * CP; ia.acc = acc + (size_t)b0 * p->V[0] * CP;
+    ia.next_in = in_pack.hi + (size_t)b0 * p->in_pad * p->V[0];
+    ia.next_in_lo = in_pack.lo ? in_pack.lo + (size_t)b0 * p->in_pad * p->V[0] : nullptr;
+    ia.C = p->C; ia.CP = CP; ia.in_pad = p->in_pad; ia.batch = nb; ia.zero_acc = zero_acc; ia.vox = p->V[0]; ia.seed = nz.seed;
+    for (int j = 0; j < nb; ++j) ia.ids[j] = nz.ids ? (long long)(((unsigned long long)nz.ids[id0 + b0 + j] & 0xFFFFFFFFFFull) | ((unsigned long long)nz.draw << 40)) : 0;
+    const int nch = std::max(CP, p->in_pad) / 8;
+    if (PROF_ON) prof_of(p)->bytes[PROF_GLUE] += (double)nb * p->V[0] * (CP * 8.0 + p->in_pad * 2.0 + 4.0 + (nz.given ? 4.0 * p->C : 0.0));
+    TRY(prof_begin(PROF_GLUE, st));
+    DUNET_FMT(fmt_h(p, in_pack.lo != nullptr), launch_k(ddim_init_kernel<HF>, dim3(grid_for((long long)nb * p->V[0] * nch, 256, 148 * 8)), dim3(256), 0, st, ia));
+    LAUNCH_CHECK();
+    TRY(prof_end(st));
+  }
   for (int i = p->n_steps - 1, k = 0; i >= 0; --i, ++k) {  // gaussian_diffusion.py:694 indices high -> low
     int nseg = 0;
     Act feat;
-    TRY(unet_body(p, p->temb_table + (size_t)i * p->temb_row, B, ws, L, st, &nseg, &feat));
+    BiasRef temb;
+    temb.p = p->temb_table + (size_t)i * p->temb_row;
+    TRY(unet_body(p, temb, B, ws, L, st, &nseg, &feat));
     FinalDdimArgs a;
     final_args_common(p, a, ws, L, nseg, B, feat);
     a.image = image; a.x_t = x_t; a.acc = acc;
@@ -1257,14 +1404,38 @@ static int ddim_sample_impl(dunet_plan* p, const float* image, const float* nois
     a.r = p->sr[i]; a.m = p->srm1[i]; a.abp = p->acp[i];
     TRY(launch_final(p, a, st));
   }
-  launch_k(state_from_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)acc, acc_out, p->C, CP, (long long)p->V[0], B, out_scale,
+  return 0;
+}
+
+// ddim_core + conversion of the voxel-major results to the reference's planar fp32 tensors
+static int ddim_sample_impl(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
+                            size_t per_step_stride, float* final_x, int B, int run_encoder, float out_scale, int out_accumulate,
+                            uint8_t* ws, cudaStream_t st) {
+  NoiseSrc nz;
+  nz.given = noise;
+  TRY(ddim_core(p, image, nz, 0, per_step_logits, per_step_stride, B, run_encoder, 1, ws, st));
+  const WsLayout L = ws_layout(p, B);
+  const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);
+  const int sgrid = grid_for((long long)B * p->V[0] * (CP / 4), 256, 148 * 8);
+  TRY(prof_begin(PROF_GLUE, st));
+  launch_k(state_from_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)(ws + L.acc), acc_out, p->C, CP, (long long)p->V[0], B, out_scale,
            out_accumulate);
   LAUNCH_CHECK();
+  TRY(prof_end(st));
   if (final_x) {
-    launch_k(state_from_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)x_t, final_x, p->C, CP, (long long)p->V[0], B, 1.f, 0);
+    launch_k(state_from_vm_kernel, dim3(sgrid), dim3(256), 0, st, (const float*)(ws + L.x_t), final_x, p->C, CP, (long long)p->V[0], B, 1.f, 0);
     LAUNCH_CHECK();
   }
   return 0;
+}
+
+// does this call run as sub-batches on the plan's internal streams?
+static bool use_dual(dunet_plan* p, int B, int run_encoder) {
+  static const int dual_min = [] { const char* e = getenv("DUNET_DUAL_MIN"); return e ? atoi(e) : 4; }();
+  const bool dual = run_encoder ? (B >= dual_min && B >= 2 && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !PROF_ON)
+                                : (p->emb_dual && p->emb_B == B);
+  if (run_encoder) { p->emb_B = B; p->emb_dual = dual; }
+  return dual;
 }
 
 int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, float* acc_out, float* per_step_logits,
@@ -1276,21 +1447,10 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t per_step_stride = (size_t)B * p->C * p->V[0];
-  static const int dual_min = [] { const char* e = getenv("DUNET_DUAL_MIN"); return e ? atoi(e) : 4; }();
-  const bool dual = run_encoder ? (B >= dual_min && B >= 2 && (p->cfg.flags & DUNET_FLAG_DUAL_STREAM) && !g_prof_on)
-                                : (p->emb_dual && p->emb_B == B);
-  if (run_encoder) { p->emb_B = B; p->emb_dual = dual; }
-  if (!dual)
+  if (!use_dual(p, B, run_encoder))
     return ddim_sample_impl(p, image, noise, acc_out, per_step_logits, per_step_stride, final_x, B, run_encoder, out_scale,
                             out_accumulate, ws, st);
   // ---- two half batches on two internal streams (fork from / join into the caller's stream; no host synchronisation)
-  if (!p->half_stream[0]) {
-    for (int i = 0; i < 4; ++i) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&p->half_stream[i], cudaStreamNonBlocking));
-      CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
-    }
-    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-  }
   const int ns = n_substreams(B);
   const int B0 = (B + ns - 1) / ns;
   const size_t half_ws = ws_layout(p, B0).total;
@@ -1324,6 +1484,96 @@ int dunet_crop_window(const float* volume, const int32_t v[3], float* patch, con
   crop_window_kernel<<<grid_for((long long)pd[0] * pd[1] * pd[2], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       volume, patch, v[0], v[1], v[2], pd[0], pd[1], pd[2], s[0], s[1], s[2]);
   LAUNCH_CHECK();
+  return 0;
+}
+
+static int crop_batch(const dunet_plan* p, const float* volume, const int32_t v[3], float* patches, const int32_t pd[3],
+                      const int32_t* starts, int B, cudaStream_t st) {
+  const long long pv = (long long)pd[0] * pd[1] * pd[2];
+  for (int b0 = 0; b0 < B; b0 += INIT_MAX_B) {
+    const int nb = std::min(INIT_MAX_B, B - b0);
+    CropArgs c;
+    memset(&c, 0, sizeof c);
+    c.vol = volume; c.patches = patches + (size_t)b0 * pv;
+    c.VD = v[0]; c.VH = v[1]; c.VW = v[2]; c.PD = pd[0]; c.PH = pd[1]; c.PW = pd[2]; c.batch = nb;
+    for (int j = 0; j < nb; ++j) {
+      TRY(check_box(v, pd, starts + 3 * (b0 + j)));
+      for (int d = 0; d < 3; ++d) c.start[j][d] = starts[3 * (b0 + j) + d];
+    }
+    if (p) {
+      if (PROF_ON) prof_of(p)->bytes[PROF_GLUE] += 8.0 * nb * pv;
+      TRY(prof_begin(PROF_GLUE, st));
+    }
+    launch_k(crop_windows_kernel, dim3(grid_for(pv * nb, 256)), dim3(256), 0, st, c);
+    LAUNCH_CHECK();
+    if (p) TRY(prof_end(st));
+  }
+  return 0;
+}
+
+int dunet_crop_windows(const float* volume, const int32_t v[3], float* patches, const int32_t pd[3], const int32_t* starts,
+                       int32_t B, void* stream) {
+  if (!volume || !patches || !v || !pd || !starts || B < 1) return fail(DUNET_E_INVALID, "bad argument");
+  return crop_batch(nullptr, volume, v, patches, pd, starts, B, static_cast<cudaStream_t>(stream));
+}
+
+int dunet_infer_windows(dunet_plan* p, const float* volume, const int32_t v[3], const int32_t* starts, int32_t B,
+                        const float* noise, uint64_t seed, const int64_t* noise_ids, int32_t ensemble, float* out_volume,
+                        float* count_volume, const float* weights, void* workspace, void* stream) {
+  TRY(check_call(p, B, workspace));
+  if (!volume || !v || !starts || !out_volume) return fail(DUNET_E_INVALID, "NULL argument");
+  if (!noise && !noise_ids) return fail(DUNET_E_INVALID, "either noise or noise_ids must be given");
+  if (ensemble < 1) return fail(DUNET_E_INVALID, "ensemble must be >= 1");
+  if ((weights == nullptr) != (count_volume == nullptr)) return fail(DUNET_E_INVALID, "weights and count_volume go together (gaussian blend)");
+  if (!aligned16(volume) || !aligned16(out_volume) || (noise && !aligned16(noise))) return fail(DUNET_E_INVALID, "tensors must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int32_t pd[3] = {p->D[0], p->H[0], p->W[0]};
+  const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);
+  const bool dual = use_dual(p, B, 1);
+  const int ns = dual ? n_substreams(B) : 1;
+  const int B0 = (B + ns - 1) / ns;
+  const WsLayout L0 = ws_layout(p, B0);
+  const size_t sub_ws = dual ? L0.total : 0;
+  // window crop: one launch per sub-batch, into that sub-batch's workspace
+  for (int h = 0; h < ns; ++h) {
+    const int b0 = h * B0, nb = std::min(B0, B - b0);
+    if (nb <= 0) break;
+    const WsLayout L = ws_layout(p, nb);
+    TRY(crop_batch(p, volume, v, reinterpret_cast<float*>(ws + h * sub_ws + L.image), pd, starts + 3 * b0, nb, st));
+  }
+  if (dual) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+  for (int h = 0; h < ns; ++h) {
+    const int b0 = h * B0, nb = std::min(B0, B - b0);
+    if (nb <= 0) break;
+    const WsLayout L = ws_layout(p, nb);
+    cudaStream_t hs = dual ? p->half_stream[h] : st;
+    if (dual) CUDA_TRY(cudaStreamWaitEvent(hs, p->ev_fork, 0));
+    const float* image = reinterpret_cast<const float*>(ws + h * sub_ws + L.image);
+    for (int r = 0; r < ensemble; ++r) {  // BASELINE config 4: R independent noise draws, summed; the encoder runs once
+      NoiseSrc nz;
+      nz.given = noise ? noise + ((size_t)r * B + b0) * p->C * p->V[0] : nullptr;
+      nz.seed = seed; nz.ids = noise_ids; nz.draw = r;
+      TRY(ddim_core(p, image, nz, b0, nullptr, 0, nb, r == 0, r == 0, ws + h * sub_ws, hs));
+    }
+    if (dual) CUDA_TRY(cudaEventRecord(p->ev_join[h], hs));
+  }
+  if (dual)
+    for (int h = 0; h < ns && h * B0 < B; ++h) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[h], 0));
+  // stitching, window by window in the caller's order (MONAI's): fp32 sums are formed in the oracle's order
+  const float scale = 1.f / (float)ensemble;
+  for (int b = 0; b < B; ++b) {
+    const int h = b / B0, j = b - h * B0, nb = std::min(B0, B - h * B0);
+    const WsLayout L = ws_layout(p, nb);
+    const float* acc = reinterpret_cast<const float*>(ws + h * sub_ws + L.acc) + (size_t)j * p->V[0] * CP;
+    const int32_t* s = starts + 3 * b;
+    if (PROF_ON) prof_of(p)->bytes[PROF_GLUE] += (double)p->V[0] * (4.0 * CP + 8.0 * p->C);
+    TRY(prof_begin(PROF_GLUE, st));
+    launch_k(stitch_from_vm_kernel, dim3(grid_for(p->V[0], 256, 148 * 8)), dim3(256), 0, st, out_volume, count_volume, acc, weights, p->C, CP,
+             v[0], v[1], v[2], pd[0], pd[1], pd[2], s[0], s[1], s[2], scale);
+    LAUNCH_CHECK();
+    TRY(prof_end(st));
+  }
   return 0;
 }
 
@@ -1376,6 +1626,17 @@ int dunet_scale_intensity(const float* in, float* out, int64_t n, float a_min, f
   return 0;
 }
 
+int dunet_q_sample(const float* x_start, const float* noise_in, float* noise_out, const int64_t* t_dev, const float* sqrt_ac,
+                   const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, uint64_t seed, int64_t id0, void* stream) {
+  if (!x_start || !t_dev || !sqrt_ac || !sqrt_1mac || !out || batch < 1 || per_sample < 1) return fail(DUNET_E_INVALID, "bad argument");
+  if (!noise_in && !noise_out) return fail(DUNET_E_INVALID, "generated noise needs noise_out (the reference returns it)");
+  q_sample_kernel<<<grid_for((per_sample + 3) / 4 * batch, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_start, noise_in, noise_out, reinterpret_cast<const long long*>(t_dev), sqrt_ac, sqrt_1mac, out, (long long)per_sample, batch,
+      (unsigned long long)seed, (long long)id0);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int dunet_dice_counts(const uint8_t* pred, const void* label, int32_t label_is_float, int32_t channels, int64_t voxels,
                       uint64_t* counts, void* stream) {
   if (!pred || !label || !counts || channels < 1 || voxels < 1) return fail(DUNET_E_INVALID, "bad argument");
@@ -1396,13 +1657,14 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
                        float* out, int32_t B, const int32_t dims[3], int32_t use_ref, void* stream) {
   if (!src0 || !weight || !out || !dims || c0 < 1 || cout < 1 || B < 1) return fail(DUNET_E_INVALID, "bad argument");
   if (c1 > 0 && !src1) return fail(DUNET_E_INVALID, "src1 is NULL but c1 > 0");
-  if (use_ref < 0 || use_ref > 4) return fail(DUNET_E_INVALID, "use_ref_kernel must be 0..4");
+  if (use_ref < 0 || use_ref > 6) return fail(DUNET_E_INVALID, "use_ref_kernel must be 0..6");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool prec = use_ref >= 3;
-  const bool generic_only = use_ref == 2 || use_ref == 4;
+  const bool prec = use_ref == 3 || use_ref == 4, fp16 = use_ref >= 5;
+  const bool generic_only = use_ref == 2 || use_ref == 4 || use_ref == 6;
   dunet_plan tmp;  // only geometry fields are used by run_conv
   memset(&tmp.cfg, 0, sizeof tmp.cfg);
-  tmp.cfg.flags = use_ref == 1 ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : (prec ? DUNET_FLAG_FP32X3 : 0);
+  TRY(dev_prepare(&tmp.num_sms));
+  tmp.cfg.flags = use_ref == 1 ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : (prec ? DUNET_FLAG_FP32X3 : (fp16 ? DUNET_FLAG_FP16 : 0));
   tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
   tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
   ConvW c;
@@ -1427,20 +1689,20 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   } else {
     CUDA_TRY(cudaMallocAsync((void**)&c.packed, c.packed_elems() * sizeof(bf16), st));
     pack_conv_w_kernel<<<grid_for((long long)c.packed_elems(), 256), 256, 0, st>>>(
-        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.ncb(), c.n_tiles, 0, c.parts);
+        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.ncb(), c.n_tiles, 0, c.parts, fp16 ? 1 : 0);
     LAUNCH_CHECK();
     if (c.coutp == 64 && !generic_only) {
       const size_t n64 = c.packed64_elems();
       CUDA_TRY(cudaMallocAsync((void**)&c.packed64, n64 * sizeof(bf16), st));
       pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(weight, c.packed64, c.coutr, c0 + c1, c.c0r, c.c0p,
-                                                                           c.c1r, c.cb64, c.ncb64(), 0, c.parts);
+                                                                           c.c1r, c.cb64, c.ncb64(), 0, c.parts, fp16 ? 1 : 0);
       LAUNCH_CHECK();
     }
   }
   int nseg_unused = 0;
   rc = run_conv(&tmp, c, a0, a1, raw, nullptr, nullptr, &nseg_unused, 0, B, st);
   if (rc == 0) {
-    unpack_c8_kernel<<<grid_for((long long)B * (c.coutp / 8) * vox, 256), 256, 0, st>>>(raw.hi, raw.lo, c.coutp, out, cout, vox, B);
+    DUNET_FMT(fp16, unpack_c8_kernel<HF><<<grid_for((long long)B * (c.coutp / 8) * vox, 256), 256, 0, st>>>(raw.hi, raw.lo, c.coutp, out, cout, vox, B));
     g_launches.fetch_add(1);
     if (cudaGetLastError() != cudaSuccess) rc = fail(DUNET_E_CUDA, "unpack launch failed");
   }
@@ -1455,13 +1717,15 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
 int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, const float* bias, int32_t cout, float* out,
                          int32_t B, const int32_t dims[3], int32_t use_ref, void* stream) {
   if (!src || !weight || !bias || !out || !dims || cin < 1 || cout < 1 || B < 1) return fail(DUNET_E_INVALID, "bad argument");
-  if (use_ref < 0 || use_ref > 4) return fail(DUNET_E_INVALID, "use_ref_kernel must be 0..4");
+  if (use_ref < 0 || use_ref > 6) return fail(DUNET_E_INVALID, "use_ref_kernel must be 0..6");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool prec = use_ref >= 3;
+  const bool prec = use_ref == 3 || use_ref == 4, fp16 = use_ref >= 5;
   dunet_plan tmp;
   memset(&tmp.cfg, 0, sizeof tmp.cfg);
-  tmp.cfg.flags = use_ref == 1 ? DUNET_FLAG_REF_CONV : ((use_ref == 2 || use_ref == 4) ? DUNET_FLAG_GENERIC_CONV : 0);
+  TRY(dev_prepare(&tmp.num_sms));
+  tmp.cfg.flags = use_ref == 1 ? DUNET_FLAG_REF_CONV : ((use_ref == 2 || use_ref == 4 || use_ref == 6) ? DUNET_FLAG_GENERIC_CONV : 0);
   if (prec) tmp.cfg.flags |= DUNET_FLAG_FP32X3;
+  if (fp16) tmp.cfg.flags |= DUNET_FLAG_FP16;
   tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
   tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
   DeconvW d;
@@ -1477,15 +1741,15 @@ int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, con
   CUDA_TRY(cudaMallocAsync((void**)&d.packed_tc, nw * d.parts * sizeof(bf16), st));
   CUDA_TRY(cudaMallocAsync((void**)&d.bias, d.coutp * sizeof(float), st));
   TRY(launch_pack(&tmp, src, cin, nullptr, 0, a0, d.cinp, vox, B, st));
-  pack_deconv_w_kernel<<<grid_for((long long)nw, 256), 256, 0, st>>>(weight, d.packed, cin, cout, d.cinp, d.coutp);
+  pack_deconv_w_kernel<<<grid_for((long long)nw, 256), 256, 0, st>>>(weight, d.packed, cin, cout, d.cinp, d.coutp, fp16 ? 1 : 0);
   LAUNCH_CHECK();
-  pack_deconv_tc_w_kernel<<<grid_for((long long)nw * d.parts, 256), 256, 0, st>>>(weight, d.packed_tc, cin, cout, d.cinp, d.coutp, d.parts);
+  pack_deconv_tc_w_kernel<<<grid_for((long long)nw * d.parts, 256), 256, 0, st>>>(weight, d.packed_tc, cin, cout, d.cinp, d.coutp, d.parts, fp16 ? 1 : 0);
   LAUNCH_CHECK();
   copy_pad_rows_kernel<<<1, 256, 0, st>>>(bias, d.bias, 1, cout, 1, d.coutp);
   LAUNCH_CHECK();
   int rc = run_deconv(&tmp, d, a0, o, 0, B, st);
   if (rc == 0) {
-    unpack_c8_kernel<<<grid_for((long long)B * (d.coutp / 8) * vox * 8, 256), 256, 0, st>>>(o.hi, o.lo, d.coutp, out, cout, vox * 8, B);
+    DUNET_FMT(fp16, unpack_c8_kernel<HF><<<grid_for((long long)B * (d.coutp / 8) * vox * 8, 256), 256, 0, st>>>(o.hi, o.lo, d.coutp, out, cout, vox * 8, B));
     g_launches.fetch_add(1);
     if (cudaGetLastError() != cudaSuccess) rc = fail(DUNET_E_CUDA, "unpack launch failed");
   }

@@ -6,52 +6,92 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "ptx.cuh"
 
 namespace dunet {
 
-struct alignas(16) BF8 {
+struct alignas(16) BF8 {  // 8 consecutive channels of one voxel: 16 bytes of 16-bit floats (bf16 or fp16, see below)
   __nv_bfloat162 v[4];
 };
 
+// 16-bit storage format of activations and packed weights, a compile-time switch `H` on every kernel that converts:
+//   H = false: bf16 (8 mantissa bits; also the element type of the hi / lo pairs of fp32x3 mode)
+//   H = true : fp16 (11 mantissa bits; DUNET_FLAG_FP16) -- the reference's own reduced precision (torch.autocast fp16,
+//              test.py:104,119 with cfg/btcv/test.yaml:16); the tensor cores take it at the bf16 rate (kind::f16)
+// Pointers stay typed __nv_bfloat16* in both modes: they are 16-bit storage, the kernels know the format.
+template <bool H>
 __device__ __forceinline__ void bf8_to_float(const BF8& b, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(b.v[i]);
+    float2 t;
+    if constexpr (H) t = __half22float2(*reinterpret_cast<const __half2*>(&b.v[i]));
+    else t = __bfloat1622float2(b.v[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
+template <bool H>
 __device__ __forceinline__ BF8 float_to_bf8(const float (&f)[8]) {
   BF8 b;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) b.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) {
+    if constexpr (H) *reinterpret_cast<__half2*>(&b.v[i]) = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    else b.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
   return b;
+}
+// two floats -> one 32-bit word of two 16-bit values (low half = first) and back
+template <bool H>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+  if constexpr (H) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+template <bool H>
+__device__ __forceinline__ float2 unpack_16x2(uint32_t w) {
+  if constexpr (H) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+template <bool H>
+__device__ __forceinline__ float round_16(float v) {
+  if constexpr (H) return __half2float(__float2half_rn(v));
+  else return __bfloat162float(__float2bfloat16_rn(v));
 }
 
 // fp32x3 ("split-bf16") mode: a tensor is a PAIR of C8-planar bf16 tensors, value = hi + lo, where hi = bf16(v) and
 // lo = bf16(v - hi) (v - hi is exact in fp32), so the pair carries ~16 mantissa bits.  `lo == nullptr` is the plain
-// bf16 mode everywhere below.
+// 16-bit mode everywhere below (fp16 mode never has a low part).
+template <bool H>
 __device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, long long idx8, const float (&f)[8]) {
-  const BF8 h = float_to_bf8(f);
+  const BF8 h = float_to_bf8<H>(f);
   reinterpret_cast<BF8*>(hi)[idx8] = h;
-  if (lo) {
-    float hf[8], r[8];
-    bf8_to_float(h, hf);
+  if constexpr (!H) {
+    if (lo) {
+      float hf[8], r[8];
+      bf8_to_float<false>(h, hf);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = f[j] - hf[j];
-    reinterpret_cast<BF8*>(lo)[idx8] = float_to_bf8(r);
+      for (int j = 0; j < 8; ++j) r[j] = f[j] - hf[j];
+      reinterpret_cast<BF8*>(lo)[idx8] = float_to_bf8<false>(r);
+    }
   }
 }
+template <bool H>
 __device__ __forceinline__ void load_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long idx8, float (&f)[8]) {
-  bf8_to_float(reinterpret_cast<const BF8*>(hi)[idx8], f);
-  if (lo) {
-    float g[8];
-    bf8_to_float(reinterpret_cast<const BF8*>(lo)[idx8], g);
+  bf8_to_float<H>(reinterpret_cast<const BF8*>(hi)[idx8], f);
+  if constexpr (!H) {
+    if (lo) {
+      float g[8];
+      bf8_to_float<false>(reinterpret_cast<const BF8*>(lo)[idx8], g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] += g[j];
+      for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
   }
 }
 
@@ -59,6 +99,7 @@ __device__ __forceinline__ void load_split(const __nv_bfloat16* hi, const __nv_b
 // pack: fp32 NCDHW (two concatenated sources) -> bf16 C8-planar with c_pad channels (zero padded).
 // Used for the denoiser input cat([image, x_t]) (reference denoiser.py:298) and for boundary tensors.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool H>
 __global__ void pack_c8_kernel(const float* __restrict__ src0, int c0, const float* __restrict__ src1, int c1,
                                __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo, int c_pad, long long vox,
                                int batch) {
@@ -79,11 +120,12 @@ __global__ void pack_c8_kernel(const float* __restrict__ src0, int c0, const flo
       else if (c < c0 + c1) val = src1[((long long)n * c1 + (c - c0)) * vox + v];
       f[j] = val;
     }
-    store_split(dst, dst_lo, i, f);
+    store_split<H>(dst, dst_lo, i, f);
   }
 }
 
 // unpack: bf16 C8-planar (hi [+ lo]) -> fp32 NCDHW (first c_out channels).
+template <bool H>
 __global__ void unpack_c8_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ src_lo, int c_pad,
                                  float* __restrict__ dst, int c_out, long long vox, int batch) {
   const int chunks = c_pad / 8;
@@ -94,7 +136,7 @@ __global__ void unpack_c8_kernel(const __nv_bfloat16* __restrict__ src, const __
     int ck = (int)((i / vox) % chunks);
     int n = (int)(i / (vox * chunks));
     float f[8];
-    load_split(src, src_lo, i, f);
+    load_split<H>(src, src_lo, i, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int c = ck * 8 + j;
@@ -109,6 +151,7 @@ __global__ void unpack_c8_kernel(const __nv_bfloat16* __restrict__ src, const __
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int STATS_THREADS = 256;
 
+template <bool H>
 __global__ void __launch_bounds__(STATS_THREADS) in_stats_kernel(const __nv_bfloat16* __restrict__ raw,
                                                                  float* __restrict__ partial, long long vox, int nseg) {
   const int plane = blockIdx.y, seg = blockIdx.x;
@@ -120,7 +163,7 @@ __global__ void __launch_bounds__(STATS_THREADS) in_stats_kernel(const __nv_bflo
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   for (long long v = lo + threadIdx.x; v < hi; v += STATS_THREADS) {
     float f[8];
-    bf8_to_float(p[v], f);
+    bf8_to_float<H>(p[v], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j] += f[j];
@@ -154,6 +197,7 @@ __global__ void __launch_bounds__(STATS_THREADS) in_stats_kernel(const __nv_bflo
 
 // Split-K epilogue: sum the fp32 partial tiles of the ksplit CTAs in a fixed order, write the bf16 raw conv output and
 // the InstanceNorm partial statistics of the (un-rounded) sums.  partial: [ks][plane][vox][8] fp32.
+template <bool H>
 __global__ void __launch_bounds__(STATS_THREADS) splitk_reduce_stats_kernel(const float* __restrict__ part, int ksplit,
                                                                             long long split_stride /*floats*/,
                                                                             __nv_bfloat16* __restrict__ raw,
@@ -177,7 +221,7 @@ __global__ void __launch_bounds__(STATS_THREADS) splitk_reduce_stats_kernel(cons
       f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
       f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
     }
-    store_split(raw, raw_lo, (long long)plane * vox + v, f);
+    store_split<H>(raw, raw_lo, (long long)plane * vox + v, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       s[j] += f[j];
@@ -222,6 +266,7 @@ struct NormActArgs {
   const float* gamma;      // [C]
   const float* beta;       // [C]
   const float* bias;       // [C] additive after activation (temb projection) or nullptr
+  int bias_n_stride;       // floats between the bias rows of consecutive samples (0: one row for the whole batch)
   const __nv_bfloat16* add;  // C8-planar tensor added after activation (encoder feature) or nullptr
   __nv_bfloat16* out;
   __nv_bfloat16* pooled;   // POOL only
@@ -283,7 +328,8 @@ __global__ void __launch_bounds__(256) in_affine_kernel(const float* __restrict_
 
 __device__ __forceinline__ void norm_prologue(const NormActArgs& a, int plane, float* sc, float* sh, float* bi,
                                               double* scratch) {
-  if (threadIdx.x < 8) bi[threadIdx.x] = a.bias ? a.bias[(plane % a.chunks) * 8 + threadIdx.x] : 0.f;
+  if (threadIdx.x < 8)
+    bi[threadIdx.x] = a.bias ? a.bias[(long long)(plane / a.chunks) * a.bias_n_stride + (plane % a.chunks) * 8 + threadIdx.x] : 0.f;
   stats_to_affine(a.partial, a.nseg, plane, a.gamma, a.beta, a.chunks, (double)a.D * a.H * a.W, a.eps, sc, sh, scratch);
 }
 
@@ -297,11 +343,17 @@ __device__ __forceinline__ void norm_apply(float (&f)[8], const float* sc, const
   }
 }
 
-// ADD: the encoder-feature residual is present.  PREC: fp32x3 mode (hi + lo pairs in, hi + lo pairs out).  All variants
-// keep 4 independent 16-byte loads per tensor in flight per thread; __launch_bounds__ asks for 3-4 resident blocks per
-// SM so ~64 KB of loads are outstanding per SM.
-template <bool ADD, bool PREC>
-__global__ void __launch_bounds__(NORM_THREADS, (ADD || PREC) ? 3 : 4) norm_act_kernel(NormActArgs a) {
+// ADD: 0 = no residual, 1 = the encoder-feature residual is present in the tensor's own format, 2 = it is present as a
+// bf16 hi + lo PAIR while everything else is 16-bit (fp16 mode keeps the encoder, whose rounding error would repeat
+// identically in all N DDIM steps, in split precision).  MODE: 0 = bf16, 1 = fp32x3 (hi + lo pairs in and out), 2 = fp16.
+// All variants keep 4 independent 16-byte loads per tensor in flight per thread; __launch_bounds__ asks for 3-4 resident
+// blocks per SM so ~64 KB of loads are outstanding per SM.
+constexpr int MODE_BF16 = 0, MODE_FP32X3 = 1, MODE_FP16 = 2;
+
+template <int ADD, int MODE>
+__global__ void __launch_bounds__(NORM_THREADS, (ADD || MODE == MODE_FP32X3) ? 3 : 4) norm_act_kernel(NormActArgs a) {
+  constexpr bool PREC = MODE == MODE_FP32X3, H = MODE == MODE_FP16;
+  constexpr bool ADD_PAIR = ADD == 2 || (ADD && PREC), ADD_H = H && ADD == 1;  // residual: hi + lo bf16 pair / fp16
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;  // n*chunks + chunk
@@ -323,7 +375,7 @@ __global__ void __launch_bounds__(NORM_THREADS, (ADD || PREC) ? 3 : 4) norm_act_
         xin[u] = in[v];
         if constexpr (PREC) xlo[u] = in_lo[v];
         if constexpr (ADD) ain[u] = add[v];
-        if constexpr (ADD && PREC) alo[u] = add_lo[v];
+        if constexpr (ADD_PAIR) alo[u] = add_lo[v];
       }
     }
 #pragma unroll
@@ -331,27 +383,27 @@ __global__ void __launch_bounds__(NORM_THREADS, (ADD || PREC) ? 3 : 4) norm_act_
       const long long v = v0 + u * stride;
       if (v < vox) {
         float f[8];
-        bf8_to_float(xin[u], f);
+        bf8_to_float<H>(xin[u], f);
         if constexpr (PREC) {
           float g[8];
-          bf8_to_float(xlo[u], g);
+          bf8_to_float<false>(xlo[u], g);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
         norm_apply(f, sc, sh, bi, a.slope);
         if constexpr (ADD) {
           float g[8];
-          bf8_to_float(ain[u], g);
-          if constexpr (PREC) {
+          bf8_to_float<ADD_H>(ain[u], g);
+          if constexpr (ADD_PAIR) {
             float h[8];
-            bf8_to_float(alo[u], h);
+            bf8_to_float<false>(alo[u], h);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] += h[j];
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
-        store_split(a.out, PREC ? a.out_lo : nullptr, plane * vox + v, f);
+        store_split<H>(a.out, PREC ? a.out_lo : nullptr, plane * vox + v, f);
       }
     }
   }
@@ -359,10 +411,12 @@ __global__ void __launch_bounds__(NORM_THREADS, (ADD || PREC) ? 3 : 4) norm_act_
 
 // Same pass + the 2x2x2 max-pool of the result (Down, denoiser.py:105-108).  thread = (x, y/2, z/2): it handles the four
 // (dz, dy) voxels at its x (lanes run along x: every load/store instruction covers 512 contiguous bytes) and completes
-// the pool with its x^1 neighbour through a shuffle; the pooled tensor is built from the ROUNDED outputs (bf16, or the
+// the pool with its x^1 neighbour through a shuffle; the pooled tensor is built from the ROUNDED outputs (16-bit, or the
 // hi + lo sum in fp32x3 mode) so that pooled == maxpool(out) exactly.
-template <bool ADD, bool PREC>
-__global__ void __launch_bounds__(NORM_THREADS, PREC ? 2 : 3) norm_act_pool_kernel(NormActArgs a) {
+template <int ADD, int MODE>
+__global__ void __launch_bounds__(NORM_THREADS, MODE == MODE_FP32X3 ? 2 : 3) norm_act_pool_kernel(NormActArgs a) {
+  constexpr bool PREC = MODE == MODE_FP32X3, H = MODE == MODE_FP16;
+  constexpr bool ADD_PAIR = ADD == 2 || (ADD && PREC), ADD_H = H && ADD == 1;
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;
@@ -392,7 +446,7 @@ __global__ void __launch_bounds__(NORM_THREADS, PREC ? 2 : 3) norm_act_pool_kern
         xin[k] = in[vv[k]];
         if constexpr (PREC) xlo[k] = in_lo[vv[k]];
         if constexpr (ADD) ain[k] = add[vv[k]];
-        if constexpr (ADD && PREC) alo[k] = add_lo[vv[k]];
+        if constexpr (ADD_PAIR) alo[k] = add_lo[vv[k]];
       }
     }
     float m[8];
@@ -402,38 +456,38 @@ __global__ void __launch_bounds__(NORM_THREADS, PREC ? 2 : 3) norm_act_pool_kern
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float f[8];
-        bf8_to_float(xin[k], f);
+        bf8_to_float<H>(xin[k], f);
         if constexpr (PREC) {
           float g[8];
-          bf8_to_float(xlo[k], g);
+          bf8_to_float<false>(xlo[k], g);
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
         norm_apply(f, sc, sh, bi, a.slope);
         if constexpr (ADD) {
           float g[8];
-          bf8_to_float(ain[k], g);
-          if constexpr (PREC) {
+          bf8_to_float<ADD_H>(ain[k], g);
+          if constexpr (ADD_PAIR) {
             float h[8];
-            bf8_to_float(alo[k], h);
+            bf8_to_float<false>(alo[k], h);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[j] += h[j];
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
-        const BF8 o = float_to_bf8(f);
+        const BF8 o = float_to_bf8<H>(f);
         out[vv[k]] = o;
         float r[8];
-        bf8_to_float(o, r);
+        bf8_to_float<H>(o, r);
         if constexpr (PREC) {
           float d[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) d[j] = f[j] - r[j];
-          const BF8 ol = float_to_bf8(d);
+          const BF8 ol = float_to_bf8<false>(d);
           out_lo[vv[k]] = ol;
           float rl[8];
-          bf8_to_float(ol, rl);
+          bf8_to_float<false>(ol, rl);
 #pragma unroll
           for (int j = 0; j < 8; ++j) r[j] += rl[j];
         }
@@ -444,7 +498,7 @@ __global__ void __launch_bounds__(NORM_THREADS, PREC ? 2 : 3) norm_act_pool_kern
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], 1));
     if (valid && !(x & 1))
-      store_split(a.pooled, PREC ? a.pooled_lo : nullptr, plane * pvox + ((long long)z2 * H2 + y2) * W2 + (x >> 1), m);
+      store_split<H>(a.pooled, PREC ? a.pooled_lo : nullptr, plane * pvox + ((long long)z2 * H2 + y2) * W2 + (x >> 1), m);
   }
 }
 
@@ -452,6 +506,7 @@ __global__ void __launch_bounds__(NORM_THREADS, PREC ? 2 : 3) norm_act_pool_kern
 // ConvTranspose3d k=2 s=2 + bias (MONAI UpSample "deconv", denoiser.py:161-170,181).  CUDA-core version:
 // thread = (input voxel, tap, 8 output channels).  weights packed [tap][cin][cout] bf16.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool HF>
 __global__ void __launch_bounds__(256) deconv2_kernel(const __nv_bfloat16* __restrict__ in, int cin,
                                                       const __nv_bfloat16* __restrict__ w, const float* __restrict__ b,
                                                       __nv_bfloat16* __restrict__ out, int cout, int D, int H, int W,
@@ -472,11 +527,11 @@ __global__ void __launch_bounds__(256) deconv2_kernel(const __nv_bfloat16* __res
     const BF8* wp = reinterpret_cast<const BF8*>(w) + ((long long)tap * cin) * och + oc;
     for (int ic = 0; ic < ich; ++ic) {
       float xi[8];
-      bf8_to_float(ip[(long long)ic * vox], xi);
+      bf8_to_float<HF>(ip[(long long)ic * vox], xi);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float wk[8];
-        bf8_to_float(wp[(long long)(ic * 8 + k) * och], wk);
+        bf8_to_float<HF>(wp[(long long)(ic * 8 + k) * och], wk);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(xi[k], wk[j], acc[j]);
       }
@@ -484,7 +539,7 @@ __global__ void __launch_bounds__(256) deconv2_kernel(const __nv_bfloat16* __res
     const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((long long)W * H));
     const int dz = tap >> 2, dy = (tap >> 1) & 1, dx = tap & 1;
     const long long ov = ((long long)(2 * z + dz) * (2 * H) + (2 * y + dy)) * (2 * W) + (2 * x + dx);
-    reinterpret_cast<BF8*>(out)[((long long)n * och + oc) * (vox * 8) + ov] = float_to_bf8(acc);
+    reinterpret_cast<BF8*>(out)[((long long)n * och + oc) * (vox * 8) + ov] = float_to_bf8<HF>(acc);
   }
 }
 
@@ -530,19 +585,22 @@ constexpr int FINAL_MAX_C = 32;
 constexpr int FINAL_MAX_F = 128;
 constexpr int FINAL_THREADS = 256;
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+template <bool H>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (H)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // NT = number of 8-class column tiles (C <= 8 * NT); NKS = F / 16 k-steps
-template <int NT, int NKS, bool PREC>
+template <int NT, int NKS, int MODE>
 __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs a) {
+  constexpr bool PREC = MODE == MODE_FP32X3, H = MODE == MODE_FP16;
   // B fragments of the weights: [k-step][n-tile][hi|lo][b0|b1][lane]
   __shared__ uint32_t wfrag[(FINAL_MAX_F / 16) * NT * 2 * 2 * 32];
   __shared__ float sbias[NT * 8];
@@ -564,14 +622,14 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
     float hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      hi[j] = __bfloat162float(__float2bfloat16_rn(wv[j]));
+      hi[j] = round_16<H>(wv[j]);
       lo[j] = wv[j] - hi[j];
     }
     uint32_t* dst = wfrag + ((ks * NT + nt) * 4) * 32 + l;
-    dst[0] = pack_bf16x2(hi[0], hi[1]);
-    dst[32] = pack_bf16x2(hi[2], hi[3]);
-    dst[64] = pack_bf16x2(lo[0], lo[1]);
-    dst[96] = pack_bf16x2(lo[2], lo[3]);
+    dst[0] = pack_16x2<H>(hi[0], hi[1]);
+    dst[32] = pack_16x2<H>(hi[2], hi[3]);
+    dst[64] = pack_16x2<H>(lo[0], lo[1]);
+    dst[96] = pack_16x2<H>(lo[2], lo[3]);
   }
   for (int i = threadIdx.x; i < NT * 8; i += FINAL_THREADS) sbias[i] = i < a.C ? a.b[i] : 0.f;
   pdl_wait();  // the weight fragments above are plan constants; everything below depends on the previous kernels
@@ -653,28 +711,28 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = ks * 16 + (j >> 1) * 8 + 2 * t;
-          float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&af[ks][j]));
+          float2 x = unpack_16x2<H>(af[ks][j]);
           if constexpr (PREC) {
-            const float2 xl = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&al[ks][j]));
+            const float2 xl = unpack_16x2<false>(al[ks][j]);
             x.x += xl.x; x.y += xl.y;
           }
           const float2 sc2 = *reinterpret_cast<const float2*>(nsc + c), sh2 = *reinterpret_cast<const float2*>(nsh + c);
           float y0 = fmaf(x.x, sc2.x, sh2.x), y1 = fmaf(x.y, sc2.y, sh2.y);
           y0 = fmaxf(y0, y0 * a.slope);  // LeakyReLU with 0 < slope < 1
           y1 = fmaxf(y1, y1 * a.slope);
-          af[ks][j] = pack_bf16x2(y0, y1);
+          af[ks][j] = pack_16x2<H>(y0, y1);
           if constexpr (PREC) {
-            const float2 h = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&af[ks][j]));
-            al[ks][j] = pack_bf16x2(y0 - h.x, y1 - h.y);
+            const float2 h = unpack_16x2<false>(af[ks][j]);
+            al[ks][j] = pack_16x2<false>(y0 - h.x, y1 - h.y);
           }
         }
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const uint32_t* wf = wfrag + ((ks * NT + nt) * 4) * 32 + lane;
-        mma_bf16_16816(d[nt], af[ks], wf[0], wf[32]);
-        mma_bf16_16816(d[nt], af[ks], wf[64], wf[96]);
-        if constexpr (PREC) mma_bf16_16816(d[nt], al[ks], wf[0], wf[32]);
+        mma_16816<H>(d[nt], af[ks], wf[0], wf[32]);
+        mma_16816<H>(d[nt], af[ks], wf[64], wf[96]);
+        if constexpr (PREC) mma_16816<false>(d[nt], al[ks], wf[0], wf[32]);
       }
     }
     // d[nt][0..1]: voxel v0, classes nt*8 + 2t, +1 ; d[nt][2..3]: voxel v1, same classes
@@ -709,14 +767,13 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
         if (ok1) { xt_n[v1 * (NT * 4) + nt * 4] = make_float2(xp4[2], xp4[3]); acc_n[v1 * (NT * 4) + nt * 4] = make_float2(ac4[2], ac4[3]); }
       }
       if (np_n && nt * 8 < a.in_pad) {
-        const uint32_t h0 = pack_bf16x2(nxt[0], nxt[1]), h1 = pack_bf16x2(nxt[2], nxt[3]);
+        const uint32_t h0 = pack_16x2<H>(nxt[0], nxt[1]), h1 = pack_16x2<H>(nxt[2], nxt[3]);
         if (ok0) np_n[(nt * vox + v0) * 4] = h0;
         if (ok1) np_n[(nt * vox + v1) * 4] = h1;
         if constexpr (PREC) {
-          const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h0));
-          const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h1));
-          if (ok0) np_lo_n[(nt * vox + v0) * 4] = pack_bf16x2(nxt[0] - f0.x, nxt[1] - f0.y);
-          if (ok1) np_lo_n[(nt * vox + v1) * 4] = pack_bf16x2(nxt[2] - f1.x, nxt[3] - f1.y);
+          const float2 f0 = unpack_16x2<false>(h0), f1 = unpack_16x2<false>(h1);
+          if (ok0) np_lo_n[(nt * vox + v0) * 4] = pack_16x2<false>(nxt[0] - f0.x, nxt[1] - f0.y);
+          if (ok1) np_lo_n[(nt * vox + v1) * 4] = pack_16x2<false>(nxt[2] - f1.x, nxt[3] - f1.y);
         }
       }
     }
@@ -764,6 +821,193 @@ __global__ void state_from_vm_kernel(const float* __restrict__ src, float* __res
         *o = accumulate ? fmaf(scale, f[j], *o) : scale * f[j];
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Start of a DDIM window (gaussian_diffusion.py:690-693 `img = noise or th.randn(shape)`): ONE pass that writes
+//   x_t  = the initial noise, voxel-major fp32 [B][vox][CP]      (state read/written by final_ddim_kernel)
+//   acc  = 0 (same layout; skipped when `zero_acc == 0`: ensemble draws keep accumulating)
+//   next = the packed 16-bit input of the first denoiser conv [x_0 .. x_{C-1}, image, 0 ..] (C8-planar, in_pad channels)
+// The noise is either the caller's tensor (planar fp32 [B][C][vox], parity runs) or generated here: Philox4x32-10 keyed by
+// `seed`, counter = (element index / 4, window id), Box-Muller -> N(0,1).  Counter-based: a window's noise depends only
+// on (seed, window id), not on batching, rank or launch order (multi-GPU runs give identical volumes).
+// thread = (sample, voxel, 8-channel chunk).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// two uniform 32-bit words -> two independent standard normals (Box-Muller; u1 in (0, 1])
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  z0 = r * cs;
+  z1 = r * sn;
+}
+constexpr int INIT_MAX_B = 16;
+struct DdimInitArgs {
+  const float* noise;      // [B][C][vox] or nullptr (generate)
+  const float* image;      // [B][1][vox]
+  float* x_t;              // [B][vox][CP]
+  float* acc;              // [B][vox][CP]
+  __nv_bfloat16* next_in;  // [B][in_pad/8][vox][8]
+  __nv_bfloat16* next_in_lo;  // fp32x3 mode or nullptr
+  int C, CP, in_pad, batch, zero_acc;
+  long long vox;
+  unsigned long long seed;
+  long long ids[INIT_MAX_B];  // noise stream id of each window of the batch
+};
+template <bool H>
+__global__ void __launch_bounds__(256) ddim_init_kernel(DdimInitArgs a) {
+  pdl_wait();
+  const int nch = (a.CP > a.in_pad ? a.CP : a.in_pad) / 8;
+  const long long total = (long long)a.batch * a.vox * nch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ck = (int)(i % nch);
+    const long long v = (i / nch) % a.vox;
+    const int n = (int)(i / (nch * a.vox));
+    float f[8];
+    if (a.noise) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = ck * 8 + j;
+        f[j] = c < a.C ? a.noise[((long long)n * a.C + c) * a.vox + v] : 0.f;
+      }
+    } else {
+      const unsigned long long e = (unsigned long long)v * (unsigned)(a.CP / 4) + (unsigned)(ck * 2);  // 4-element group index
+      const unsigned long long id = (unsigned long long)a.ids[n];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t c4[4] = {(uint32_t)(e + h), (uint32_t)((e + h) >> 32), (uint32_t)id, (uint32_t)(id >> 32)};
+        philox4x32_10(c4, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        box_muller(c4[0], c4[1], f[4 * h + 0], f[4 * h + 1]);
+        box_muller(c4[2], c4[3], f[4 * h + 2], f[4 * h + 3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (ck * 8 + j >= a.C) f[j] = 0.f;
+    }
+    if (ck * 8 < a.CP) {
+      float4* xs = reinterpret_cast<float4*>(a.x_t + ((long long)n * a.vox + v) * a.CP + ck * 8);
+      xs[0] = make_float4(f[0], f[1], f[2], f[3]);
+      xs[1] = make_float4(f[4], f[5], f[6], f[7]);
+      if (a.zero_acc) {
+        float4* as = reinterpret_cast<float4*>(a.acc + ((long long)n * a.vox + v) * a.CP + ck * 8);
+        as[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        as[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (ck * 8 < a.in_pad) {
+      if (a.C >= ck * 8 && a.C < ck * 8 + 8) f[a.C - ck * 8] = a.image[(long long)n * a.vox + v];  // packed order [x.., image, 0..]
+      store_split<H>(a.next_in, a.next_in_lo, ((long long)n * (a.in_pad / 8) + ck) * a.vox + v, f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// q(x_t | x_0) of the training forward (GaussianDiffusion.q_sample, gaussian_diffusion.py:187-205, called from
+// Diffusion.q_sample, models/diffusion/diffusion.py:65-69):
+//   x_t = sqrt_alphas_cumprod[t_n] * x_0 + sqrt_one_minus_alphas_cumprod[t_n] * noise       (per sample n)
+// fp32, multiplies and add kept separate (no FMA contraction) so the result is bit-identical to the torch expression.
+// noise_in == nullptr: the noise is drawn here (same Philox stream as ddim_init_kernel, id = id0 + n) and written to
+// noise_out (the reference returns it: `return sample, t, noise`).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise_in,
+                                                       float* __restrict__ noise_out, const long long* __restrict__ t,
+                                                       const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac,
+                                                       float* __restrict__ out, long long per_sample, int batch,
+                                                       unsigned long long seed, long long id0) {
+  const long long groups = (per_sample + 3) / 4;
+  const long long total = groups * batch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / groups);
+    const long long g = i % groups;
+    const float a = sqrt_ac[t[n]], b = sqrt_1mac[t[n]];
+    float z[4];
+    if (!noise_in) {
+      const unsigned long long id = (unsigned long long)(id0 + n);
+      uint32_t c4[4] = {(uint32_t)g, (uint32_t)((unsigned long long)g >> 32), (uint32_t)id, (uint32_t)(id >> 32)};
+      philox4x32_10(c4, (uint32_t)seed, (uint32_t)(seed >> 32));
+      box_muller(c4[0], c4[1], z[0], z[1]);
+      box_muller(c4[2], c4[3], z[2], z[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long e = g * 4 + j;
+      if (e < per_sample) {
+        const long long o = (long long)n * per_sample + e;
+        const float nz = noise_in ? noise_in[o] : z[j];
+        if (noise_out) noise_out[o] = nz;
+        out[o] = __fadd_rn(__fmul_rn(a, x0[o]), __fmul_rn(b, nz));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Window crop for a whole batch in one launch (MONAI: `torch.cat([inputs[win_slice] for ...])`, engine.py:173-177 driver):
+// patches[b] = volume[start_b : start_b + roi].
+// ---------------------------------------------------------------------------------------------------------------
+struct CropArgs {
+  const float* vol;
+  float* patches;
+  int VD, VH, VW, PD, PH, PW, batch;
+  int start[INIT_MAX_B][3];
+};
+__global__ void crop_windows_kernel(CropArgs a) {
+  pdl_wait();
+  const long long pv = (long long)a.PD * a.PH * a.PW;
+  const long long total = pv * a.batch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / pv);
+    const long long r = i % pv;
+    const int x = (int)(r % a.PW), y = (int)((r / a.PW) % a.PH), z = (int)(r / ((long long)a.PW * a.PH));
+    a.patches[i] = a.vol[((long long)(a.start[b][0] + z) * a.VH + a.start[b][1] + y) * a.VW + a.start[b][2] + x];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stitching straight from the voxel-major DDIM accumulator (no planar [C][roi] intermediate):
+//   out[:, start : start + roi] += scale * acc[n]            (constant blend; scale = 1: exactly `out[slices] += pred`)
+//   out += w * (scale * acc[n]); count += w                  (gaussian blend, `weights` != nullptr)
+// One launch per window, in MONAI's window order: fp32 sums are formed in the oracle's order, no atomics.
+// thread = one window voxel: reads its CP classes (contiguous), writes class by class (lanes run along x: coalesced).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_from_vm_kernel(float* __restrict__ vol, float* __restrict__ cnt,
+                                                             const float* __restrict__ acc_vm, const float* __restrict__ w,
+                                                             int C, int CP, int VD, int VH, int VW, int PD, int PH, int PW,
+                                                             int sz, int sy, int sx, float scale) {
+  pdl_wait();
+  const long long pv = (long long)PD * PH * PW, vv = (long long)VD * VH * VW;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < pv; v += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(v % PW), y = (int)((v / PW) % PH), z = (int)(v / ((long long)PW * PH));
+    const long long o = ((long long)(sz + z) * VH + sy + y) * VW + sx + x;
+    const float4* src = reinterpret_cast<const float4*>(acc_vm + v * CP);
+    const float wv = w ? w[v] : 1.f;
+    for (int q = 0; q < CP / 4; ++q) {
+      const float4 f4 = src[q];
+      const float f[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = q * 4 + j;
+        if (c < C) {
+          const float pred = scale == 1.f ? f[j] : __fmul_rn(scale, f[j]);
+          float* dst = vol + c * vv + o;
+          *dst = w ? __fadd_rn(*dst, __fmul_rn(wv, pred)) : __fadd_rn(*dst, pred);
+        }
+      }
+    }
+    if (w) cnt[o] = __fadd_rn(cnt[o], wv);
   }
 }
 

@@ -179,11 +179,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10),
-// both operands K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format at [7,10) / [10,13) with
+// F16 = 0, BF16 = 1 (kind::f16 runs both at the same rate), both operands K-major (bits 15,16 = 0), N>>3 at [17,23),
+// M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc_16(int m, int n, bool fp16) {
+  return (1u << 4) | (fp16 ? 0u : ((1u << 7) | (1u << 10))) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) { return make_idesc_16(m, n, false); }
 
 }  // namespace dunet

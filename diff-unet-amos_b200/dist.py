@@ -1,14 +1,29 @@
-"""Multi-GPU sliding-window inference: one process per GPU, windows sharded contiguously, ONE collective.
+"""Multi-GPU sliding-window inference: one process per GPU, windows sharded contiguously, ONE exchange per volume.
 
 The reference runs inference on a single GPU (engine.py:172-177); its only distributed idiom on the evaluation side is a
 contiguous per-rank shard followed by a gather (light_training/sampler.py:5-48).  Windows are independent units, so the
-same idea applies: rank r processes windows [lo, hi) of MONAI's window order into its own partial fp32 sum volume, the
-partial volumes are summed onto rank 0 (NCCL reduce over NVLink: the "gather of the stitched logits"), and rank 0
-divides by the analytically known coverage counts.  No collective touches the per-window data path.
+same idea applies.  Rank r processes a contiguous range of MONAI's window order into its own partial fp32 sum volume;
+then the partial volumes are exchanged ONCE per volume:
+
+  * ``ncclReduceScatter`` by channel (rank r keeps the summed logits of C/N channels),
+  * every rank divides its channels by the analytic coverage counts and binarises them (finalize kernel),
+  * the uint8 labels (4x smaller than the logits) are gathered on rank 0.
+
+(``ncclReduce`` of the whole volume to rank 0 when C is not divisible by N.)  No collective touches the per-window data
+path.  Two schedules:
+
+  * latency mode   (``infer_volume_distributed``): the windows of ONE volume are split over all ranks.  With 98 windows
+    on 8 ranks somebody owns ceil(98 / 8) = 13: scaling ceiling 98 / (8 * 13) = 0.942.
+  * throughput mode (``infer_volumes_distributed``): G consecutive volumes form one window queue, G the smallest count
+    with G * n_windows divisible by the world size (98 windows, 8 ranks: G = 4, 49 windows per rank), so every rank does
+    exactly the same work between two exchange points.  The exchanges of a group run back to back once all its windows
+    are done (never concurrently with the convolutions: a spinning NCCL kernel would take SMs away from the persistent
+    one-CTA-per-SM conv kernels).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -16,18 +31,44 @@ import torch.distributed as dist
 from .windows import shard_range, window_starts
 
 
+def _world() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def _rank() -> int:
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
 def my_window_range(n_windows: int, rank: Optional[int] = None, world: Optional[int] = None) -> Tuple[int, int]:
     if world is None:
-        world = dist.get_world_size() if dist.is_initialized() else 1
+        world = _world()
     if rank is None:
-        rank = dist.get_rank() if dist.is_initialized() else 0
+        rank = _rank()
     return shard_range(n_windows, rank, world)
+
+
+def queue_group_size(n_windows: int, world: int, cap: int = 8) -> int:
+    """Smallest number of volumes G (<= cap) whose combined window queue splits evenly over ``world`` ranks."""
+    g = world // math.gcd(n_windows, world)
+    return g if g <= cap else 1
+
+
+def queue_shares(n_windows: int, group: int, rank: int, world: int) -> List[Tuple[int, int, int]]:
+    """Rank ``rank``'s share of the window queue of ``group`` consecutive volumes: a list of (volume index in the group,
+    first window, one past the last window), contiguous in the concatenated MONAI order."""
+    lo, hi = shard_range(n_windows * group, rank, world)
+    out = []
+    for v in range(group):
+        a, b = max(lo, v * n_windows), min(hi, (v + 1) * n_windows)
+        if a < b:
+            out.append((v, a - v * n_windows, b - v * n_windows))
+    return out
 
 
 def reduce_partial_volume(partial: torch.Tensor, dst: int = 0) -> torch.Tensor:
     """Sum the per-rank partial stitched volumes onto ``dst`` (in place on ``dst``).  Works with NCCL (CUDA tensors) and
     gloo (CPU tensors, used by the CPU tests)."""
-    if dist.is_initialized() and dist.get_world_size() > 1:
+    if _world() > 1:
         dist.reduce(partial, dst=dst, op=dist.ReduceOp.SUM)
     return partial
 
@@ -37,7 +78,7 @@ def reduce_scatter_channels(partial: torch.Tensor) -> torch.Tensor:
     sum (C must be divisible by the world size).  NCCL: one reduce-scatter over NVLink -- every rank then divides /
     binarises its own channels, so the fp32 volume is never gathered.  gloo (CPU tests) has no reduce-scatter: all-reduce
     then slice."""
-    world = dist.get_world_size() if dist.is_initialized() else 1
+    world = _world()
     if world == 1:
         return partial
     C = partial.shape[0]
@@ -55,7 +96,7 @@ def reduce_scatter_channels(partial: torch.Tensor) -> torch.Tensor:
 
 def gather_channel_chunks(chunk: torch.Tensor, dst: int = 0):
     """Concatenate every rank's channel chunk (in rank order) on ``dst``; returns None elsewhere."""
-    world = dist.get_world_size() if dist.is_initialized() else 1
+    world = _world()
     if world == 1:
         return chunk
     chunk = chunk.contiguous()
@@ -67,49 +108,118 @@ def gather_channel_chunks(chunk: torch.Tensor, dst: int = 0):
     return None
 
 
+def exchange_and_finalize(buf, dst: int = 0, want_blended: bool = True):
+    """The one exchange of a volume: partial StitchBuffers of every rank -> (blended fp32 volume or None, uint8 binary
+    labels) on ``dst``, (None, None) elsewhere.  Constant blend with C divisible by the world size: reduce-scatter by
+    channel + local finalize + gather of the results; otherwise reduce to ``dst`` (the gaussian count volume included)."""
+    from .inference import StitchBuffers
+
+    world = _world()
+    if world > 1 and buf.channels % world == 0 and buf.mode == "constant":
+        mine = StitchBuffers.__new__(StitchBuffers)
+        mine.vol, mine.roi, mine.mode, mine.counts, mine._finalized = buf.vol, buf.roi, buf.mode, buf.counts, False
+        mine.channels = buf.channels // world
+        mine.out = reduce_scatter_channels(buf.out)
+        blended_c, binary_c, _ = mine.finalize(binary=True)
+        blended = gather_channel_chunks(blended_c, dst) if want_blended else None
+        binary = gather_channel_chunks(binary_c, dst)
+        return (blended, binary) if _rank() == dst else (None, None)
+    reduce_partial_volume(buf.out, dst)
+    if buf.mode == "gaussian":
+        reduce_partial_volume(buf.count_vol, dst)
+    if _rank() == dst:
+        blended, binary, _ = buf.finalize(binary=True)
+        return (blended if want_blended else None), binary
+    return None, None
+
+
 @torch.no_grad()
 def infer_volume_distributed(model, image: torch.Tensor, sw_batch_size: int = 4, overlap: float = 0.25,
-                             noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None, dst: int = 0):
-    """Engine.infer (engine.py:167-182) with the window list sharded over the process group.
+                             noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None, dst: int = 0,
+                             seed: Optional[int] = 0, mode: str = "constant"):
+    """Engine.infer (engine.py:167-182) with the window list of every volume sharded over the process group (latency mode).
 
     Every rank holds the full input volume and the same weights.  Returns (blended volume, binary labels) on ``dst``
-    and (None, None) elsewhere.  ``noise_fn(first_window_index, count)`` supplies explicit noise (parity runs)."""
-    from .inference import sliding_window_inference
+    and (None, None) elsewhere, cropped back to the input shape like the single-GPU driver.  ``noise_fn(first_window_index,
+    count)`` supplies explicit noise (parity runs), window indices numbered ``n * n_windows + w`` like ``infer_volume``;
+    otherwise window w draws from the library's counter-based stream (``seed``, w): the result does not depend on the
+    number of ranks."""
+    from .inference import crop_to, sliding_window_inference
 
     roi = model.patch
     vol = tuple(max(int(i), int(r)) for i, r in zip(image.shape[2:], roi))
     n_win = len(window_starts(vol, roi, overlap))
     lo, hi = my_window_range(n_win)
-    cursor = {"w": lo}
-
-    def predictor(batch, pred_type=None):
-        nz = noise_fn(cursor["w"], batch.shape[0]) if noise_fn is not None else None
-        cursor["w"] += batch.shape[0]
-        return model(image=batch, pred_type=pred_type, noise=nz)
-
-    bufs = sliding_window_inference(image, roi, sw_batch_size, predictor, overlap, window_range=(lo, hi), finalize=False,
-                                    out_channels=model.num_classes, pred_type="ddim_sample")
-    world = dist.get_world_size() if dist.is_initialized() else 1
+    bufs = sliding_window_inference(image, roi, sw_batch_size, model, overlap, mode=mode, window_range=(lo, hi), finalize=False,
+                                    out_channels=model.num_classes, noise_fn=noise_fn, seed=seed, pred_type="ddim_sample")
     outs = []
     for b in bufs:
-        if world > 1 and b.channels % world == 0 and b.mode == "constant":
-            # reduce-scatter by channel, finalize locally (the count map does not depend on the channel), gather results
-            from .inference import StitchBuffers
-
-            mine = StitchBuffers.__new__(StitchBuffers)
-            mine.vol, mine.roi, mine.mode, mine.counts = b.vol, b.roi, b.mode, b.counts
-            mine.channels = b.channels // world
-            mine.out = reduce_scatter_channels(b.out)
-            blended_c, binary_c, _ = mine.finalize(binary=True)
-            blended, binary = gather_channel_chunks(blended_c, dst), gather_channel_chunks(binary_c, dst)
-            if dist.get_rank() == dst:
-                outs.append((blended, binary))
-        else:
-            reduce_partial_volume(b.out, dst)
-            if not dist.is_initialized() or dist.get_rank() == dst:
-                outs.append(b.finalize(binary=True)[:2])
-    if dist.is_initialized() and dist.get_rank() != dst:
+        blended, binary = exchange_and_finalize(b, dst)
+        if _rank() == dst:
+            outs.append((crop_to(blended, image.shape[2:], b.vol), crop_to(binary, image.shape[2:], b.vol)))
+    if _rank() != dst:
         return None, None
     blended = torch.stack([o[0] for o in outs])
     labels = torch.stack([o[1] for o in outs]).float()
     return blended, labels
+
+
+@torch.no_grad()
+def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_size: int = 4, overlap: float = 0.25, dst: int = 0,
+                              seed: int = 0, on_result: Optional[Callable[[int, torch.Tensor], None]] = None,
+                              noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None):
+    """Throughput mode: ``images`` (a sequence of [1, 1, D, H, W] volumes of ONE shape, already >= the roi on every axis,
+    present on every rank) are processed as window queues of G volumes (``queue_group_size``) so that every rank does the
+    same number of windows between two exchange points.  ``on_result(volume_index, binary_labels_uint8)`` is called on
+    ``dst`` as results become available (e.g. to start the D2H copy); returns the list of label volumes on ``dst``.
+    Window w of volume i draws its noise from the stream (``seed``, i * n_windows + w): identical to running the volumes
+    one by one through ``infer_volume_distributed`` / ``infer_volume`` with the same seed."""
+    from .inference import StitchBuffers
+
+    world, rank = _world(), _rank()
+    roi = model.patch
+    if not images:
+        return []
+    vol = tuple(images[0].shape[2:])
+    if any(v < r for v, r in zip(vol, roi)):
+        raise ValueError("throughput mode needs volumes that are at least the window size on every axis")
+    starts = window_starts(vol, roi, overlap)
+    n_win = len(starts)
+    G = queue_group_size(n_win, world)
+    step = min(int(sw_batch_size), model.batch_max)
+    results = []
+    dev = images[0].device
+    for g0 in range(0, len(images), G):
+        grp = list(range(g0, min(g0 + G, len(images))))
+        shares = queue_shares(n_win, len(grp), rank, world)
+        bufs = {}
+        for v, lo, hi in shares:
+            img = images[grp[v]]
+            if tuple(img.shape[2:]) != vol:
+                raise ValueError("all volumes of a queue must have the same shape")
+            buf = bufs[v] = StitchBuffers(model.num_classes, vol, roi, overlap, dev)
+            bounds = list(range(lo, hi, step)) + [hi]
+            if len(bounds) > 2 and bounds[-1] - bounds[-2] == 1 and step + 1 <= model.batch_max:
+                del bounds[-2]  # a single left-over window joins the previous batch instead of running alone
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                base = grp[v] * n_win
+                if noise_fn is not None:
+                    buf.add_windows(model, img[0, 0], starts[a:b], noise=noise_fn(base + a, b - a))
+                else:
+                    buf.add_windows(model, img[0, 0], starts[a:b], seed=seed, noise_ids=range(base + a, base + b))
+        zero = None
+        for v in range(len(grp)):  # the exchanges of the group, back to back, every rank takes part in every one
+            buf = bufs.get(v)
+            if buf is None:
+                if zero is None:
+                    zero = StitchBuffers(model.num_classes, vol, roi, overlap, dev)
+                else:
+                    zero.out.zero_()
+                    zero._finalized = False
+                buf = zero
+            _, binary = exchange_and_finalize(buf, dst, want_blended=False)
+            if rank == dst:
+                if on_result is not None:
+                    on_result(grp[v], binary)
+                results.append(binary)
+    return results if rank == dst else None

@@ -9,8 +9,9 @@ Mirrors the evaluation seams of the reference:
   * ``test(batches)``                  -> test.py:101-110
 
 The window driver, stitching, binarisation and the Dice reductions run in CUDA kernels through the C ABI; this file is
-host sequencing only.  ``use_amp`` is accepted for signature compatibility: the kernels' precision is chosen by the
-model's ``precision`` ("bf16" | "fp32x3"), there is no autocast.
+host sequencing only.  ``use_amp`` maps the reference's autocast switch (test.py:104,119: fp16 autocast when the config
+sets ``use_amp``, plain fp32 otherwise) onto the kernels' arithmetic mode: True -> "fp16" operands, False -> "fp32x3"
+(fp32-class split operands), None (default) -> keep the model's own ``precision``.
 """
 from __future__ import annotations
 
@@ -23,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .inference import StitchBuffers, sliding_window_inference
+from .inference import StitchBuffers, crop_to, sliding_window_inference
 
 
 def _ptr(t):
@@ -74,7 +75,9 @@ def dice_from_counts(counts: Sequence[Sequence[int]]) -> list:
 
 class EngineB200:
     def __init__(self, model, class_names: Optional[Dict[int, str]] = None, sw_batch_size: int = 4, overlap: float = 0.25,
-                 include_background: bool = True, use_amp: bool = False, device="cuda", epoch: Optional[int] = None):
+                 include_background: bool = True, use_amp: Optional[bool] = None, device="cuda", epoch: Optional[int] = None):
+        if use_amp is not None:
+            model.set_precision("fp16" if use_amp else "fp32x3")
         self.model = model.to(device).eval()
         self.device = torch.device(device)
         self.num_classes = model.num_classes
@@ -113,31 +116,18 @@ class EngineB200:
 
     def _infer_binary(self, image: torch.Tensor, noise_fn=None) -> torch.Tensor:
         """[N, C, D, H, W] uint8: ``(sigmoid(sliding_window(...)) > 0.5)`` formed by the finalize kernel."""
-        roi = (self.spatial_size, self.image_size, self.image_size)
-        cursor = {"w": 0}
-
-        def predictor(b, pred_type=None):
-            nz = noise_fn(cursor["w"], b.shape[0]) if noise_fn is not None else None
-            cursor["w"] += b.shape[0]
-            return self.model(image=b, pred_type=pred_type, noise=nz)
-
-        bufs = sliding_window_inference(image, roi, self.sw_batch_size, predictor, self.overlap, finalize=False,
-                                        pred_type="ddim_sample")
+        roi = tuple(self.model.patch)
+        # the reference's call, engine.py:173-177: sliding_window_inference(image, roi, sw_batch_size, self.model, overlap,
+        # pred_type="ddim_sample") -- the driver recognises the model and runs the fused window loop
+        bufs = sliding_window_inference(image, roi, self.sw_batch_size, self.model, self.overlap, finalize=False,
+                                        noise_fn=noise_fn, pred_type="ddim_sample")
         outs = []
         for b in bufs:
             _, binary, _ = b.finalize(binary=True)
-            outs.append(self._crop_to(binary, image.shape[2:], b.vol))
+            outs.append(crop_to(binary, image.shape[2:], b.vol))
         return torch.stack(outs)
 
-    @staticmethod
-    def _crop_to(t: torch.Tensor, orig, vol) -> torch.Tensor:
-        if tuple(orig) == tuple(vol):
-            return t
-        sl = [slice(None)]
-        for o, v in zip(orig, vol):  # the driver pads symmetrically (floor on the low side) up to the roi
-            lo = (v - o) // 2
-            sl.append(slice(lo, lo + o))
-        return t[tuple(sl)].contiguous()
+    _crop_to = staticmethod(crop_to)
 
     # ---- test.py:112-160
     @torch.no_grad()

@@ -37,6 +37,7 @@ class StitchBuffers:
         self.channels = channels
         self.mode = mode
         self.out = torch.zeros((channels,) + self.vol, dtype=torch.float32, device=device)
+        self._finalized = False
         if mode == "constant":
             self.counts = [torch.from_numpy(c).to(device) for c in axis_counts(self.vol, self.roi, overlap)]
         elif mode == "gaussian":
@@ -55,7 +56,17 @@ class StitchBuffers:
                                                      _ptr(patch), _ptr(self.weights), _lib.i32x3(self.roi), _lib.i32x3(start),
                                                      _stream()))
 
+    def add_windows(self, model, volume: torch.Tensor, starts, **kw) -> None:
+        """Fused crop + encoder + DDIM + ``out[slices] += pred`` for a batch of windows (model.infer_windows)."""
+        if self.mode == "constant":
+            model.infer_windows(volume, starts, self.out, **kw)
+        else:
+            model.infer_windows(volume, starts, self.out, count_volume=self.count_vol, weights=self.weights, **kw)
+
     def finalize(self, binary: bool = False, argmax: bool = False):
+        if self._finalized:
+            raise RuntimeError("StitchBuffers.finalize() was already called: the volume has been divided by the counts")
+        self._finalized = True
         b = torch.empty((self.channels,) + self.vol, dtype=torch.uint8, device=self.out.device) if binary else None
         a = torch.empty(self.vol, dtype=torch.uint8, device=self.out.device) if argmax else None
         lib = _lib.load()
@@ -93,21 +104,29 @@ def _pad_to_roi(inputs: torch.Tensor, roi) -> Tuple[torch.Tensor, list]:
 
 
 def crop_windows(volume: torch.Tensor, starts, roi) -> torch.Tensor:
-    """volume [1, D, H, W] fp32 -> [len(starts), 1, *roi] via the crop kernel."""
+    """volume [1, D, H, W] fp32 -> [len(starts), 1, *roi]: one launch of the batched crop kernel."""
     lib = _lib.load()
     vol = tuple(volume.shape[-3:])
-    out = torch.empty((len(starts), 1) + tuple(roi), dtype=torch.float32, device=volume.device)
-    for j, s in enumerate(starts):
-        _lib.check(lib.dunet_crop_window(_ptr(volume), _lib.i32x3(vol), _ptr(out[j]), _lib.i32x3(roi), _lib.i32x3(s), _stream()))
+    b = len(starts)
+    out = torch.empty((b, 1) + tuple(roi), dtype=torch.float32, device=volume.device)
+    st = (ctypes.c_int32 * (3 * b))(*[int(x) for s3 in starts for x in s3])
+    _lib.check(lib.dunet_crop_windows(_ptr(volume), _lib.i32x3(vol), _ptr(out), _lib.i32x3(roi), st, b, _stream()))
     return out
 
 
 def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int, predictor: Callable[..., torch.Tensor],
                              overlap: float = 0.25, mode: str = "constant", sigma_scale: float = 0.125,
                              window_range: Optional[Tuple[int, int]] = None, finalize: bool = True,
-                             out_channels: Optional[int] = None, **kwargs):
+                             out_channels: Optional[int] = None, noise_fn=None, seed: Optional[int] = None, ensemble: int = 1,
+                             **kwargs):
     """Sliding window on the GPU, ``mode`` "constant" (what the reference uses) or "gaussian" (MONAI's other blend).
     ``predictor(window_batch, **kwargs)`` -> [b, C, *roi].
+
+    When ``predictor`` is a DiffUNetB200 and the call is the reference's (``pred_type="ddim_sample"``, engine.py:173-177)
+    the loop body runs fused in the library (crop + encoder + DDIM + ``out[slices] += pred``, no planar intermediates);
+    results are bit-identical to the generic loop.  ``noise_fn(first_window_index, count)`` supplies explicit initial
+    noise (parity runs); otherwise the noise of window w is the library's counter-based stream (seed, w) -- ``seed``
+    defaults to a draw from torch's global generator, so ``torch.manual_seed`` makes runs repeatable.
 
     ``window_range=(lo, hi)`` restricts the run to a contiguous shard of the window list (multi-GPU); with
     ``finalize=False`` the un-normalised StitchBuffers is returned instead of the blended volume.
@@ -128,9 +147,30 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
     n_win = len(starts)
     lo, hi = (0, n_win) if window_range is None else window_range
     outs = []
+    from .model import DiffUNetB200
+
+    fused = isinstance(predictor, DiffUNetB200) and kwargs.get("pred_type") == "ddim_sample" and tuple(predictor.patch) == roi
+    if fused and seed is None and noise_fn is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     with torch.cuda.device(inputs.device):
         for n in range(inputs.shape[0]):
             buf = None
+            if fused:
+                model = predictor
+                step = min(int(sw_batch_size), model.batch_max)
+                buf = StitchBuffers(model.num_classes, vol, roi, overlap, inputs.device, mode, sigma_scale)
+                vol_n = inputs[n, 0]
+                if vol_n.data_ptr() % 16:
+                    vol_n = vol_n.clone()
+                for g in range(lo, hi, step):
+                    g1 = min(g + step, hi)
+                    if noise_fn is not None:
+                        buf.add_windows(model, vol_n, starts[g:g1], noise=noise_fn(n * n_win + g, g1 - g), ensemble=ensemble)
+                    else:
+                        buf.add_windows(model, vol_n, starts[g:g1], seed=seed, noise_ids=range(n * n_win + g, n * n_win + g1),
+                                        ensemble=ensemble)
+                outs.append(buf)
+                continue
             for g in range(lo, hi, sw_batch_size):
                 grp = starts[g:min(g + sw_batch_size, hi)]
                 batch = crop_windows(inputs[n], grp, roi)
@@ -159,19 +199,27 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size, sw_batch_size: int,
 
 
 @torch.no_grad()
-def infer_volume(model, image: torch.Tensor, sw_batch_size: int = 4, overlap: float = 0.25, noise_fn=None):
+def infer_volume(model, image: torch.Tensor, sw_batch_size: int = 4, overlap: float = 0.25, noise_fn=None, seed: Optional[int] = None,
+                 ensemble: int = 1, mode: str = "constant"):
     """``Engine.infer`` for a diffusion model (engine.py:167-182): window driver with pred_type="ddim_sample", then
-    ``(sigmoid(out) > 0.5).float()``.  Returns (blended fp32 volume, binary labels as float)."""
-    roi = model.patch
-    counter = {"w": 0}
+    ``(sigmoid(out) > 0.5).float()`` -- formed by the finalize kernel together with the division by the counts.
+    Returns (blended fp32 volume [N, C, D, H, W], binary labels as float)."""
+    bufs = sliding_window_inference(image, model.patch, sw_batch_size, model, overlap, mode=mode, finalize=False, noise_fn=noise_fn,
+                                    seed=seed, ensemble=ensemble, pred_type="ddim_sample")
+    outs, labs = [], []
+    for b in bufs:
+        blended, binary, _ = b.finalize(binary=True)
+        outs.append(crop_to(blended, image.shape[2:], b.vol))
+        labs.append(crop_to(binary, image.shape[2:], b.vol))
+    return torch.stack(outs), torch.stack(labs).float()
 
-    def predictor(batch, pred_type=None):
-        nz = None
-        if noise_fn is not None:
-            nz = noise_fn(counter["w"], batch.shape[0])
-        counter["w"] += batch.shape[0]
-        return model(image=batch, pred_type=pred_type, noise=nz)
 
-    out = sliding_window_inference(image, roi, sw_batch_size, predictor, overlap, pred_type="ddim_sample")
-    labels = (torch.sigmoid(out) > 0.5).float()
-    return out, labels
+def crop_to(t: torch.Tensor, orig, vol) -> torch.Tensor:
+    """Undo the symmetric padding (floor on the low side) the driver applies to volumes smaller than the roi."""
+    if tuple(orig) == tuple(vol):
+        return t
+    sl = [slice(None)]
+    for o, v in zip(orig, vol):
+        lo = (v - o) // 2
+        sl.append(slice(lo, lo + o))
+    return t[tuple(sl)].contiguous()

@@ -29,6 +29,7 @@ from . import _lib
 from .schedule import DdimSchedule
 
 DEFAULT_FEATURES = (64, 64, 128, 256, 512, 64)
+PRECISIONS = ("fp16", "bf16", "fp32x3")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -116,21 +117,43 @@ class _UniformSampler:
 
 
 class _TrainDiffusion:
-    """The 1000-step process used by ``q_sample`` (models/diffusion/diffusion.py:31-36,65-69).  Training-side glue,
-    outside the inference hot path; kept so the ``pred_type="q_sample"`` seam exists."""
+    """The 1000-step process used by ``q_sample`` (models/diffusion/diffusion.py:31-36,65-69): fp32-cast tables of the
+    linear schedule on the device + the CUDA ``q_sample`` kernel (gaussian_diffusion.py:187-205)."""
 
     def __init__(self, timesteps):
         betas = np.linspace(1000 / timesteps * 1e-4, 1000 / timesteps * 0.02, timesteps, dtype=np.float64)
         ac = np.cumprod(1.0 - betas)
         self.num_timesteps = timesteps
-        self.sqrt_ac = np.sqrt(ac)
-        self.sqrt_1mac = np.sqrt(1.0 - ac)
+        self.sqrt_alphas_cumprod = np.sqrt(ac)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - ac)
+        self._dev = {}
 
-    def q_sample(self, x_start, t, noise):
-        shape = (-1,) + (1,) * (x_start.dim() - 1)
-        a = torch.from_numpy(self.sqrt_ac).to(t.device)[t].float().view(shape)
-        b = torch.from_numpy(self.sqrt_1mac).to(t.device)[t].float().view(shape)
-        return a * x_start + b * noise
+    def _tables(self, device):
+        if device not in self._dev:
+            self._dev[device] = (torch.from_numpy(self.sqrt_alphas_cumprod).float().to(device),
+                                 torch.from_numpy(self.sqrt_one_minus_alphas_cumprod).float().to(device))
+        return self._dev[device]
+
+    def q_sample(self, x_start, t, noise=None, seed: int = 0, stream_id: int = 0, return_noise: bool = False):
+        x_start = _f32c(x_start, "x_start")
+        t = t.to(device=x_start.device, dtype=torch.int64).contiguous()
+        if int(t.min()) < 0 or int(t.max()) >= self.num_timesteps:
+            raise IndexError(f"timesteps must lie in [0, {self.num_timesteps})")
+        a, b = self._tables(x_start.device)
+        out = torch.empty_like(x_start)
+        nz_out = None
+        if noise is None:
+            nz_out = torch.empty_like(x_start)
+        else:
+            noise = _f32c(noise, "noise")
+            assert noise.shape == x_start.shape
+        B = x_start.shape[0]
+        with torch.cuda.device(x_start.device):
+            _lib.check(_lib.load().dunet_q_sample(_ptr(x_start), _ptr(noise), _ptr(nz_out), _ptr(t), _ptr(a), _ptr(b), _ptr(out), B,
+                                                  x_start[0].numel(), ctypes.c_uint64(seed & (2 ** 64 - 1)), int(stream_id), _stream()))
+        if return_noise:
+            return out, (noise if noise is not None else nz_out)
+        return out
 
 
 class _Runtime:
@@ -259,16 +282,19 @@ class DenoiserB200(nn.Module):
         image = _f32c(image, "image")
         o._check_image(image)
         B = x.shape[0]
-        tv = torch.as_tensor(t).reshape(-1).tolist()
-        if len(set(tv)) != 1:
-            raise NotImplementedError("per-sample timesteps in one batch are not implemented (inference uses one t)")
+        tv = [int(v) for v in torch.as_tensor(t).reshape(-1).tolist()]
+        if len(tv) == 1:
+            tv = tv * B
+        if len(tv) != B:
+            raise ValueError(f"t must hold one timestep per sample ({B}), got {len(tv)}")
         rt = o._rt
         plan = rt.ensure(x.device)
         ws = rt.workspace(B)
         o._upload_embeddings(embeddings, B, ws)
         out = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().dunet_denoise_step(plan, _ptr(x), _ptr(image), int(tv[0]), _ptr(out), B, _ptr(ws), _stream()))
+            _lib.check(_lib.load().dunet_denoise_step(plan, _ptr(x), _ptr(image), (ctypes.c_int32 * B)(*tv), _ptr(out), B, _ptr(ws),
+                                                      _stream()))
         return out
 
 
@@ -318,7 +344,7 @@ class DiffUNetB200(nn.Module):
     def __init__(self, spatial_dims: int = 3, in_channels: int = 3, out_channels: int = 1, image_size=96,
                  spatial_size=96, features: Sequence[int] = DEFAULT_FEATURES, dropout: float = 0.2,
                  timesteps: int = 1000, mode: str = "train", *, num_steps: int = 10, batch_max: int = 4,
-                 debug_flags: int = 0, precision: str = "bf16", dual_stream: bool = True):
+                 debug_flags: int = 0, precision: str = "fp16", dual_stream: bool = True):
         super().__init__()
         if spatial_dims != 3:
             raise NotImplementedError("only spatial_dims == 3")
@@ -332,12 +358,12 @@ class DiffUNetB200(nn.Module):
         # window shape (spatial_size, image_size, image_size) as Engine.infer builds it (engine.py:169)
         hw = (image_size, image_size) if isinstance(image_size, int) else tuple(image_size)
         self.patch = (int(spatial_size),) + tuple(int(v) for v in hw)
-        if precision not in ("bf16", "fp32x3"):
-            raise ValueError('precision must be "bf16" (2e-2 gate) or "fp32x3" (split-bf16 operands, 1e-4 gate; SURVEY 8d)')
-        self.precision = precision
+        if precision not in PRECISIONS:
+            raise ValueError('precision must be "fp16" (default: 11-bit mantissa operands, the reference\'s AMP precision, '
+                             'test.py:104), "bf16" (8-bit mantissa, 2e-2 gate) or "fp32x3" (split-bf16 operands, 1e-4 gate; '
+                             'SURVEY 8d)')
         self.num_steps, self.batch_max, self.debug_flags = int(num_steps), int(batch_max), int(debug_flags)
-        if precision == "fp32x3":
-            self.debug_flags |= _lib.DUNET_FLAG_FP32X3
+        self._set_precision_flags(precision)
         if dual_stream:  # batches of >= 4 windows: two half batches on two internal streams (bit-identical results)
             self.debug_flags |= _lib.DUNET_FLAG_DUAL_STREAM
         self.timesteps = timesteps
@@ -354,6 +380,26 @@ class DiffUNetB200(nn.Module):
         object.__setattr__(self, "sample_diffusion", SampleDiffusionB200(self))
         object.__setattr__(self, "diffusion", _TrainDiffusion(timesteps))
         object.__setattr__(self, "sampler", _UniformSampler(timesteps))
+
+    def _set_precision_flags(self, precision: str) -> None:
+        self.precision = precision
+        self.debug_flags &= ~(_lib.DUNET_FLAG_FP32X3 | _lib.DUNET_FLAG_FP16)
+        if precision == "fp32x3":
+            self.debug_flags |= _lib.DUNET_FLAG_FP32X3
+        elif precision == "fp16":
+            self.debug_flags |= _lib.DUNET_FLAG_FP16
+
+    def set_precision(self, precision: str) -> "DiffUNetB200":
+        """Switch the arithmetic mode of the kernels ("fp16" | "bf16" | "fp32x3"); the plan (packed weights) is rebuilt on
+        the next call.  EngineB200 maps the reference's ``use_amp`` flag onto this (test.py:104,119)."""
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        if precision != self.precision:
+            self._set_precision_flags(precision)
+            self._rt.close()
+            self._rt.weights_sig = None
+            self._rt.workspaces.clear()
+        return self
 
     # ---- checkpoint keys: "embed_model.*" / "model.*" exactly like the reference ---------------------------------
     def state_dict(self, *args, **kwargs):
@@ -419,6 +465,41 @@ class DiffUNetB200(nn.Module):
             rt.emb_token = None
         return {"acc": acc, "per_step": per, "final_x": fin}
 
+    def infer_windows(self, volume: torch.Tensor, starts, out_volume: torch.Tensor, *, noise: torch.Tensor = None,
+                      seed: int = 0, noise_ids=None, ensemble: int = 1, count_volume: torch.Tensor = None,
+                      weights: torch.Tensor = None) -> None:
+        """One iteration of the window loop of the sliding-window driver, fused (``dunet_infer_windows``): crop the windows
+        at ``starts`` ([b, 3]) out of ``volume`` ([D, H, W] fp32, padded to >= the patch), run encoder + DDIM on them and do
+        ``out_volume[:, window] += pred`` window by window.  Bit-identical to crop + forward(pred_type="ddim_sample") +
+        ``out[slices] += pred`` (engine.py:173-177, models/diffusion/diffusion.py:86-102).  ``noise`` ([b, C, *patch] or
+        [R, b, C, *patch]) fixes the initial x_T; otherwise the library draws it from (seed, noise_ids[b], draw)."""
+        if not volume.is_cuda or volume.dtype != torch.float32 or not volume.is_contiguous():
+            raise RuntimeError("volume must be a contiguous fp32 CUDA tensor: the B200 path has no CPU fallback")
+        b = len(starts)
+        if b < 1 or b > self.batch_max:
+            raise ValueError(f"{b} windows outside [1, batch_max = {self.batch_max}]")
+        vol = tuple(volume.shape[-3:])
+        if tuple(out_volume.shape) != (self.num_classes,) + vol or out_volume.dtype != torch.float32 or not out_volume.is_contiguous():
+            raise ValueError(f"out_volume must be contiguous fp32 {(self.num_classes,) + vol}")
+        rt = self._rt
+        plan = rt.ensure(volume.device)
+        ws = rt.workspace(b)
+        st = (ctypes.c_int32 * (3 * b))(*[int(x) for s3 in starts for x in s3])
+        ids = None
+        if noise is not None:
+            noise = _f32c(noise, "noise")
+            if tuple(noise.shape) not in ((b, self.num_classes) + self.patch, (ensemble, b, self.num_classes) + self.patch):
+                raise ValueError(f"noise must be [{ensemble}, {b}, {self.num_classes}, *{self.patch}], got {tuple(noise.shape)}")
+        else:
+            if noise_ids is None:
+                raise ValueError("pass noise= or noise_ids= (one counter-based noise stream id per window)")
+            ids = (ctypes.c_int64 * b)(*[int(i) for i in noise_ids])
+        with torch.cuda.device(volume.device):
+            _lib.check(_lib.load().dunet_infer_windows(plan, _ptr(volume), _lib.i32x3(vol), st, b, _ptr(noise), ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                                                       ids, int(ensemble), _ptr(out_volume), _ptr(count_volume), _ptr(weights), _ptr(ws),
+                                                       _stream()))
+        rt.emb_token = None
+
     # ---- the reference's Diffusion.forward dispatch (models/diffusion/diffusion.py:49-63) ------------------------
     def forward(self, image: torch.Tensor = None, x: torch.Tensor = None, step: torch.Tensor = None,
                 pred_type: str = None, noise: torch.Tensor = None, ensemble: int = 1):
@@ -433,9 +514,12 @@ class DiffUNetB200(nn.Module):
         raise NotImplementedError(f"No such prediction type : {pred_type}")
 
     def q_sample(self, x):
-        noise = torch.randn_like(x)
+        """models/diffusion/diffusion.py:65-69: (x_t, t, noise) with t ~ UniformSampler and noise ~ N(0, 1); the noise comes
+        from the library's counter-based generator, seeded from torch's global generator (torch.manual_seed applies)."""
         t, _ = self.sampler.sample(x.shape[0], x.device)
-        return self.diffusion.q_sample(x, t, noise), t, noise
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        sample, noise = self.diffusion.q_sample(x, t, None, seed=seed, return_noise=True)
+        return sample, t, noise
 
     def denoise(self, image, x, step):
         assert image.size(0) == x.size(0) == step.size(0)

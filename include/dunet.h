@@ -8,11 +8,15 @@
  *   - every function returns 0 on success and a negative DUNET_E_* code on failure; dunet_last_error() returns a
  *     thread-local human-readable message for the last failure on the calling thread.  Nothing throws across the ABI.
  *   - the CALLER owns every buffer (inputs, outputs, workspace).  A plan owns only packed weights, the time-embedding
- *     table and the DDIM coefficient tables.  No hidden allocation after dunet_plan_commit(), no hidden
+ *     table, the DDIM coefficient tables, two internal streams + events (DUNET_FLAG_DUAL_STREAM) and a few hundred bytes
+ *     of pinned staging for per-sample timesteps -- all created by dunet_plan_commit().  No hidden allocation after
+ *     dunet_plan_commit() (exception: with dunet_profile_enable the profiler grows its event pool), no hidden
  *     synchronisation: all work is enqueued on the caller's stream (a cudaStream_t passed as void*).
  *   - device pointers must be 16-byte aligned; the workspace pointer 256-byte aligned (checked).
  *   - boundary tensors are fp32, NCDHW, contiguous -- the reference's layout.  bf16 channels-last staging is internal.
- *   - a plan is not thread-safe (one plan per GPU / stream); distinct plans are independent.
+ *   - a plan is not thread-safe (one plan per GPU / stream); distinct plans are independent (profiler state is per
+ *     plan; per-device kernel attributes are set once per device under a mutex; the only process-global state is the
+ *     dunet_debug_set_conv_timeline hook and the launch counter).
  *   - there is NO CPU fallback: every function that computes requires a CUDA device of compute capability 10.x.
  */
 #ifndef DUNET_H_
@@ -58,6 +62,19 @@ enum {
                                        TMA-loaded halo plane in shared memory (InstanceNorm + LeakyReLU + time bias) before
                                        the MMAs read it, so that tensor never exists in HBM.  Bit-identical results (tested);
                                        64->64 @96^3 x4: 558 us instead of 532 + 157 us */
+
+#define DUNET_FLAG_FP16 128u /* 16-bit storage format of activations and packed weights is IEEE fp16 (11 mantissa bits) instead of
+                               bf16 (8): the reference's own reduced precision (torch.autocast fp16, test.py:104,119 with
+                               cfg/btcv/test.yaml:16, cfg/msd/test.yaml:16).  Same kernels, same speed (tcgen05 kind::f16 takes
+                               F16 operands at the BF16 rate), fp32 accumulation / statistics / DDIM state as in bf16 mode.
+                               Range: conv outputs are stored before normalisation, |x| must stay below 65504 (the reference's
+                               AMP path has the same limit).  Mutually exclusive with DUNET_FLAG_FP32X3 */
+
+#define DUNET_FLAG_PLAIN_ENCODER 256u /* A-B measurements: with DUNET_FLAG_FP16 the image ENCODER runs in split precision (bf16
+                               hi + lo pairs, 3 MMAs per product, like DUNET_FLAG_FP32X3) because its feature maps are added
+                               into the denoiser at every level of every DDIM step: its rounding error is the one source that
+                               repeats identically in all N steps (2/3 of the fp16 error variance of a window).  The encoder
+                               is 2.6 % of the FLOPs.  This flag runs the encoder in plain fp16 as well */
 
 #define DUNET_FLAG_TC64_CB64 64u /* debug / A-B timing: the Cout = 64 kernel walks 64-channel blocks with a 7-slot plane ring
                                    instead of 32-channel blocks with a 13-slot ring */
@@ -117,11 +134,14 @@ int dunet_get_embedding(dunet_plan* plan, int32_t level, float* out, int32_t bat
 int dunet_set_embedding(dunet_plan* plan, int32_t level, const float* in, int32_t batch, void* workspace, void* stream);
 
 /* replaces: BasicUNetRDenoiser.forward(x, t, image=, embeddings=), models/basic_unet/denoiser.py:284-312, as called
- * from GaussianDiffusion.p_mean_variance (gaussian_diffusion.py:259).  `t_original` is the ORIGINAL timestep (after
- * the respace remap), identical for the whole batch.  Embeddings are those left in the workspace by dunet_encode /
- * dunet_set_embedding.  logits_out: [batch, C, D, H, W] fp32. */
-int dunet_denoise_step(dunet_plan* plan, const float* x_t, const float* image, int32_t t_original, float* logits_out,
-                       int32_t batch, void* workspace, void* stream);
+ * from GaussianDiffusion.p_mean_variance (gaussian_diffusion.py:259) and from Diffusion.denoise (training forward,
+ * models/diffusion/diffusion.py:71-84, train.py:258-268).  `t_original`: HOST array of `batch` ORIGINAL timesteps (after
+ * the respace remap), one per sample.  When all are equal and a member of the plan's schedule (the inference call) the
+ * precomputed time-embedding row is used; otherwise a per-sample bias table is built for this call (the timesteps are
+ * staged through plan-owned pinned memory, nothing is allocated).  Embeddings are those left in the workspace by
+ * dunet_encode / dunet_set_embedding.  logits_out: [batch, C, D, H, W] fp32. */
+int dunet_denoise_step(dunet_plan* plan, const float* x_t, const float* image, const int32_t* t_original,
+                       float* logits_out, int32_t batch, void* workspace, void* stream);
 
 /* replaces: Diffusion.ddim_sample(image) for a batch of windows (models/diffusion/diffusion.py:86-102), i.e.
  * embed_model + SpacedDiffusion.ddim_sample_loop (gaussian_diffusion.py:626-716) + the sum of the N clamped x0
@@ -142,6 +162,25 @@ int dunet_crop_window(const float* volume, const int32_t vol_dims[3], float* pat
                       const int32_t start[3], void* stream);
 int dunet_stitch_add(float* out_volume, const int32_t vol_dims[3], int32_t channels, const float* patch,
                      const int32_t patch_dims[3], const int32_t start[3], void* stream);
+/* all windows of a batch in one launch: patches[b] = volume[start_b : start_b + patch_dims]; starts: HOST [batch][3] */
+int dunet_crop_windows(const float* volume, const int32_t vol_dims[3], float* patches, const int32_t patch_dims[3],
+                       const int32_t* starts, int32_t batch, void* stream);
+
+/* replaces: ONE iteration of the window loop of sliding_window_inference with predictor = Diffusion.forward(pred_type=
+ * "ddim_sample") (engine.py:173-177 + models/diffusion/diffusion.py:86-102): crop `batch` windows out of `volume`
+ * ([1, D, H, W] fp32, already padded to >= the plan's patch), run encoder + N DDIM steps on them, and add the results into
+ * `out_volume` ([C, D, H, W] fp32) window by window in the given order -- `out[slices] += pred`, bit-identical to
+ * dunet_crop_window + dunet_ddim_sample + dunet_stitch_add, without the planar [batch, C, patch] intermediates.
+ *   starts     HOST [batch][3] window corners (MONAI order)
+ *   noise      nullable device [ensemble][batch][C][patch] fp32: the initial x_T (parity runs).  NULL: the library draws
+ *              N(0,1) itself with a counter-based generator (Philox4x32-10, Box-Muller) keyed by (seed, noise_ids[b],
+ *              draw): a window's noise does not depend on batching, rank or launch order
+ *   noise_ids  HOST [batch] stream id per window (e.g. its global index in the volume's window list); needed if noise == NULL
+ *   ensemble   R >= 1 independent draws averaged (BASELINE config 4; R = 1 is the reference)
+ *   weights / count_volume   both NULL: constant blend.  Otherwise MONAI mode="gaussian": out += w * pred, count += w. */
+int dunet_infer_windows(dunet_plan* plan, const float* volume, const int32_t vol_dims[3], const int32_t* starts,
+                        int32_t batch, const float* noise, uint64_t seed, const int64_t* noise_ids, int32_t ensemble,
+                        float* out_volume, float* count_volume, const float* weights, void* workspace, void* stream);
 /* counts_d/h/w: device int32 arrays, number of windows covering each coordinate along that axis (the window grid is a
  * Cartesian product so count(z,y,x) = counts_d[z]*counts_h[y]*counts_w[x]).  binary/argmax_labels nullable. */
 int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channels, const int32_t* counts_d,
@@ -163,6 +202,15 @@ int dunet_finalize_weighted(float* out_volume, const float* count_volume, const 
 int dunet_scale_intensity(const float* in, float* out, int64_t n, float a_min, float a_max, float b_min, float b_max,
                           int32_t clip, void* stream);
 
+/* replaces: GaussianDiffusion.q_sample (gaussian_diffusion.py:187-205) as Diffusion.q_sample calls it in the training forward
+ * (models/diffusion/diffusion.py:65-69, train.py:258-268): out[n] = sqrt_ac[t[n]] * x_start[n] + sqrt_1mac[t[n]] * noise[n].
+ * x_start / out: [batch][per_sample] fp32; t_dev: DEVICE int64 [batch]; sqrt_ac / sqrt_1mac: DEVICE fp32 tables of the
+ * training schedule (float64 tables cast to fp32 like _extract_into_tensor, :914).  noise_in NULL: N(0,1) noise is drawn by
+ * the library generator (stream ids id0 + n) and returned in noise_out.  Bit-identical to the torch expression. */
+int dunet_q_sample(const float* x_start, const float* noise_in, float* noise_out, const int64_t* t_dev, const float* sqrt_ac,
+                   const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, uint64_t seed, int64_t id0,
+                   void* stream);
+
 /* replaces: the per-class reductions of dice_coeff (metric.py:3-49) as Tester.validation_step calls it on the binarised
  * volume (test.py:143-151).  pred: uint8 {0,1} [channels][voxels] (dunet_finalize's `binary`); label: one-hot
  * [channels][voxels], uint8 or fp32 (label_is_float), non-zero = foreground.  counts (device, [channels][3] uint64):
@@ -174,7 +222,8 @@ int dunet_dice_counts(const uint8_t* pred, const void* label, int32_t label_is_f
 /* Stand-alone operator (also the unit-test seam of the tensor-core kernel): y = conv3d(cat([src0, src1]), weight),
  * 3x3x3, stride 1, zero padding 1, no bias.  fp32 NCDHW in/out, bf16 operands + fp32 accumulation inside.
  * use_ref_kernel: 0 = production tcgen05 kernels, 1 = CUDA-core debug kernel, 2 = generic tcgen05 kernel only,
- * 3 / 4 = as 0 / 2 in fp32x3 mode (operands split into hi + lo bf16 pairs, see DUNET_FLAG_FP32X3).
+ * 3 / 4 = as 0 / 2 in fp32x3 mode (operands split into hi + lo bf16 pairs, see DUNET_FLAG_FP32X3),
+ * 5 / 6 = as 0 / 2 with fp16 operands (DUNET_FLAG_FP16).
  * replaces: nn.Conv3d inside MONAI Convolution (denoiser.py:56-58).  use_ref_kernel != 0 selects the debug CUDA-core
  * kernel.  Allocates its own scratch with cudaMallocAsync on `stream`. */
 int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t c1, const float* weight, int32_t cout,
@@ -186,21 +235,23 @@ int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, con
                          int32_t batch, const int32_t dims[3], int32_t use_ref_kernel, void* stream);
 
 /* tools only: when non-NULL every conv CTA writes 8 clock64 stamps to dev_buffer[cta * 8 ..] (kernel start, first MMA
- * batch issued, last MMA committed, accumulators complete, epilogue done). */
+ * batch issued, last MMA committed, accumulators complete, epilogue done).  PROCESS-GLOBAL debugging hook (the one
+ * piece of library state that is not per plan): it applies to every plan's generic conv launches until reset. */
 int dunet_debug_set_conv_timeline(int64_t* dev_buffer);
 
-/* Live kernel timing for bench.py's roofline: when enabled, every 3x3x3-conv launch is bracketed by CUDA events on the
- * launching stream.  dunet_profile_read synchronises those events and returns, since the last enable: summed conv
- * kernel time (ms), number of conv launches, and their ALGORITHMIC flops 2*B*V*Cout*27*Cin (real channels only). */
-int dunet_profile_enable(int32_t on);
-int dunet_profile_read(double* conv_ms, uint64_t* conv_launches, double* conv_flops);
+/* Live kernel timing for bench.py's roofline, PER PLAN: when enabled, every launch this plan makes is bracketed by CUDA
+ * events on the launching stream (and DUNET_FLAG_DUAL_STREAM is suspended so kernel times do not overlap).
+ * dunet_profile_read synchronises those events and returns, since the last enable: summed conv kernel time (ms), number
+ * of conv launches, and their ALGORITHMIC flops 2*B*V*Cout*27*Cin (real channels only). */
+int dunet_profile_enable(dunet_plan* plan, int32_t on);
+int dunet_profile_read(dunet_plan* plan, double* conv_ms, uint64_t* conv_launches, double* conv_flops);
 /* per kernel family [8]: 0 conv3x3x3, 1 normalise (launches moving >= 64 MB), 2 final+DDIM, 3 transposed conv, 4 split-K reduce,
- * 5 other (affine-map kernel), 6 normalise launches below 64 MB (launch-latency bound).
+ * 5 other (affine-map kernel), 6 normalise launches below 64 MB (launch-latency bound), 7 glue (state layout, pack, noise).
  * bytes_by_tag (nullable): ALGORITHMIC HBM bytes of the bandwidth-bound families (normalise: 4 B/element (+2 residual,
  * +0.25 pooled); final+DDIM: per voxel 2F + 16C (+2C re-pack); transposed conv: 2(Cin + 8 Cout) per input voxel). */
-int dunet_profile_read_all(double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag);
+int dunet_profile_read_all(dunet_plan* plan, double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag);
 /* every profiled launch in issue order: duration (ms) and kernel family tag */
-int dunet_profile_dump(double* ms, int32_t* tags, int32_t capacity, int32_t* count);
+int dunet_profile_dump(dunet_plan* plan, double* ms, int32_t* tags, int32_t capacity, int32_t* count);
 
 /* Device-side pipeline watchdog: non-zero if a bounded mbarrier wait expired inside a kernel (kernel bug). */
 int dunet_debug_barrier_timeouts(uint32_t* out_flag);

@@ -89,8 +89,8 @@ def test_forward_dispatch_errors():
         m(image=torch.zeros(1, 1, 32, 32, 32), pred_type="nope")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(image=torch.zeros(1, 1, 32, 32, 32), pred_type="ddim_sample")
-    x, t, nz = m(x=torch.zeros(2, 2, 8, 8, 8), pred_type="q_sample")
-    assert x.shape == (2, 2, 8, 8, 8) and t.shape == (2,)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # q_sample is a CUDA kernel too (round 2)
+        m(x=torch.zeros(2, 2, 8, 8, 8), pred_type="q_sample")
     with pytest.raises(NotImplementedError):
         pkg.model_hub("swin_unetr")
 
@@ -176,3 +176,28 @@ def test_bench_reference_arm_prints_one_valid_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_window_queue_shares_balance_and_cover():
+    """Throughput-mode sharding (dist.py): G consecutive volumes form one queue that splits evenly; every window of every
+    volume is owned by exactly one rank, shares are contiguous in MONAI order."""
+    from diff_unet_amos_b200 import queue_group_size, queue_shares
+
+    assert queue_group_size(98, 8) == 4 and queue_group_size(98, 4) == 2 and queue_group_size(98, 2) == 1
+    assert queue_group_size(98, 1) == 1 and queue_group_size(2645, 8) == 8 and queue_group_size(50, 8) == 4
+    for n_win, world in ((98, 8), (98, 4), (98, 3), (50, 8), (7, 2)):
+        G = queue_group_size(n_win, world)
+        owner = np.full((G, n_win), -1)
+        per_rank = []
+        for r in range(world):
+            tot = 0
+            for v, lo, hi in queue_shares(n_win, G, r, world):
+                assert 0 <= lo < hi <= n_win and (owner[v, lo:hi] == -1).all()
+                owner[v, lo:hi] = r
+                tot += hi - lo
+            per_rank.append(tot)
+        assert (owner >= 0).all() and max(per_rank) - min(per_rank) <= 1
+        if (n_win * G) % world == 0:
+            assert max(per_rank) == min(per_rank)
+        flat = owner.reshape(-1)
+        assert (np.diff(flat) >= 0).all()  # contiguous, rank order = queue order

@@ -19,7 +19,7 @@ ap.add_argument("--ddim", type=int, default=10)
 ap.add_argument("--prof", action="store_true")
 ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--dump", action="store_true")
-ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32x3"])
+ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32x3"])
 ap.add_argument("--features", default="64,64,128,256,512,64")
 a = ap.parse_args()
 torch.manual_seed(0)
@@ -42,14 +42,15 @@ if a.prof:
     import ctypes
     from diff_unet_amos_b200 import _lib
     lib = _lib.load()
-    lib.dunet_profile_enable(1)
+    plan = m._rt.plan
+    lib.dunet_profile_enable(plan, 1)
     with torch.no_grad():
         m(image=image, pred_type="ddim_sample", noise=noise)
     torch.cuda.synchronize()
     msb = (ctypes.c_double * 8)(); cnt = (ctypes.c_uint64 * 8)(); byt = (ctypes.c_double * 8)()
-    _lib.check(lib.dunet_profile_read_all(msb, cnt, byt))
-    lib.dunet_profile_enable(0)
-    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "affine-map", "norm-small", "-"]
+    _lib.check(lib.dunet_profile_read_all(plan, msb, cnt, byt))
+    lib.dunet_profile_enable(plan, 0)
+    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "affine-map", "norm-small", "glue"]
     tot = sum(msb)
     print("in-situ CUDA-event time per kernel family (one call, batch %d):" % a.batch)
     for i, nme in enumerate(names):
@@ -59,12 +60,12 @@ if a.prof:
     if a.dump:
         cap = 4096
         dms = (ctypes.c_double * cap)(); dtg = (ctypes.c_int32 * cap)(); dn = ctypes.c_int32()
-        lib.dunet_profile_enable(1)
+        lib.dunet_profile_enable(plan, 1)
         with torch.no_grad():
             m(image=image, pred_type="ddim_sample", noise=noise)
         torch.cuda.synchronize()
-        _lib.check(lib.dunet_profile_dump(dms, dtg, cap, ctypes.byref(dn)))
-        lib.dunet_profile_enable(0)
+        _lib.check(lib.dunet_profile_dump(plan, dms, dtg, cap, ctypes.byref(dn)))
+        lib.dunet_profile_enable(plan, 0)
         seq = [(dtg[i], dms[i] * 1e3) for i in range(dn.value)]
         # one denoiser step = the launches between the 2nd and 3rd final kernel
         fin = [i for i, (tg, _) in enumerate(seq) if tg == 2]
