@@ -65,6 +65,10 @@ SIGNATURES = {
     "dunet_stitch_add_weighted": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "dunet_finalize_weighted": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_void_p]),
     "dunet_scale_intensity": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32, c_void_p]),
+    "dunet_foreground_bbox": (c_int32, [c_void_p, c_int32, POINTER(c_int32), c_void_p, c_void_p]),
+    "dunet_crop_box": (c_int32, [c_void_p, c_int32, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    "dunet_resample_spacing": (c_int32, [c_void_p, c_int32, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(ctypes.c_double), c_int32, c_void_p]),
+    "dunet_uncertainty_fuse": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "dunet_q_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_uint64, c_int64, c_void_p]),
     "dunet_dice_counts": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "dunet_op_conv3x3x3": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, POINTER(c_int32), c_int32, c_void_p]),

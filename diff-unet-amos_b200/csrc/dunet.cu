@@ -1626,6 +1626,46 @@ int dunet_scale_intensity(const float* in, float* out, int64_t n, float a_min, f
   return 0;
 }
 
+int dunet_foreground_bbox(const float* image, int32_t channels, const int32_t dims[3], int32_t* bbox_dev, void* stream) {
+  if (!image || !dims || !bbox_dev || channels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bbox_init_kernel<<<1, 32, 0, st>>>(bbox_dev, dims[0], dims[1], dims[2]);
+  LAUNCH_CHECK();
+  foreground_bbox_kernel<<<grid_for((long long)channels * dims[0] * dims[1] * dims[2], 256, 148 * 8), 256, 0, st>>>(
+      image, channels, dims[0], dims[1], dims[2], bbox_dev);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_crop_box(const float* in, int32_t channels, const int32_t dims[3], float* out, const int32_t out_dims[3],
+                   const int32_t start[3], void* stream) {
+  if (!in || !out || !dims || !out_dims || !start || channels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  TRY(check_box(dims, out_dims, start));
+  crop_box_kernel<<<grid_for((long long)channels * out_dims[0] * out_dims[1] * out_dims[2], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, channels, dims[0], dims[1], dims[2], out_dims[0], out_dims[1], out_dims[2], start[0], start[1], start[2]);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_resample_spacing(const float* in, int32_t channels, const int32_t dims[3], float* out, const int32_t out_dims[3],
+                           const double ratio[3], int32_t mode, void* stream) {
+  if (!in || !out || !dims || !out_dims || !ratio || channels < 1) return fail(DUNET_E_INVALID, "bad argument");
+  if (mode != 0 && mode != 1) return fail(DUNET_E_INVALID, "mode must be 0 (trilinear) or 1 (nearest)");
+  for (int d = 0; d < 3; ++d)
+    if (dims[d] < 1 || out_dims[d] < 1 || !(ratio[d] > 0.0)) return fail(DUNET_E_INVALID, "bad dims / ratio on axis %d", d);
+  resample_spacing_kernel<<<grid_for((long long)channels * out_dims[0] * out_dims[1] * out_dims[2], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, channels, dims[0], dims[1], dims[2], out_dims[0], out_dims[1], out_dims[2], ratio[0], ratio[1], ratio[2], mode);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int dunet_uncertainty_fuse(const float* per_step, int32_t runs, int32_t n_steps, int64_t n, float* out, void* stream) {
+  if (!per_step || !out || runs < 1 || n_steps < 1 || n < 1) return fail(DUNET_E_INVALID, "bad argument");
+  uncertainty_fuse_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(per_step, out, runs, n_steps, (long long)n);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int dunet_q_sample(const float* x_start, const float* noise_in, float* noise_out, const int64_t* t_dev, const float* sqrt_ac,
                    const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, uint64_t seed, int64_t id0, void* stream) {
   if (!x_start || !t_dev || !sqrt_ac || !sqrt_1mac || !out || batch < 1 || per_sample < 1) return fail(DUNET_E_INVALID, "bad argument");

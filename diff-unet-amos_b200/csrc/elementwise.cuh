@@ -1167,6 +1167,115 @@ __global__ void finalize_kernel(float* __restrict__ vol, const int* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Input-side pre-pass of the reference's val transforms (utils.py:165-181) after ScaleIntensityRanged:
+//   CropForegroundd(source_key="image")     bounding box of image > 0 (MONAI generate_spatial_bounding_box, select_fn =
+//                                           is_positive, margin 0), then the same crop of image and label
+//   Spacingd(pixdim=(1.5, 1.5, 2.0), mode=("bilinear", "nearest"))   resample to the new voxel spacing
+// ---------------------------------------------------------------------------------------------------------------
+// bbox[0..2] = min index with a positive voxel per axis, bbox[3..5] = max index + 1 (caller initialises to {D,H,W,0,0,0});
+// the box is over all channels.  Integer atomics: exact, order-independent.
+__global__ void bbox_init_kernel(int* __restrict__ bbox, int D, int H, int W) {
+  if (threadIdx.x == 0) { bbox[0] = D; bbox[1] = H; bbox[2] = W; bbox[3] = bbox[4] = bbox[5] = 0; }
+}
+__global__ void __launch_bounds__(256) foreground_bbox_kernel(const float* __restrict__ img, int C, int D, int H, int W,
+                                                              int* __restrict__ bbox) {
+  const long long vox = (long long)D * H * W, total = vox * C;
+  int lo[3] = {D, H, W}, hi[3] = {0, 0, 0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (img[i] > 0.f) {
+      const long long v = i % vox;
+      const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((long long)W * H));
+      lo[0] = min(lo[0], z); lo[1] = min(lo[1], y); lo[2] = min(lo[2], x);
+      hi[0] = max(hi[0], z + 1); hi[1] = max(hi[1], y + 1); hi[2] = max(hi[2], x + 1);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      atomicMin(bbox + d, lo[d]);
+      atomicMax(bbox + 3 + d, hi[d]);
+    }
+  }
+}
+// out[c] = in[c][s0 : s0 + OD, s1 : s1 + OH, s2 : s2 + OW]   (SpatialCrop of every channel)
+__global__ void crop_box_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int D, int H, int W, int OD, int OH,
+                                int OW, int s0, int s1, int s2) {
+  const long long ov = (long long)OD * OH * OW, total = ov * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / ov);
+    const long long r = i % ov;
+    const int x = (int)(r % OW), y = (int)((r / OW) % OH), z = (int)(r / ((long long)OW * OH));
+    out[i] = in[(((long long)c * D + s0 + z) * H + s1 + y) * W + s2 + x];
+  }
+}
+// Spacing resample for axis-aligned affines: output voxel (i, j, k) samples the input at index (i*rz, j*ry, k*rx) with
+// r = new spacing / old spacing (voxel 0 stays on voxel 0, MONAI compute_shape_offset with scale_extent = False), border
+// clamped.  mode 0: trilinear (image), weights and lerps in fp32 in a fixed order (x, then y, then z); mode 1: nearest
+// (label), index = rint(coordinate) (round half to even, like grid_sample's nearest).  Coordinates are formed in fp64.
+__global__ void __launch_bounds__(256) resample_spacing_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int D,
+                                                               int H, int W, int OD, int OH, int OW, double rz, double ry,
+                                                               double rx, int mode) {
+  const long long ov = (long long)OD * OH * OW, total = ov * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / ov);
+    const long long r = i % ov;
+    const int x = (int)(r % OW), y = (int)((r / OW) % OH), z = (int)(r / ((long long)OW * OH));
+    const double cz = fmin(fmax(z * rz, 0.0), (double)(D - 1)), cy = fmin(fmax(y * ry, 0.0), (double)(H - 1)),
+                 cx = fmin(fmax(x * rx, 0.0), (double)(W - 1));
+    const float* src = in + (long long)c * D * H * W;
+    if (mode == 1) {
+      const int iz = (int)rint(cz), iy = (int)rint(cy), ix = (int)rint(cx);
+      out[i] = src[((long long)iz * H + iy) * W + ix];
+      continue;
+    }
+    const int z0 = (int)floor(cz), y0 = (int)floor(cy), x0 = (int)floor(cx);
+    const int z1 = min(z0 + 1, D - 1), y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float fz = (float)(cz - z0), fy = (float)(cy - y0), fx = (float)(cx - x0);
+    auto at = [&](int zz, int yy, int xx) { return src[((long long)zz * H + yy) * W + xx]; };
+    auto lerp = [](float a, float b, float t) { return __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a))); };
+    const float c00 = lerp(at(z0, y0, x0), at(z0, y0, x1), fx), c01 = lerp(at(z0, y1, x0), at(z0, y1, x1), fx);
+    const float c10 = lerp(at(z1, y0, x0), at(z1, y0, x1), fx), c11 = lerp(at(z1, y1, x0), at(z1, y1, x1), fx);
+    out[i] = lerp(lerp(c00, c01, fy), lerp(c10, c11, fy), fz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Uncertainty-weighted fusion of the DDIM steps of R independent runs (upstream Diff-UNet's test-time fusion; NOT used
+// by this reference, whose ddim_sample returns the plain sum, models/diffusion/diffusion.py:94-98):
+//   for every step k (loop order, t high -> low):  m = mean_r(model_output[r][k]);  p = max(sigmoid(m), 0.001)
+//     u = -p * log(p);   w = exp(sigmoid((k + 1) / N) * (1 - u));   out += w * sum_r clamp(model_output[r][k], -1, 1)
+// steps: [R][N][n] fp32 raw model outputs (dunet_ddim_sample's per_step_logits of each run).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) uncertainty_fuse_kernel(const float* __restrict__ steps, float* __restrict__ out, int R, int N,
+                                                               long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < N; ++k) {
+      float m = 0.f, sx0 = 0.f;
+      for (int r = 0; r < R; ++r) {
+        const float v = steps[((long long)r * N + k) * n + i];
+        m += v;
+        sx0 += fminf(fmaxf(v, -1.f), 1.f);
+      }
+      m /= (float)R;
+      const float p = fmaxf(1.f / (1.f + expf(-m)), 0.001f);
+      const float u = -p * logf(p);
+      const float sg = 1.f / (1.f + expf(-(float)(k + 1) / (float)N));
+      acc += expf(sg * (1.f - u)) * sx0;
+    }
+    out[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Per-class Dice inputs (reference metric.py:3-49 dice_coeff as used by Tester.validation_step, test.py:143-151):
 // counts[c] = { |pred_c & label_c|, |pred_c|, |label_c| } as exact 64-bit integers.  pred: uint8 {0,1} [C][vox] (the
 // binary volume finalize_kernel writes); label: uint8 or fp32 one-hot [C][vox], non-zero = foreground.

@@ -526,6 +526,35 @@ class DiffUNetB200(nn.Module):
         embeddings = self.embed_model(image)
         return self.model(x=x, t=step, embeddings=embeddings, image=image)
 
+    def ddim_sample_uncertainty(self, image: torch.Tensor, noise: torch.Tensor = None, uncer_step: int = 4) -> torch.Tensor:
+        """Upstream Diff-UNet's uncertainty-weighted step fusion (this reference returns the plain sum,
+        models/diffusion/diffusion.py:94-98): ``uncer_step`` independent DDIM runs per window, then for every step the
+        run-averaged model output gives an uncertainty map that weights the sum of the runs' clamped x0 predictions
+        (``dunet_uncertainty_fuse``).  ``noise``: optional [uncer_step, B, C, *patch]."""
+        image = _f32c(image, "image")
+        self._check_image(image)
+        B = image.shape[0]
+        shape = (B, self.num_classes) + self.patch
+        if noise is None:
+            noise = torch.randn((uncer_step,) + shape, device=image.device)
+        noise = _f32c(noise, "noise")
+        if tuple(noise.shape) != (uncer_step,) + shape:
+            raise ValueError(f"noise must be {(uncer_step,) + shape}, got {tuple(noise.shape)}")
+        steps = torch.empty((uncer_step, self.num_steps) + shape, dtype=torch.float32, device=image.device)
+        rt = self._rt
+        plan = rt.ensure(image.device)
+        ws = rt.workspace(B)
+        scratch = torch.empty(shape, dtype=torch.float32, device=image.device)
+        lib = _lib.load()
+        with torch.cuda.device(image.device):
+            for r in range(uncer_step):
+                _lib.check(lib.dunet_ddim_sample(plan, _ptr(image), _ptr(noise[r]), _ptr(scratch), _ptr(steps[r]), None, B,
+                                                 1 if r == 0 else 0, ctypes.c_float(1.0), 0, _ptr(ws), _stream()))
+            out = torch.empty(shape, dtype=torch.float32, device=image.device)
+            _lib.check(lib.dunet_uncertainty_fuse(_ptr(steps), uncer_step, self.num_steps, out.numel(), _ptr(out), _stream()))
+        rt.emb_token = None
+        return out
+
     def ddim_sample(self, image: torch.Tensor, noise: torch.Tensor = None, ensemble: int = 1) -> torch.Tensor:
         """Sum over the N DDIM steps of the clamped x0 prediction for every window of the batch
         (models/diffusion/diffusion.py:86-102).  ``noise`` ([B, C, *patch], or [R, B, C, *patch] with ``ensemble=R``)

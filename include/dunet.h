@@ -202,6 +202,28 @@ int dunet_finalize_weighted(float* out_volume, const float* count_volume, const 
 int dunet_scale_intensity(const float* in, float* out, int64_t n, float a_min, float a_max, float b_min, float b_max,
                           int32_t clip, void* stream);
 
+/* replaces: monai.transforms.CropForegroundd(keys=["image", "label"], source_key="image") of the reference's val transforms
+ * (utils.py:171).  dunet_foreground_bbox writes {min z, min y, min x, max z + 1, max y + 1, max x + 1} of the voxels with
+ * image > 0 (any channel; MONAI generate_spatial_bounding_box with select_fn = is_positive, margin 0) to the DEVICE array
+ * bbox_dev[6]; an all-background image gives {D, H, W, 0, 0, 0}.  dunet_crop_box is the SpatialCrop applied to image and
+ * label: out[c] = in[c][start : start + out_dims].  Exact (integer / copy). */
+int dunet_foreground_bbox(const float* image, int32_t channels, const int32_t dims[3], int32_t* bbox_dev, void* stream);
+int dunet_crop_box(const float* in, int32_t channels, const int32_t dims[3], float* out, const int32_t out_dims[3],
+                   const int32_t start[3], void* stream);
+/* replaces: monai.transforms.Spacingd(pixdim=(1.5, 1.5, 2.0), mode=("bilinear", "nearest")) (utils.py:173-177) for
+ * axis-aligned affines: out[c][i, j, k] = sample(in[c], (i * ratio[0], j * ratio[1], k * ratio[2])), ratio = new / old
+ * spacing per axis, coordinates clamped to the border; mode 0 trilinear (image), 1 nearest (label).  The caller sizes
+ * `out` as round((dim - 1) / ratio) + 1 per axis (MONAI compute_shape_offset).  Interpolation in fp32 in a fixed order. */
+int dunet_resample_spacing(const float* in, int32_t channels, const int32_t dims[3], float* out, const int32_t out_dims[3],
+                           const double ratio[3], int32_t mode, void* stream);
+
+/* Uncertainty-weighted fusion of the DDIM steps of `runs` independent sampling runs (the test-time fusion of upstream
+ * Diff-UNet; this reference returns the plain sum instead, models/diffusion/diffusion.py:94-98).
+ * per_step: [runs][n_steps][n] fp32 raw model outputs in loop order (per_step_logits of dunet_ddim_sample);
+ * out[n] = sum_k exp(sigmoid((k + 1) / n_steps) * (1 - u_k)) * sum_r clamp(per_step[r][k], -1, 1) with
+ * u_k = -p log p, p = max(sigmoid(mean_r per_step[r][k]), 0.001). */
+int dunet_uncertainty_fuse(const float* per_step, int32_t runs, int32_t n_steps, int64_t n, float* out, void* stream);
+
 /* replaces: GaussianDiffusion.q_sample (gaussian_diffusion.py:187-205) as Diffusion.q_sample calls it in the training forward
  * (models/diffusion/diffusion.py:65-69, train.py:258-268): out[n] = sqrt_ac[t[n]] * x_start[n] + sqrt_1mac[t[n]] * noise[n].
  * x_start / out: [batch][per_sample] fp32; t_dev: DEVICE int64 [batch]; sqrt_ac / sqrt_1mac: DEVICE fp32 tables of the

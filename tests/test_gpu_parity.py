@@ -655,3 +655,55 @@ def test_use_amp_maps_to_the_kernel_precision(tmp_path):
     image = seeded_image((1, 1, 32, 32, 32))
     img, out, lab = e.infer({"image": image, "label": torch.zeros(1, 2, 32, 32, 32)})
     assert out.shape == (1, 2, 32, 32, 32)
+
+
+def test_val_prepass_foreground_crop_and_spacing_resample():
+    """CropForegroundd + Spacingd of the reference's val transforms (utils.py:171-177) as GPU kernels vs the
+    oracle restatement: bounding box and nearest-neighbour label resample exact, trilinear image resample bit-exact
+    (same fp32 lerp order), plus the composed val_transform."""
+    from oracle import oracle_preprocess as op
+
+    torch.manual_seed(4)
+    hu = torch.randn(1, 37, 45, 52) * 300.0 - 100.0
+    hu[:, :5] = -1000.0; hu[:, :, 40:] = -1000.0; hu[:, :, :, :7] = -500.0   # air margins -> intensity 0 after scaling
+    label = (torch.rand(3, 37, 45, 52) > 0.7).float()
+    img = pkg.scale_intensity_range(hu.cuda())
+    start, end = pkg.foreground_bbox(img)
+    assert (start, end) == op.foreground_bbox(img.cpu()) and start[0] == 5 and end[1] <= 40 and start[2] == 7
+    assert pkg.foreground_bbox(torch.zeros(1, 8, 8, 8, device="cuda")) == ((0, 0, 0), (0, 0, 0))
+    ci, cl, _ = pkg.crop_foreground(img, label.cuda())
+    sl = (slice(None),) + tuple(slice(s, e) for s, e in zip(start, end))
+    assert torch.equal(ci.cpu(), img.cpu()[sl]) and torch.equal(cl.cpu(), label[sl])
+    for spacing in ((0.8, 0.8, 5.0), (1.5, 1.5, 2.0), (2.2, 0.7, 1.0)):
+        for mode in ("bilinear", "nearest"):
+            got = pkg.spacing_resample(ci, spacing, (1.5, 1.5, 2.0), mode)
+            ref = op.spacing_resample(ci.cpu(), spacing, (1.5, 1.5, 2.0), mode)
+            assert got.shape == ref.shape == (1,) + op.resampled_shape(ci.shape[1:], spacing, (1.5, 1.5, 2.0))
+            assert torch.equal(got.cpu(), ref), (spacing, mode)
+    im2, lb2 = pkg.val_transform(hu.cuda(), label.cuda(), (0.8, 0.8, 5.0))
+    assert torch.equal(im2.cpu(), op.spacing_resample(ci.cpu(), (0.8, 0.8, 5.0), (1.5, 1.5, 2.0), "bilinear"))
+    assert torch.equal(lb2.cpu(), op.spacing_resample(cl.cpu(), (0.8, 0.8, 5.0), (1.5, 1.5, 2.0), "nearest"))
+
+
+def test_uncertainty_weighted_step_fusion():
+    """upstream Diff-UNet's uncertainty-weighted fusion of the DDIM steps of R runs: the fusion kernel vs the
+    oracle restatement on the same per-step tensors, and the whole ddim_sample_uncertainty call vs the oracle pipeline."""
+    from oracle import oracle_preprocess as op
+
+    torch.manual_seed(6)
+    steps = torch.randn(3, 10, 2, 4, 16, 16, 16) * 2.0
+    out = torch.empty(2, 4, 16, 16, 16, device="cuda")
+    sc = steps.cuda().contiguous()
+    _lib.check(_lib.load().dunet_uncertainty_fuse(_p(sc), 3, 10, out.numel(), _p(out), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert rel_l2(out.cpu(), op.uncertainty_fuse(steps)) < 1e-6
+    cout, S, R = 2, 32, 3
+    m = _build(cout, S, SMALL)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    image, noise = seeded_image((1, 1, S, S, S)), seeded_noise((R, 1, cout, S, S, S))
+    with torch.no_grad():
+        got = m.ddim_sample_uncertainty(image.cuda(), noise=noise.cuda(), uncer_step=R)
+        e = oracle_model.encoder_forward(sd, image)
+        runs = [oracle_ddim.ddim_sample_window(lambda x, t: oracle_model.denoiser_forward(sd, x, t, image, e), noise[r], collect=True)
+                for r in range(R)]
+        ref = op.uncertainty_fuse(torch.stack([torch.stack(r["model_outputs"]) for r in runs]))
+    assert rel_l2(got.cpu(), ref) < FP16_TOL
