@@ -400,22 +400,26 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
   ConvGeom g;
   g.tiles_x = (p->W[lvl] + CONV_TX - 1) / CONV_TX;
   g.tiles_y = (p->H[lvl] + CONV_TY - 1) / CONV_TY;
-  // ZT (z-slabs per work item) trades weight re-use (each streamed weight tile feeds ZT slabs) against parallelism.
-  // Small volumes (deep U-Net levels) get thinner items when a single sample would otherwise give fewer than ~half a
-  // wave of work items.  Decided from per-sample shapes only (batch-invariant results).  The Cout = 64 z-stacked
-  // kernel always uses ZT = 4.
+  // ZT (z-slabs per work item) trades weight re-use (each streamed weight tile feeds ZT slabs) against parallelism, and
+  // split-K trades parallelism against an fp32 partial round trip + a reduce launch.  Both are decided from PER-SAMPLE
+  // shapes only (a window's result is bit-identical whatever it is batched with) and are tuned for the way the path is
+  // actually driven: 2-4 windows per launch (dual-stream half batches), so ~24+ work items per sample already fill the GPU.
+  // Round 1 split K whenever a sample had < 96 items: at batch 4 that doubled the 24^3 / 12^3 launches into two waves of
+  // half-K items, each still streaming its weights from L2, plus the reduce kernels (measured 0.31-0.38 of the tensor peak).
+  // The Cout = 64 z-stacked kernel always uses ZT = 4.
+  static const int zt_items = [] { const char* e = getenv("DUNET_GEOM_ZT_ITEMS"); return e ? atoi(e) : 24; }();
+  static const int split_items = [] { const char* e = getenv("DUNET_GEOM_SPLIT_ITEMS"); return e ? atoi(e) : 20; }();
   {
     const int tz4 = (p->D[lvl] + CONV_ZT - 1) / CONV_ZT;
-    const int items4 = g.tiles_x * g.tiles_y * tz4 * c.n_tiles * std::max(1, std::min(c.ncb(), 4));
-    g.zt = (items4 < 64 && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
+    const int items4 = g.tiles_x * g.tiles_y * tz4 * c.n_tiles;
+    g.zt = (items4 < zt_items && !(c.coutp == 64 && c.cb_ch == 32)) ? 2 : CONV_ZT;
   }
   g.tiles_z = (p->D[lvl] + g.zt - 1) / g.zt;
   g.tiles = g.tiles_x * g.tiles_y * g.tiles_z;
-  // the split factor must not depend on the batch: a window's result is bit-identical whatever it is batched with
   (void)B;
   const int ctas = g.tiles * c.n_tiles, ncb = c.ncb();
   g.ksplit = 1;
-  if (ncb >= 2 && ctas < 96) g.ksplit = std::max(1, std::min(ncb, 148 / ctas));
+  if (ncb >= 2 && ctas < split_items) g.ksplit = std::max(1, std::min(ncb, 96 / ctas));
   return g;
 }
 
@@ -454,7 +458,7 @@ static inline Act ws_act(const dunet_plan* p, uint8_t* ws, size_t off, int ch, i
 // (measured on a 96^3 window: 2/3 of the fp16 error variance; argmax agreement 99.90 % -> 99.94 % with an exact encoder).
 // It is 2.6 % of the FLOPs, so 3x its MMAs costs ~5 %.  DUNET_FLAG_PLAIN_ENCODER switches this off (A-B measurements).
 static inline bool enc_prec(const dunet_plan* p) {
-  return is_prec(p) || (is_fp16(p) && !(p->cfg.flags & DUNET_FLAG_PLAIN_ENCODER));
+  return is_prec(p) || (is_fp16(p) && !(p->cfg.flags & (DUNET_FLAG_PLAIN_ENCODER | DUNET_FLAG_REF_CONV)));
 }
 // 16-bit storage format of a tensor: fp16 in fp16 mode unless it is (part of) a split hi/lo bf16 pair
 static inline bool fmt_h(const dunet_plan* p, bool prec) { return is_fp16(p) && !prec; }
