@@ -324,7 +324,7 @@ def run_b200(args, cfg):
         launches = lib.dunet_launch_count() - l0
         clk = clocks.stop() if clocks else None
         ms = e0.elapsed_time(e1)
-        last_labels = labels[-1] if rank == 0 else None
+        last_labels = labels[0] if rank == 0 else None  # volume 0 of the queue: its windows draw the noise streams (seed, 0 .. n_win - 1)
         del labels
         # ---------------- end-to-end leg: host volume in, host labels out, every step ----------------
         barrier()

@@ -493,7 +493,7 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
   L.acc = take((size_t)B * CP * p->V[0] * sizeof(float));
   L.image = take((size_t)B * p->cfg.in_channels * p->V[0] * sizeof(float));  // cropped windows (dunet_infer_windows)
   for (int l = 0; l < 5; ++l) {
-    L.emb[l] = take(act_m(p->fp[l], l, pme));
+    L.emb[l] = take(act(p->fp[l], l));
     L.x[l] = take(act(p->fp[l], l));
     L.epool[l] = l ? take(act_m(p->fp[l - 1], l, pme)) : 0;
     L.dpool[l] = l ? take(act(p->fp[l - 1], l)) : 0;
@@ -713,25 +713,26 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
   // one bf16 read + one bf16 write per element (+ read of the residual, + 1/8 write of the pooled tensor); launches that move
   // less than 64 MB are launch-latency bound and are reported as their own family so that the HBM roofline of the large
   // ones stays readable
-  const double nbytes = (prec ? 2.0 : 1.0) * B * c.coutp * (double)p->V[lvl] * (4.0 + (add.hi ? (add.lo && !prec ? 4.0 : 2.0) : 0.0) + (pooled.hi ? 0.25 : 0.0));
+  const double nbytes = (prec ? 2.0 : 1.0) * B * c.coutp * (double)p->V[lvl] * (4.0 + (add.hi ? 2.0 : 0.0) + (pooled.hi ? 0.25 : 0.0));
   const int ptag = nbytes >= 64e6 ? PROF_NORM : PROF_NORM_SMALL;
   if (PROF_ON) prof_of(p)->bytes[ptag] += nbytes;
   TRY(prof_begin(ptag, st));
   const int mode = prec ? MODE_FP32X3 : (is_fp16(p) ? MODE_FP16 : MODE_BF16);
   if (prec && add.hi && !add.lo) return fail(DUNET_E_STATE, "fp32x3 normalise needs a hi + lo residual");
-  if (mode == MODE_BF16 && add.lo) return fail(DUNET_E_STATE, "bf16 normalise cannot take a hi + lo residual");
+  if (!prec && add.lo) return fail(DUNET_E_STATE, "16-bit normalise cannot take a hi + lo residual");
+  a.out_single_h = (prec && !out.lo) ? 1 : 0;  // split-precision producer, fp16 consumer (encoder feature maps in fp16 mode)
+  if (a.out_single_h && !is_fp16(p)) return fail(DUNET_E_STATE, "single-tensor output of a split-precision pass exists in fp16 mode only");
 #define DUNET_NORM(KERN, GRID)                                                                     \
   do {                                                                                             \
     if (mode == MODE_FP32X3) {                                                                     \
-      if (add.hi) launch_k(KERN<1, MODE_FP32X3>, GRID, dim3(NORM_THREADS), 0, st, a);              \
-      else launch_k(KERN<0, MODE_FP32X3>, GRID, dim3(NORM_THREADS), 0, st, a);                     \
+      if (add.hi) launch_k(KERN<true, MODE_FP32X3>, GRID, dim3(NORM_THREADS), 0, st, a);           \
+      else launch_k(KERN<false, MODE_FP32X3>, GRID, dim3(NORM_THREADS), 0, st, a);                 \
     } else if (mode == MODE_FP16) {                                                                \
-      if (add.hi && add.lo) launch_k(KERN<2, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);      \
-      else if (add.hi) launch_k(KERN<1, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);           \
-      else launch_k(KERN<0, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);                       \
+      if (add.hi) launch_k(KERN<true, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);             \
+      else launch_k(KERN<false, MODE_FP16>, GRID, dim3(NORM_THREADS), 0, st, a);                   \
     } else {                                                                                       \
-      if (add.hi) launch_k(KERN<1, MODE_BF16>, GRID, dim3(NORM_THREADS), 0, st, a);                \
-      else launch_k(KERN<0, MODE_BF16>, GRID, dim3(NORM_THREADS), 0, st, a);                       \
+      if (add.hi) launch_k(KERN<true, MODE_BF16>, GRID, dim3(NORM_THREADS), 0, st, a);             \
+      else launch_k(KERN<false, MODE_BF16>, GRID, dim3(NORM_THREADS), 0, st, a);                   \
     }                                                                                              \
   } while (0)
   if (pooled.hi) {
@@ -875,7 +876,8 @@ static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, co
   for (int l = 0; l < 5; ++l) {
     const Act src = l ? ws_act_x(p, ws, L.epool[l], p->fp[l - 1], l, B, ep) : in_pack;
     const Act pooled = l < 4 ? ws_act_x(p, ws, L.epool[l + 1], p->fp[l], l + 1, B, ep) : Act();
-    TRY(run_twoconv(p, p->enc[l], src, Act(), BiasRef(), Act(), ws_act_x(p, ws, L.emb[l], p->fp[l], l, B, ep), pooled, l, B, ws, L, st));
+    // feature maps: hi + lo pairs in fp32x3 mode; ONE fp16 tensor in fp16 mode (rounded once from the split-precision result)
+    TRY(run_twoconv(p, p->enc[l], src, Act(), BiasRef(), Act(), ws_act(p, ws, L.emb[l], p->fp[l], l, B), pooled, l, B, ws, L, st));
   }
   return 0;
 }
@@ -887,7 +889,7 @@ static int unet_body(dunet_plan* p, BiasRef temb_row, int B, uint8_t* ws, const 
   for (int l = 0; l < 5; ++l) {
     const Act src = l ? ws_act(p, ws, L.dpool[l], p->fp[l - 1], l, B) : in_pack;
     const Act pooled = l < 4 ? ws_act(p, ws, L.dpool[l + 1], p->fp[l], l + 1, B) : Act();
-    TRY(run_twoconv(p, p->den[l], src, Act(), temb_row.at(p->temb_off[l]), ws_act_x(p, ws, L.emb[l], p->fp[l], l, B, enc_prec(p)),
+    TRY(run_twoconv(p, p->den[l], src, Act(), temb_row.at(p->temb_off[l]), ws_act(p, ws, L.emb[l], p->fp[l], l, B),
                     ws_act(p, ws, L.x[l], p->fp[l], l, B), pooled, l, B, ws, L, st));
   }
   Act prev = ws_act(p, ws, L.x[4], p->fp[4], 4, B);
@@ -1295,7 +1297,7 @@ int dunet_get_embedding(dunet_plan* p, int32_t level, float* out, int32_t B, voi
   TRY(check_call(p, B, workspace));
   if (level < 0 || level > 4 || !out) return fail(DUNET_E_INVALID, "bad level / NULL out");
   const WsLayout L = ws_layout(p, B);
-  const Act e = ws_act_x(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B, enc_prec(p));
+  const Act e = ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B);
   DUNET_FMT(fmt_h(p, e.lo != nullptr), unpack_c8_kernel<HF><<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       e.hi, e.lo, p->fp[level], out, p->fr[level], p->V[level], B));
   LAUNCH_CHECK();
@@ -1307,7 +1309,7 @@ int dunet_set_embedding(dunet_plan* p, int32_t level, const float* in, int32_t B
   if (level < 0 || level > 4 || !in) return fail(DUNET_E_INVALID, "bad level / NULL in");
   p->emb_B = B; p->emb_dual = false;
   const WsLayout L = ws_layout(p, B);
-  return launch_pack(p, in, p->fr[level], nullptr, 0, ws_act_x(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B, enc_prec(p)),
+  return launch_pack(p, in, p->fr[level], nullptr, 0, ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B),
                      p->fp[level], p->V[level], B, static_cast<cudaStream_t>(stream));
 }
 

@@ -272,6 +272,8 @@ struct NormActArgs {
   __nv_bfloat16* pooled;   // POOL only
   const __nv_bfloat16 *raw_lo, *add_lo;  // fp32x3 mode: low parts (all four set, or all nullptr)
   __nv_bfloat16 *out_lo, *pooled_lo;
+  int out_single_h;        // fp32x3 kernels only: write `out` as ONE fp16 tensor (out_lo unused) -- the encoder's feature maps in
+                           // fp16 mode: computed in split precision, consumed by the fp16 denoiser (pooled stays a hi + lo pair)
   int chunks;              // C/8
   int D, H, W;
   float eps, slope;
@@ -343,17 +345,16 @@ __device__ __forceinline__ void norm_apply(float (&f)[8], const float* sc, const
   }
 }
 
-// ADD: 0 = no residual, 1 = the encoder-feature residual is present in the tensor's own format, 2 = it is present as a
-// bf16 hi + lo PAIR while everything else is 16-bit (fp16 mode keeps the encoder, whose rounding error would repeat
-// identically in all N DDIM steps, in split precision).  MODE: 0 = bf16, 1 = fp32x3 (hi + lo pairs in and out), 2 = fp16.
+// ADD: the encoder-feature residual is present (in the tensor's own format).  MODE: 0 = bf16, 1 = fp32x3 (hi + lo pairs in
+// and out; with out_single_h the output is one fp16 tensor instead), 2 = fp16.
 // All variants keep 4 independent 16-byte loads per tensor in flight per thread; __launch_bounds__ asks for 3-4 resident
 // blocks per SM so ~64 KB of loads are outstanding per SM.
 constexpr int MODE_BF16 = 0, MODE_FP32X3 = 1, MODE_FP16 = 2;
 
-template <int ADD, int MODE>
+template <bool ADD, int MODE>
 __global__ void __launch_bounds__(NORM_THREADS, (ADD || MODE == MODE_FP32X3) ? 3 : 4) norm_act_kernel(NormActArgs a) {
   constexpr bool PREC = MODE == MODE_FP32X3, H = MODE == MODE_FP16;
-  constexpr bool ADD_PAIR = ADD == 2 || (ADD && PREC), ADD_H = H && ADD == 1;  // residual: hi + lo bf16 pair / fp16
+  constexpr bool ADD_PAIR = ADD && PREC, ADD_H = H;
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;  // n*chunks + chunk
@@ -403,7 +404,8 @@ __global__ void __launch_bounds__(NORM_THREADS, (ADD || MODE == MODE_FP32X3) ? 3
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
-        store_split<H>(a.out, PREC ? a.out_lo : nullptr, plane * vox + v, f);
+        if (PREC && a.out_single_h) reinterpret_cast<BF8*>(a.out)[plane * vox + v] = float_to_bf8<true>(f);
+        else store_split<H>(a.out, PREC ? a.out_lo : nullptr, plane * vox + v, f);
       }
     }
   }
@@ -413,10 +415,10 @@ __global__ void __launch_bounds__(NORM_THREADS, (ADD || MODE == MODE_FP32X3) ? 3
 // (dz, dy) voxels at its x (lanes run along x: every load/store instruction covers 512 contiguous bytes) and completes
 // the pool with its x^1 neighbour through a shuffle; the pooled tensor is built from the ROUNDED outputs (16-bit, or the
 // hi + lo sum in fp32x3 mode) so that pooled == maxpool(out) exactly.
-template <int ADD, int MODE>
+template <bool ADD, int MODE>
 __global__ void __launch_bounds__(NORM_THREADS, MODE == MODE_FP32X3 ? 2 : 3) norm_act_pool_kernel(NormActArgs a) {
   constexpr bool PREC = MODE == MODE_FP32X3, H = MODE == MODE_FP16;
-  constexpr bool ADD_PAIR = ADD == 2 || (ADD && PREC), ADD_H = H && ADD == 1;
+  constexpr bool ADD_PAIR = ADD && PREC, ADD_H = H;
   __shared__ float sc[8], sh[8], bi[8];
   __shared__ double scratch[256];
   const int plane = blockIdx.y;
@@ -476,11 +478,17 @@ __global__ void __launch_bounds__(NORM_THREADS, MODE == MODE_FP32X3 ? 2 : 3) nor
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += g[j];
         }
-        const BF8 o = float_to_bf8<H>(f);
+        const bool single_h = PREC && a.out_single_h;  // warp-uniform
+        const BF8 o = single_h ? float_to_bf8<true>(f) : float_to_bf8<H>(f);
         out[vv[k]] = o;
         float r[8];
-        bf8_to_float<H>(o, r);
-        if constexpr (PREC) {
+        if (single_h) {  // the pooled pair is formed from the un-rounded values (the reference pools fp32 activations)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = f[j];
+        } else {
+          bf8_to_float<H>(o, r);
+        }
+        if (PREC && !single_h) {
           float d[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) d[j] = f[j] - r[j];
