@@ -59,7 +59,8 @@ SIGNATURES = {
     "dunet_crop_window": (c_int32, [c_void_p, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "dunet_crop_windows": (c_int32, [c_void_p, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p]),
     "dunet_infer_windows": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p, c_uint64, POINTER(c_int64),
-                                      c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "dunet_infer_flush": (c_int32, [c_void_p, c_void_p]),
     "dunet_stitch_add": (c_int32, [c_void_p, POINTER(c_int32), c_int32, c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "dunet_finalize": (c_int32, [c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dunet_stitch_add_weighted": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), c_int32, c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),

@@ -317,7 +317,7 @@ struct Slot {
 };
 
 struct WsLayout {
-  size_t in_pack, raw, mid, partial, ss, splitk, affine, x_t, acc, image, total;
+  size_t in_pack, raw, mid, partial, ss, splitk, affine, x_t, acc, acc2, image, total;
   size_t emb[5], epool[5], x[5], dpool[5], up[5], u[5];
 };
 
@@ -352,6 +352,17 @@ struct dunet_plan {
   // (normalise, final/DDIM, transposed conv) overlap the tensor-core-bound convolutions of the other
   cudaStream_t half_stream[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  // deferred (pipelined) dunet_infer_windows: the sub-batches run on the internal streams WITHOUT joining the caller's
+  // stream; the stitch kernels run in window order on a third internal stream; dunet_infer_flush() joins.  Each half
+  // alternates between two accumulator buffers so that its next batch never waits for the stitch of the previous one.
+  cudaStream_t stitch_stream = nullptr;
+  cudaEvent_t ev_done[4] = {nullptr, nullptr, nullptr, nullptr};      // half h finished the DDIM steps of its current batch
+  cudaEvent_t ev_stitched[4][2] = {};                                 // the stitch kernels reading acc buffer f of half h are done
+  bool stitched_valid[4][2] = {};
+  int acc_flip[4] = {0, 0, 0, 0};
+  cudaEvent_t ev_stitch_tail = nullptr;
+  bool async_pending = false;
+  int async_B0 = 0;
   int num_sms = 0;
   mutable Prof prof;  // per-plan launch profiler (dunet_profile_*)
   // timesteps passed to dunet_denoise_step that are not one shared schedule entry (training-style calls, per-sample t):
@@ -491,6 +502,7 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
   const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);  // voxel-major DDIM state, classes padded to the MMA column tiles
   L.x_t = take((size_t)B * CP * p->V[0] * sizeof(float));
   L.acc = take((size_t)B * CP * p->V[0] * sizeof(float));
+  L.acc2 = take((size_t)B * CP * p->V[0] * sizeof(float));  // second accumulator of the pipelined window loop
   L.image = take((size_t)B * p->cfg.in_channels * p->V[0] * sizeof(float));  // cropped windows (dunet_infer_windows)
   for (int l = 0; l < 5; ++l) {
     L.emb[l] = take(act(p->fp[l], l));
@@ -861,6 +873,16 @@ static int check_call(const dunet_plan* p, int B, const void* ws) {
   return 0;
 }
 
+// Work of a deferred dunet_infer_windows may still be in flight on the internal streams: every other entry point that
+// touches the workspace first makes the caller's stream wait for it (a device-side wait, no host synchronisation).
+static int drain_async(dunet_plan* p, cudaStream_t st) {
+  if (p && p->async_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_stitch_tail, 0));  // the stitch stream waited for every half's ev_done
+    p->async_pending = false;
+  }
+  return 0;
+}
+
 static int launch_pack(const dunet_plan* p, const float* src0, int c0, const float* src1, int c1, Act dst, int c_pad,
                        long long vox, int B, cudaStream_t st) {
   DUNET_FMT(fmt_h(p, dst.lo != nullptr), launch_k(pack_c8_kernel<HF>, dim3(grid_for((long long)B * (c_pad / 8) * vox, 256)), dim3(256), 0, st, src0, c0, src1, c1,
@@ -1130,6 +1152,13 @@ void dunet_plan_destroy(dunet_plan* p) {
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
   }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->stitch_stream) cudaStreamDestroy(p->stitch_stream);
+  if (p->ev_stitch_tail) cudaEventDestroy(p->ev_stitch_tail);
+  for (int i = 0; i < 4; ++i) {
+    if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+    for (int f = 0; f < 2; ++f)
+      if (p->ev_stitched[i][f]) cudaEventDestroy(p->ev_stitched[i][f]);
+  }
   delete p;
 }
 
@@ -1270,6 +1299,12 @@ int dunet_plan_commit(dunet_plan* p, void* stream) {
       CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->stitch_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_stitch_tail, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+      for (int f = 0; f < 2; ++f) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_stitched[i][f], cudaEventDisableTiming));
+    }
   }
   CUDA_TRY(cudaStreamSynchronize(st));  // host vector above must outlive the copy; commit is a setup-time call
   p->committed = true;
@@ -1290,12 +1325,14 @@ int dunet_encode(dunet_plan* p, const float* image, int32_t B, void* workspace, 
   TRY(check_call(p, B, workspace));
   if (!image || !aligned16(image)) return fail(DUNET_E_INVALID, "image must be a 16-byte aligned device pointer");
   p->emb_B = B; p->emb_dual = false;
+  TRY(drain_async(p, static_cast<cudaStream_t>(stream)));
   return encode_impl(p, image, B, static_cast<uint8_t*>(workspace), ws_layout(p, B), static_cast<cudaStream_t>(stream));
 }
 
 int dunet_get_embedding(dunet_plan* p, int32_t level, float* out, int32_t B, void* workspace, void* stream) {
   TRY(check_call(p, B, workspace));
   if (level < 0 || level > 4 || !out) return fail(DUNET_E_INVALID, "bad level / NULL out");
+  TRY(drain_async(p, static_cast<cudaStream_t>(stream)));
   const WsLayout L = ws_layout(p, B);
   const Act e = ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B);
   DUNET_FMT(fmt_h(p, e.lo != nullptr), unpack_c8_kernel<HF><<<grid_for((long long)B * (p->fp[level] / 8) * p->V[level], 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -1307,6 +1344,7 @@ int dunet_get_embedding(dunet_plan* p, int32_t level, float* out, int32_t B, voi
 int dunet_set_embedding(dunet_plan* p, int32_t level, const float* in, int32_t B, void* workspace, void* stream) {
   TRY(check_call(p, B, workspace));
   if (level < 0 || level > 4 || !in) return fail(DUNET_E_INVALID, "bad level / NULL in");
+  TRY(drain_async(p, static_cast<cudaStream_t>(stream)));
   p->emb_B = B; p->emb_dual = false;
   const WsLayout L = ws_layout(p, B);
   return launch_pack(p, in, p->fr[level], nullptr, 0, ws_act(p, static_cast<uint8_t*>(workspace), L.emb[level], p->fp[level], level, B),
@@ -1318,6 +1356,7 @@ int dunet_denoise_step(dunet_plan* p, const float* x_t, const float* image, cons
   TRY(check_call(p, B, workspace));
   if (!x_t || !image || !logits_out || !t_original) return fail(DUNET_E_INVALID, "NULL tensor argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TRY(drain_async(p, st));
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const WsLayout L = ws_layout(p, B);
   // one timestep shared by the batch and present in the respaced schedule (the inference call): its precomputed row
@@ -1370,11 +1409,11 @@ struct NoiseSrc {
 // initialisation, the N DDIM steps.  Leaves sum_k clamp(x0_k) in ws.acc and the last sample in ws.x_t, both voxel-major.
 // per_step_stride = elements between consecutive steps in per_step_logits (the FULL batch size when halves are used).
 static int ddim_core(dunet_plan* p, const float* image, const NoiseSrc& nz, int id0, float* per_step_logits, size_t per_step_stride,
-                     int B, int run_encoder, int zero_acc, uint8_t* ws, cudaStream_t st) {
+                     int B, int run_encoder, int zero_acc, uint8_t* ws, cudaStream_t st, int acc_sel = 0) {
   const WsLayout L = ws_layout(p, B);
   const int CP = p->C <= 8 ? 8 : (p->C <= 16 ? 16 : 32);
   float* x_t = reinterpret_cast<float*>(ws + L.x_t);   // voxel-major [B][vox][CP]
-  float* acc = reinterpret_cast<float*>(ws + L.acc);
+  float* acc = reinterpret_cast<float*>(ws + (acc_sel ? L.acc2 : L.acc));
   if (run_encoder) TRY(encode_impl(p, image, B, ws, L, st));
   const Act in_pack = ws_act(p, ws, L.in_pack, p->in_pad, 0, B);
   for (int b0 = 0; b0 < B; b0 += INIT_MAX_B) {  // x_t = noise, acc = 0, first conv input = [noise, image] in one pass
@@ -1453,6 +1492,7 @@ int dunet_ddim_sample(dunet_plan* p, const float* image, const float* noise, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   const size_t per_step_stride = (size_t)B * p->C * p->V[0];
+  TRY(drain_async(p, st));
   if (!use_dual(p, B, run_encoder))
     return ddim_sample_impl(p, image, noise, acc_out, per_step_logits, per_step_stride, final_x, B, run_encoder, out_scale,
                             out_accumulate, ws, st);
@@ -1525,7 +1565,7 @@ int dunet_crop_windows(const float* volume, const int32_t v[3], float* patches, 
 
 int dunet_infer_windows(dunet_plan* p, const float* volume, const int32_t v[3], const int32_t* starts, int32_t B,
                         const float* noise, uint64_t seed, const int64_t* noise_ids, int32_t ensemble, float* out_volume,
-                        float* count_volume, const float* weights, void* workspace, void* stream) {
+                        float* count_volume, const float* weights, int32_t deferred, void* workspace, void* stream) {
   TRY(check_call(p, B, workspace));
   if (!volume || !v || !starts || !out_volume) return fail(DUNET_E_INVALID, "NULL argument");
   if (!noise && !noise_ids) return fail(DUNET_E_INVALID, "either noise or noise_ids must be given");
@@ -1541,46 +1581,85 @@ int dunet_infer_windows(dunet_plan* p, const float* volume, const int32_t v[3], 
   const int B0 = (B + ns - 1) / ns;
   const WsLayout L0 = ws_layout(p, B0);
   const size_t sub_ws = dual ? L0.total : 0;
-  // window crop: one launch per sub-batch, into that sub-batch's workspace
-  for (int h = 0; h < ns; ++h) {
+  const bool pipe = dual && deferred;
+  // Work of an earlier deferred call may still be running on the internal streams.  It only has to be waited for when
+  // this call cannot simply queue behind it on the same streams with the same workspace partition.
+  if (!pipe || B0 != p->async_B0) TRY(drain_async(p, st));
+  const float scale = 1.f / (float)ensemble;
+  auto stitch = [&](int b, const float* acc_base, cudaStream_t ss) -> int {
+    const int32_t* s = starts + 3 * b;
+    if (PROF_ON) prof_of(p)->bytes[PROF_GLUE] += (double)p->V[0] * (4.0 * CP + 8.0 * p->C);
+    TRY(prof_begin(PROF_GLUE, ss));
+    launch_k(stitch_from_vm_kernel, dim3(grid_for(p->V[0], 256, 148 * 8)), dim3(256), 0, ss, out_volume, count_volume, acc_base, weights, p->C, CP,
+             v[0], v[1], v[2], pd[0], pd[1], pd[2], s[0], s[1], s[2], scale);
+    LAUNCH_CHECK();
+    TRY(prof_end(ss));
+    return 0;
+  };
+  auto run_half = [&](int h, cudaStream_t hs, int acc_sel) -> int {
     const int b0 = h * B0, nb = std::min(B0, B - b0);
-    if (nb <= 0) break;
     const WsLayout L = ws_layout(p, nb);
-    TRY(crop_batch(p, volume, v, reinterpret_cast<float*>(ws + h * sub_ws + L.image), pd, starts + 3 * b0, nb, st));
-  }
-  if (dual) CUDA_TRY(cudaEventRecord(p->ev_fork, st));
-  for (int h = 0; h < ns; ++h) {
-    const int b0 = h * B0, nb = std::min(B0, B - b0);
-    if (nb <= 0) break;
-    const WsLayout L = ws_layout(p, nb);
-    cudaStream_t hs = dual ? p->half_stream[h] : st;
-    if (dual) CUDA_TRY(cudaStreamWaitEvent(hs, p->ev_fork, 0));
-    const float* image = reinterpret_cast<const float*>(ws + h * sub_ws + L.image);
+    float* image = reinterpret_cast<float*>(ws + h * sub_ws + L.image);
+    TRY(crop_batch(p, volume, v, image, pd, starts + 3 * b0, nb, hs));  // window crop: one launch per sub-batch
     for (int r = 0; r < ensemble; ++r) {  // BASELINE config 4: R independent noise draws, summed; the encoder runs once
       NoiseSrc nz;
       nz.given = noise ? noise + ((size_t)r * B + b0) * p->C * p->V[0] : nullptr;
       nz.seed = seed; nz.ids = noise_ids; nz.draw = r;
-      TRY(ddim_core(p, image, nz, b0, nullptr, 0, nb, r == 0, r == 0, ws + h * sub_ws, hs));
+      TRY(ddim_core(p, image, nz, b0, nullptr, 0, nb, r == 0, r == 0, ws + h * sub_ws, hs, acc_sel));
     }
-    if (dual) CUDA_TRY(cudaEventRecord(p->ev_join[h], hs));
-  }
-  if (dual)
-    for (int h = 0; h < ns && h * B0 < B; ++h) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[h], 0));
-  // stitching, window by window in the caller's order (MONAI's): fp32 sums are formed in the oracle's order
-  const float scale = 1.f / (float)ensemble;
-  for (int b = 0; b < B; ++b) {
-    const int h = b / B0, j = b - h * B0, nb = std::min(B0, B - h * B0);
+    return 0;
+  };
+  auto acc_of = [&](int h, int j, int acc_sel) -> const float* {
+    const int nb = std::min(B0, B - h * B0);
     const WsLayout L = ws_layout(p, nb);
-    const float* acc = reinterpret_cast<const float*>(ws + h * sub_ws + L.acc) + (size_t)j * p->V[0] * CP;
-    const int32_t* s = starts + 3 * b;
-    if (PROF_ON) prof_of(p)->bytes[PROF_GLUE] += (double)p->V[0] * (4.0 * CP + 8.0 * p->C);
-    TRY(prof_begin(PROF_GLUE, st));
-    launch_k(stitch_from_vm_kernel, dim3(grid_for(p->V[0], 256, 148 * 8)), dim3(256), 0, st, out_volume, count_volume, acc, weights, p->C, CP,
-             v[0], v[1], v[2], pd[0], pd[1], pd[2], s[0], s[1], s[2], scale);
-    LAUNCH_CHECK();
-    TRY(prof_end(st));
+    return reinterpret_cast<const float*>(ws + h * sub_ws + (acc_sel ? L.acc2 : L.acc)) + (size_t)j * p->V[0] * CP;
+  };
+  if (!dual) {
+    TRY(run_half(0, st, 0));
+    for (int b = 0; b < B; ++b) TRY(stitch(b, acc_of(0, b, 0), st));  // MONAI's window order: fp32 sums in the oracle's order
+    return 0;
   }
+  CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+  if (!pipe) {
+    // sub-batches on the internal streams, joined back into the caller's stream before the stitching
+    for (int h = 0; h < ns && h * B0 < B; ++h) {
+      CUDA_TRY(cudaStreamWaitEvent(p->half_stream[h], p->ev_fork, 0));
+      TRY(run_half(h, p->half_stream[h], 0));
+      CUDA_TRY(cudaEventRecord(p->ev_join[h], p->half_stream[h]));
+    }
+    for (int h = 0; h < ns && h * B0 < B; ++h) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join[h], 0));
+    for (int b = 0; b < B; ++b) TRY(stitch(b, acc_of(b / B0, b % B0, 0), st));
+    return 0;
+  }
+  // ---- deferred: nothing is joined into the caller's stream (dunet_infer_flush does that).  A half only waits for
+  // (a) the caller's earlier work (ev_fork) and (b) the stitch kernels that last read the accumulator buffer it is
+  // about to overwrite -- two calls back, so consecutive calls keep both internal streams busy without bubbles.
+  CUDA_TRY(cudaStreamWaitEvent(p->stitch_stream, p->ev_fork, 0));
+  for (int h = 0; h < ns && h * B0 < B; ++h) {
+    cudaStream_t hs = p->half_stream[h];
+    const int f = p->acc_flip[h];
+    CUDA_TRY(cudaStreamWaitEvent(hs, p->ev_fork, 0));
+    if (p->stitched_valid[h][f]) CUDA_TRY(cudaStreamWaitEvent(hs, p->ev_stitched[h][f], 0));
+    TRY(run_half(h, hs, f));
+    CUDA_TRY(cudaEventRecord(p->ev_done[h], hs));
+  }
+  for (int h = 0; h < ns && h * B0 < B; ++h) {  // halves hold contiguous window ranges: h = 0 first keeps MONAI's order
+    const int f = p->acc_flip[h], nb = std::min(B0, B - h * B0);
+    CUDA_TRY(cudaStreamWaitEvent(p->stitch_stream, p->ev_done[h], 0));
+    for (int j = 0; j < nb; ++j) TRY(stitch(h * B0 + j, acc_of(h, j, f), p->stitch_stream));
+    CUDA_TRY(cudaEventRecord(p->ev_stitched[h][f], p->stitch_stream));
+    p->stitched_valid[h][f] = true;
+    p->acc_flip[h] = f ^ 1;
+  }
+  CUDA_TRY(cudaEventRecord(p->ev_stitch_tail, p->stitch_stream));
+  p->async_pending = true;
+  p->async_B0 = B0;
   return 0;
+}
+
+int dunet_infer_flush(dunet_plan* p, void* stream) {
+  if (!p) return fail(DUNET_E_INVALID, "plan is NULL");
+  return drain_async(p, static_cast<cudaStream_t>(stream));
 }
 
 int dunet_stitch_add(float* out_volume, const int32_t v[3], int32_t channels, const float* patch, const int32_t pd[3],

@@ -115,9 +115,11 @@ def exchange_and_finalize(buf, dst: int = 0, want_blended: bool = True):
     from .inference import StitchBuffers
 
     world = _world()
+    buf.sync()  # pipelined window work must be complete (on this stream) before the exchange reads the partial volume
     if world > 1 and buf.channels % world == 0 and buf.mode == "constant":
         mine = StitchBuffers.__new__(StitchBuffers)
         mine.vol, mine.roi, mine.mode, mine.counts, mine._finalized = buf.vol, buf.roi, buf.mode, buf.counts, False
+        mine._pending_model, mine._keepalive = None, []
         mine.channels = buf.channels // world
         mine.out = reduce_scatter_channels(buf.out)
         blended_c, binary_c, _ = mine.finalize(binary=True)

@@ -177,10 +177,19 @@ int dunet_crop_windows(const float* volume, const int32_t vol_dims[3], float* pa
  *              draw): a window's noise does not depend on batching, rank or launch order
  *   noise_ids  HOST [batch] stream id per window (e.g. its global index in the volume's window list); needed if noise == NULL
  *   ensemble   R >= 1 independent draws averaged (BASELINE config 4; R = 1 is the reference)
- *   weights / count_volume   both NULL: constant blend.  Otherwise MONAI mode="gaussian": out += w * pred, count += w. */
+ *   weights / count_volume   both NULL: constant blend.  Otherwise MONAI mode="gaussian": out += w * pred, count += w.
+ *   deferred   0: everything is ordered on `stream` when the call returns (like every other entry point).
+ *              1: PIPELINED -- with DUNET_FLAG_DUAL_STREAM the sub-batches run on the plan's internal streams and the
+ *              stitch kernels on a third one, none of them joined into `stream`: consecutive calls keep both sub-batch
+ *              streams busy (each alternates between two accumulator buffers, so it never waits for the other half or
+ *              for the stitching of its previous batch).  The caller must keep volume / noise / out_volume alive and
+ *              untouched until dunet_infer_flush(plan, stream), which makes `stream` wait for all deferred work.  Other
+ *              entry points of the same plan wait for deferred work by themselves.  Results are bit-identical. */
 int dunet_infer_windows(dunet_plan* plan, const float* volume, const int32_t vol_dims[3], const int32_t* starts,
                         int32_t batch, const float* noise, uint64_t seed, const int64_t* noise_ids, int32_t ensemble,
-                        float* out_volume, float* count_volume, const float* weights, void* workspace, void* stream);
+                        float* out_volume, float* count_volume, const float* weights, int32_t deferred, void* workspace,
+                        void* stream);
+int dunet_infer_flush(dunet_plan* plan, void* stream);
 /* counts_d/h/w: device int32 arrays, number of windows covering each coordinate along that axis (the window grid is a
  * Cartesian product so count(z,y,x) = counts_d[z]*counts_h[y]*counts_w[x]).  binary/argmax_labels nullable. */
 int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channels, const int32_t* counts_d,
