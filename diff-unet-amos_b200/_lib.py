@@ -87,19 +87,25 @@ _lib = None
 
 
 def load(build_if_missing: bool = True) -> ctypes.CDLL:
-    """Load (building in-tree with nvcc if absent) the CUDA library.  Raises if that is impossible."""
+    """Load the CUDA library, (re)building it in-tree with nvcc first when it is missing or older than its sources (the
+    build is a no-op when the source digest matches the stamp; it is serialised across processes by a file lock and the
+    .so is replaced atomically, so concurrent ranks never dlopen a half-written file).  Raises if that is impossible."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise ImportError(f"{LIB_PATH} is missing and there is no non-CUDA fallback; run diff-unet-amos_b200/build.py")
+    if build_if_missing:
         import importlib.util
 
         spec = importlib.util.spec_from_file_location("_dunet_build", os.path.join(HERE, "build.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        mod.build()
+        try:
+            mod.build()
+        except Exception:
+            if not os.path.exists(LIB_PATH):  # no compiler on this box: a prebuilt library (it travels with the tree) is fine
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing and there is no non-CUDA fallback; run diff-unet-amos_b200/build.py")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

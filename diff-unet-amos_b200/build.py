@@ -44,22 +44,37 @@ def nvcc_path() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    import fcntl
+    import tempfile
+
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest
+
+    if not force and fresh():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lcuda" if False else "-lcudart_static"]
-    cmd = [c for c in cmd if c]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libdunet_b200.so")
-    if verbose:
-        print(log)
-    with open(STAMP, "w") as fh:
-        fh.write(digest)
+    with open(os.path.join(HERE, ".libdunet_b200.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)  # one builder at a time (torchrun / mp.spawn ranks start together)
+        if not force and fresh():          # another process built it while we waited
+            return LIB
+        fd, tmp = tempfile.mkstemp(prefix=".libdunet_b200.", suffix=".so.tmp", dir=HERE)
+        os.close(fd)
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart_static"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log = res.stdout + res.stderr
+        with open(os.path.join(HERE, "build.log"), "w") as fh:
+            fh.write(" ".join(cmd) + "\n" + log)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            sys.stderr.write(log)
+            raise RuntimeError("nvcc failed building libdunet_b200.so")
+        os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new file, never a partial one
+        if verbose:
+            print(log)
+        with open(STAMP, "w") as fh:
+            fh.write(digest)
     return LIB
 
 

@@ -298,6 +298,30 @@ class DenoiserB200(nn.Module):
         return out
 
 
+class SmoothUNetDenoiserB200(DenoiserB200):
+    """``SmoothUNetDenoiser`` seam (models/smooth_unet/denoiser.py:9-61).  Its ``forward`` (:41-61) is the same
+    graph as ``BasicUNetRDenoiser.forward`` -- time embedding, cat([image, x]), five TwoConv levels + encoder residuals, four
+    UpCat blocks, final 1x1x1 conv -- so it runs on the same kernels; this class only mirrors the keyword order of the
+    reference signature ``forward(x, t, embeddings=None, image=None)``.
+
+    ``norm``: the reference class defaults to ``("layer", {"affine": True})`` (:17).  MONAI's ``get_norm_layer`` turns that
+    into ``nn.LayerNorm(affine=True)`` -- LayerNorm has neither a ``num_features`` nor an ``affine`` argument and needs a
+    ``normalized_shape`` the factory never supplies -- so the default cannot be constructed (TypeError) and no reference
+    behaviour exists to match.  Only ``norm="instance"`` (what BasicUNetRDenoiser uses, denoiser.py:206-209) is accepted."""
+
+    def __init__(self, owner, norm="instance", smoothing: bool = False):
+        name = norm[0] if isinstance(norm, (tuple, list)) else norm
+        if str(name).lower() != "instance":
+            raise NotImplementedError(
+                f"norm={norm!r}: the reference's default ('layer') is not constructible through MONAI's norm factory "
+                "(nn.LayerNorm(affine=True) raises); only the instance-norm graph is defined")
+        super().__init__(owner)
+        self.smoothing = smoothing
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, embeddings=None, image: torch.Tensor = None) -> torch.Tensor:
+        return super().forward(x, t, image=image, embeddings=embeddings)
+
+
 class SampleDiffusionB200:
     """``SpacedDiffusion`` seam for sampling: tables + ``ddim_sample_loop`` (gaussian_diffusion.py:626-665)."""
 
@@ -373,6 +397,8 @@ class DiffUNetB200(nn.Module):
         # expose parameters under the reference's top-level names: embed_model.* and model.*
         self.add_module("embed_params", holder._modules["embed_model"])
         self.add_module("model_params", holder._modules["model"])
+        self._register_state_dict_hook(DiffUNetB200._rename_on_save)
+        self.register_load_state_dict_pre_hook(DiffUNetB200._rename_on_load)
         object.__setattr__(self, "_rt", _Runtime(self))
         object.__setattr__(self, "_emb_keepalive", None)
         object.__setattr__(self, "embed_model", EncoderB200(self))
@@ -402,22 +428,31 @@ class DiffUNetB200(nn.Module):
         return self
 
     # ---- checkpoint keys: "embed_model.*" / "model.*" exactly like the reference ---------------------------------
-    def state_dict(self, *args, **kwargs):
-        sd = super().state_dict(*args, **kwargs)
-        out = type(sd)()
-        for k, v in sd.items():
-            out[k.replace("embed_params.", "embed_model.", 1).replace("model_params.", "model.", 1)] = v
-        return out
+    # Implemented with state-dict hooks so that it also holds when this module is a sub-module (nn.DataParallel /
+    # DistributedDataParallel wrap it as ``module.``: the parent passes ``destination`` and ``prefix`` and ignores return values).
+    @staticmethod
+    def _rename_on_save(module, state_dict, prefix, local_metadata):
+        for k in list(state_dict.keys()):
+            if k.startswith(prefix + "embed_params."):
+                state_dict[prefix + "embed_model." + k[len(prefix) + len("embed_params."):]] = state_dict.pop(k)
+            elif k.startswith(prefix + "model_params."):
+                state_dict[prefix + "model." + k[len(prefix) + len("model_params."):]] = state_dict.pop(k)
+        return state_dict
+
+    @staticmethod
+    def _rename_on_load(module, state_dict, prefix, *args):
+        for k in list(state_dict.keys()):
+            if k.startswith(prefix + "embed_model."):
+                state_dict[prefix + "embed_params." + k[len(prefix) + len("embed_model."):]] = state_dict.pop(k)
+            elif k.startswith(prefix + "model."):
+                state_dict[prefix + "model_params." + k[len(prefix) + len("model."):]] = state_dict.pop(k)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
-        remapped = {}
-        for k, v in state_dict.items():
-            if k.startswith("embed_model."):
-                k = "embed_params." + k[len("embed_model."):]
-            elif k.startswith("model."):
-                k = "model_params." + k[len("model."):]
-            remapped[k] = v
-        return super().load_state_dict(remapped, strict=strict, **kwargs)
+        # checkpoints saved from nn.DataParallel / DDP carry a "module." prefix (the reference saves self.model.state_dict()
+        # of the wrapped module in multi-GPU training, light_training); accept both
+        if state_dict and all(k.startswith("module.") for k in state_dict):
+            state_dict = type(state_dict)((k[len("module."):], v) for k, v in state_dict.items())
+        return super().load_state_dict(dict(state_dict), strict=strict, **kwargs)
 
     def __del__(self):
         try:

@@ -707,3 +707,19 @@ def test_uncertainty_weighted_step_fusion():
                 for r in range(R)]
         ref = op.uncertainty_fuse(torch.stack([torch.stack(r["model_outputs"]) for r in runs]))
     assert rel_l2(got.cpu(), ref) < FP16_TOL
+
+
+def test_smooth_unet_denoiser_seam():
+    """SmoothUNetDenoiser.forward(x, t, embeddings=, image=) (models/smooth_unet/denoiser.py:41-61) is the BasicUNetR graph
+    with another keyword order: same kernels, same result; the unconstructible 'layer' norm default is refused."""
+    cout, S = 2, 32
+    m = _build(cout, S, SMALL, batch_max=2)
+    image, x = seeded_image((2, 1, S, S, S)).cuda(), seeded_noise((2, cout, S, S, S)).cuda()
+    t = torch.tensor([300, 40]).cuda()
+    with torch.no_grad():
+        emb = m.embed_model(image)
+        a = m.model(x, t, image=image, embeddings=emb)
+        b = pkg.SmoothUNetDenoiserB200(m)(x, t, emb, image)
+    assert torch.equal(a, b)
+    with pytest.raises(NotImplementedError, match="LayerNorm"):
+        pkg.SmoothUNetDenoiserB200(m, norm=("layer", {"affine": True}))
