@@ -286,7 +286,8 @@ def run_b200(args, cfg):
         torch.cuda.synchronize()
 
     def run_queue(volumes, on_result=None):
-        return pkg.infer_volumes_distributed(model, volumes, sw_batch_size=sw_batch, overlap=cfg["overlap"], seed=SEED, on_result=on_result)
+        return pkg.infer_volumes_distributed(model, volumes, sw_batch_size=sw_batch, overlap=cfg["overlap"], seed=SEED, on_result=on_result,
+                                             exchange=args.exchange)
 
     def my_windows_only(volume):
         """this rank's latency-mode shard of one volume, no exchange (profiled pass)"""
@@ -448,8 +449,11 @@ def run_b200(args, cfg):
             "dtype": dtype, "data": "synthetic",
             "config": {"workload": cfg["workload"], "name": args.config, "features": list(FEATURES), "classes": C, "sw_batch": sw_batch,
                        "ddim_steps": cfg["ddim"], "ensemble": ens, "windows_per_step": n_win, "volumes_per_s": value / n_win,
-                       "schedule": (f"throughput mode: window queues of {G} volume(s) sharded evenly over {world} ranks, one NCCL exchange per volume at the "
+                       "schedule": (f"throughput mode: window queues of {G} volume(s) sharded evenly over {world} ranks, one exchange per volume at the "
                                     "group boundary") if world > 1 else "single GPU, windows in batches of sw_batch",
+                       "exchange": (("fused peer-memory kernel over NVLink (dunet_finalize_peers: reduce + divide + binarise + gather; NCCL only for two "
+                                     "4-byte stream barriers per group)" if (args.exchange != "nccl" and ens == 1 and C % world == 0 and VOLUME[2] % 4 == 0)
+                                     else "NCCL reduce-scatter by channel + local finalize + gather") if world > 1 else None),
                        "dual_stream": "on (half batches on two internal streams)" if args.dual_stream else "off",
                        "l2": "inputs larger than L2 (each window streams > 1 GB of activations; no flush needed)",
                        "algorithmic_tflop_per_window": gflop_per_window / 1e3,
@@ -523,6 +527,9 @@ def main():
     ap.add_argument("--no-library-bar", action="store_true")
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32x3"],
                     help="fp16 (default, passes every north_star gate), bf16 (misses the 99.9 %% label gate), fp32x3 (fp32-class)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: how the per-rank partial volumes are combined: p2p = one fused kernel over NVLink peer memory (reduce + "
+                         "finalize + gather, dist.PeerExchange), nccl = reduce-scatter + finalize + gather collectives; auto = p2p when it applies")
     ap.add_argument("--dual-stream", type=int, default=1, help="DUNET_FLAG_DUAL_STREAM: two half batches on two internal streams (the product default)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -1751,6 +1751,59 @@ int dunet_uncertainty_fuse(const float* per_step, int32_t runs, int32_t n_steps,
   return 0;
 }
 
+// ---- CUDA IPC helpers for the peer-memory exchange (one process per GPU: a rank maps the other ranks' partial-sum
+// buffers into its own address space; NVLink peer access is enabled by the open call)
+int dunet_ipc_alloc(void** ptr, size_t bytes, uint8_t handle_out[64]) {
+  if (!ptr || !handle_out || bytes == 0) return fail(DUNET_E_INVALID, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaMalloc(ptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) {
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    return fail(DUNET_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle_out, &h, 64);
+  return 0;
+}
+int dunet_ipc_open(const uint8_t handle[64], void** ptr) {
+  if (!handle || !ptr) return fail(DUNET_E_INVALID, "NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int dunet_ipc_close(void* ptr) {
+  if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+int dunet_ipc_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFree(ptr));
+  return 0;
+}
+
+int dunet_finalize_peers(const float* const* partial_ptrs, const int32_t* slab_lo, const int32_t* slab_hi, int32_t n_src,
+                         const int32_t v[3], int32_t channel_lo, int32_t channel_hi, const int32_t* cd, const int32_t* ch,
+                         const int32_t* cw, uint8_t* binary, float* blended, void* stream) {
+  if (!partial_ptrs || !slab_lo || !slab_hi || !v || !cd || !ch || !cw || !binary) return fail(DUNET_E_INVALID, "NULL argument");
+  if (n_src < 1 || n_src > PEER_MAX_SRC) return fail(DUNET_E_INVALID, "n_src must be in [1, %d]", PEER_MAX_SRC);
+  if (channel_lo < 0 || channel_hi <= channel_lo) return fail(DUNET_E_INVALID, "bad channel range");
+  if (v[2] % 4) return fail(DUNET_E_UNSUPPORTED, "dunet_finalize_peers needs a volume width that is a multiple of 4");
+  FinalizePeersArgs a;
+  memset(&a, 0, sizeof a);
+  for (int k = 0; k < n_src; ++k) {
+    if (!partial_ptrs[k] || !aligned16(partial_ptrs[k])) return fail(DUNET_E_INVALID, "source %d is NULL or not 16-byte aligned", k);
+    a.src[k] = partial_ptrs[k]; a.lo[k] = slab_lo[k]; a.hi[k] = slab_hi[k];
+  }
+  a.n_src = n_src; a.cd = cd; a.ch = ch; a.cw = cw; a.binary = binary; a.blended = blended;
+  a.c_lo = channel_lo; a.c_hi = channel_hi; a.D = v[0]; a.H = v[1]; a.W = v[2];
+  const long long total = (long long)v[0] * v[1] * v[2] / 4 * (channel_hi - channel_lo);
+  finalize_peers_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int dunet_q_sample(const float* x_start, const float* noise_in, float* noise_out, const int64_t* t_dev, const float* sqrt_ac,
                    const float* sqrt_1mac, float* out, int32_t batch, int64_t per_sample, uint64_t seed, int64_t id0, void* stream) {
   if (!x_start || !t_dev || !sqrt_ac || !sqrt_1mac || !out || batch < 1 || per_sample < 1) return fail(DUNET_E_INVALID, "bad argument");

@@ -1284,6 +1284,54 @@ __global__ void __launch_bounds__(256) uncertainty_fuse_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU exchange fused with the finalize step, over NVLink peer memory (no NCCL on the data): rank r owns channels
+// [c_lo, c_hi) of a volume.  It READS the partial stitched sums of those channels straight out of every contributing
+// rank's buffer (peer pointers: plain ld.global over NVLink / NVSwitch; a rank only contributes the slab of dim-0 rows
+// its windows touch, the others are skipped), adds them in rank order, divides by the coverage counts, binarises
+// (sigmoid > 0.5, engine.py:179-180) and WRITES the uint8 labels into the destination rank's volume (peer store).
+// Replaces reduce-scatter + local finalize + gather: the fp32 sums cross NVLink once, only where they are non-zero.
+// thread = 4 consecutive voxels along x (16-byte loads, 4-byte stores); W % 4 == 0 required.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PEER_MAX_SRC = 16;
+struct FinalizePeersArgs {
+  const float* src[PEER_MAX_SRC];  // [C][D][H][W] fp32 partial sums of source k (local or peer memory)
+  int lo[PEER_MAX_SRC], hi[PEER_MAX_SRC];  // dim-0 rows [lo, hi) source k has contributed to
+  int n_src;
+  const int *cd, *ch, *cw;         // per-axis coverage counts (device, local)
+  uint8_t* binary;                 // [C][D][H][W] destination labels (local or peer memory)
+  float* blended;                  // optional [C][D][H][W] fp32 destination of the normalised logits, or nullptr
+  int c_lo, c_hi, D, H, W;
+};
+__global__ void __launch_bounds__(256) finalize_peers_kernel(FinalizePeersArgs a) {
+  const long long vv = (long long)a.D * a.H * a.W, q = vv / 4;
+  const long long total = q * (a.c_hi - a.c_lo);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = a.c_lo + (int)(i / q);
+    const long long v = (i % q) * 4;
+    const int x = (int)(v % a.W), y = (int)((v / a.W) % a.H), z = (int)(v / ((long long)a.W * a.H));
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool first = true;
+#pragma unroll 1
+    for (int k = 0; k < a.n_src; ++k) {
+      if (z < a.lo[k] || z >= a.hi[k]) continue;
+      const float4 t = *reinterpret_cast<const float4*>(a.src[k] + c * vv + v);
+      if (first) { s = t; first = false; }   // the first contribution is taken as is (0 + t would lose the sign of -0)
+      else { s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+    }
+    const float czy = (float)(a.cd[z] * a.ch[y]);
+    const float o[4] = {s.x / (czy * (float)a.cw[x]), s.y / (czy * (float)a.cw[x + 1]), s.z / (czy * (float)a.cw[x + 2]),
+                        s.w / (czy * (float)a.cw[x + 3])};
+    uchar4 lab;
+    lab.x = (1.f / (1.f + expf(-o[0])) > 0.5f) ? 1 : 0;
+    lab.y = (1.f / (1.f + expf(-o[1])) > 0.5f) ? 1 : 0;
+    lab.z = (1.f / (1.f + expf(-o[2])) > 0.5f) ? 1 : 0;
+    lab.w = (1.f / (1.f + expf(-o[3])) > 0.5f) ? 1 : 0;
+    *reinterpret_cast<uchar4*>(a.binary + c * vv + v) = lab;
+    if (a.blended) *reinterpret_cast<float4*>(a.blended + c * vv + v) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Per-class Dice inputs (reference metric.py:3-49 dice_coeff as used by Tester.validation_step, test.py:143-151):
 // counts[c] = { |pred_c & label_c|, |pred_c|, |label_c| } as exact 64-bit integers.  pred: uint8 {0,1} [C][vox] (the
 // binary volume finalize_kernel writes); label: uint8 or fp32 one-hot [C][vox], non-zero = foreground.

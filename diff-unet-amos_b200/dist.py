@@ -19,16 +19,27 @@ path.  Two schedules:
     exactly the same work between two exchange points.  The exchanges of a group run back to back once all its windows
     are done (never concurrently with the convolutions: a spinning NCCL kernel would take SMs away from the persistent
     one-CTA-per-SM conv kernels).
+
+In throughput mode the exchange itself is NOT an NCCL collective: ``PeerExchange`` maps every rank's partial-sum buffers
+into every other rank through CUDA IPC, and one kernel per (rank, volume) -- ``dunet_finalize_peers`` -- reads the
+contributing ranks' partial sums of its channels directly over NVLink (only the slabs their windows touched), adds them,
+divides by the counts, binarises and stores the uint8 labels straight into rank 0's volume.  The fp32 sums cross NVLink
+once, only where they are non-zero (a volume of a 4-volume queue is covered by 2-3 of the 8 ranks), instead of an 8-rank
+reduce-scatter of mostly-zero 2.7 GB buffers followed by a gather.  NCCL is used for two 4-byte all-reduces per group
+that order the streams of the ranks (all partial sums written before / all peer reads done after).
 """
 from __future__ import annotations
 
+import ctypes
 import math
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
-from .windows import shard_range, window_starts
+from . import _lib
+from .windows import axis_counts, shard_range, window_starts
 
 
 def _world() -> int:
@@ -135,6 +146,117 @@ def exchange_and_finalize(buf, dst: int = 0, want_blended: bool = True):
     return None, None
 
 
+class _RawCuda:
+    """__cuda_array_interface__ view of a raw device pointer (memory owned by the library / another process)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """Peer-memory exchange of the partial stitched volumes (see the module docstring).  Every rank owns ``slots`` partial
+    buffers [C, D, H, W] fp32 and (on ``dst``) ``label_slots`` label volumes [C, D, H, W] uint8, all allocated with
+    ``dunet_ipc_alloc`` and mapped into every other rank with ``dunet_ipc_open`` (one exchange of 64-byte handles through
+    torch.distributed at construction).  ``channels`` must be divisible by the world size, the volume width by 4."""
+
+    def __init__(self, channels: int, vol: Sequence[int], roi: Sequence[int], overlap: float, device, slots: int = 3,
+                 label_slots: int = 8, dst: int = 0):
+        self.world, self.rank, self.dst = _world(), _rank(), dst
+        self.channels, self.vol, self.roi, self.overlap = int(channels), tuple(int(v) for v in vol), tuple(roi), overlap
+        if self.channels % self.world or self.vol[2] % 4:
+            raise ValueError("PeerExchange needs channels % world == 0 and a volume width that is a multiple of 4")
+        self.device = torch.device(device)
+        self.lib = _lib.load()
+        self.vox = self.vol[0] * self.vol[1] * self.vol[2]
+        self.counts = [torch.from_numpy(c).to(self.device) for c in axis_counts(self.vol, self.roi, overlap)]
+        self._owned, self._opened = [], []
+        pbytes, lbytes = self.channels * self.vox * 4, self.channels * self.vox
+        n_lab = label_slots if self.rank == dst else 0
+        handles = np.zeros((slots + label_slots, 64), dtype=np.uint8)
+        self.partial_ptr: List[List[int]] = [[0] * slots for _ in range(self.world)]
+        self.label_ptr: List[int] = [0] * label_slots
+        with torch.cuda.device(self.device):
+            for i in range(slots + n_lab):
+                ptr = ctypes.c_void_p()
+                h = (ctypes.c_uint8 * 64)()
+                _lib.check(self.lib.dunet_ipc_alloc(ctypes.byref(ptr), pbytes if i < slots else lbytes, h))
+                self._owned.append(ptr.value)
+                handles[i] = np.frombuffer(bytes(h), dtype=np.uint8)
+                if i < slots:
+                    self.partial_ptr[self.rank][i] = ptr.value
+                else:
+                    self.label_ptr[i - slots] = ptr.value
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handles.tobytes())
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                hs = np.frombuffer(gathered[r], dtype=np.uint8).reshape(slots + label_slots, 64)
+                rng = list(range(slots)) + (list(range(slots, slots + label_slots)) if r == dst else [])
+                for i in rng:
+                    ptr = ctypes.c_void_p()
+                    h = (ctypes.c_uint8 * 64).from_buffer_copy(hs[i].tobytes())
+                    _lib.check(self.lib.dunet_ipc_open(h, ctypes.byref(ptr)))
+                    self._opened.append(ptr.value)
+                    if i < slots:
+                        self.partial_ptr[r][i] = ptr.value
+                    else:
+                        self.label_ptr[i - slots] = ptr.value
+            # torch views of this rank's own buffers
+            self.partial = [torch.as_tensor(_RawCuda(self.partial_ptr[self.rank][i], pbytes), device=self.device).view(torch.float32)
+                            .view((self.channels,) + self.vol) for i in range(slots)]
+            self.labels = ([torch.as_tensor(_RawCuda(self.label_ptr[i], lbytes), device=self.device).view((self.channels,) + self.vol)
+                            for i in range(label_slots)] if self.rank == dst else [])
+        self._flag = torch.zeros(1, device=self.device)
+        self.slots, self.label_slots = slots, label_slots
+
+    def barrier(self) -> None:
+        """Stream-ordered barrier across the ranks: everything enqueued before it on every rank's current stream is
+        complete (and visible to peers) before anything enqueued after it on any rank starts."""
+        dist.all_reduce(self._flag)
+
+    def finalize(self, sources: Sequence[Tuple[int, int, int, int]], label_slot: int) -> None:
+        """sources: (rank, partial slot, first dim-0 row, one past the last row) of every rank that contributed to the
+        volume, in rank order.  This rank reduces + finalizes its channel range into rank ``dst``'s label slot."""
+        per = self.channels // self.world
+        n = len(sources)
+        ptrs = (ctypes.c_void_p * n)(*[self.partial_ptr[r][s] for r, s, _, _ in sources])
+        lo = (ctypes.c_int32 * n)(*[a for _, _, a, _ in sources])
+        hi = (ctypes.c_int32 * n)(*[b for _, _, _, b in sources])
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dunet_finalize_peers(ptrs, lo, hi, n, _lib.i32x3(self.vol), self.rank * per, (self.rank + 1) * per,
+                                                     ctypes.c_void_p(self.counts[0].data_ptr()), ctypes.c_void_p(self.counts[1].data_ptr()),
+                                                     ctypes.c_void_p(self.counts[2].data_ptr()), ctypes.c_void_p(self.label_ptr[label_slot]),
+                                                     None, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier()
+        for p in self._opened:
+            self.lib.dunet_ipc_close(ctypes.c_void_p(p))
+        self._opened = []
+        if dist.is_initialized():
+            dist.barrier()
+        for p in self._owned:
+            self.lib.dunet_ipc_free(ctypes.c_void_p(p))
+        self._owned = []
+
+
+_PEER_CACHE: Dict[tuple, PeerExchange] = {}
+
+
+def peer_exchange_for(channels: int, vol, roi, overlap: float, device, dst: int = 0) -> Optional[PeerExchange]:
+    """The process-wide PeerExchange for this geometry (created on first use, collectively), or None when the fused
+    peer-memory path does not apply (single rank, CPU / gloo tests, channels not divisible by the world size, ...)."""
+    if _world() == 1 or torch.device(device).type != "cuda" or channels % _world() or vol[2] % 4 or dist.get_backend() != "nccl":
+        return None
+    key = (channels, tuple(vol), tuple(roi), float(overlap), str(device), dst, _world())
+    if key not in _PEER_CACHE:
+        _PEER_CACHE[key] = PeerExchange(channels, vol, roi, overlap, device, dst=dst)
+    return _PEER_CACHE[key]
+
+
 @torch.no_grad()
 def infer_volume_distributed(model, image: torch.Tensor, sw_batch_size: int = 4, overlap: float = 0.25,
                              noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None, dst: int = 0,
@@ -169,13 +291,15 @@ def infer_volume_distributed(model, image: torch.Tensor, sw_batch_size: int = 4,
 @torch.no_grad()
 def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_size: int = 4, overlap: float = 0.25, dst: int = 0,
                               seed: int = 0, on_result: Optional[Callable[[int, torch.Tensor], None]] = None,
-                              noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None):
+                              noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None, exchange: str = "auto"):
     """Throughput mode: ``images`` (a sequence of [1, 1, D, H, W] volumes of ONE shape, already >= the roi on every axis,
     present on every rank) are processed as window queues of G volumes (``queue_group_size``) so that every rank does the
     same number of windows between two exchange points.  ``on_result(volume_index, binary_labels_uint8)`` is called on
     ``dst`` as results become available (e.g. to start the D2H copy); returns the list of label volumes on ``dst``.
     Window w of volume i draws its noise from the stream (``seed``, i * n_windows + w): identical to running the volumes
-    one by one through ``infer_volume_distributed`` / ``infer_volume`` with the same seed."""
+    one by one through ``infer_volume_distributed`` / ``infer_volume`` with the same seed.
+    ``exchange``: "p2p" = fused peer-memory reduce + finalize + gather (``PeerExchange``), "nccl" = reduce-scatter +
+    finalize + gather collectives, "auto" = p2p whenever it applies."""
     from .inference import StitchBuffers
 
     world, rank = _world(), _rank()
@@ -191,15 +315,25 @@ def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_si
     step = min(int(sw_batch_size), model.batch_max)
     results = []
     dev = images[0].device
+    px = peer_exchange_for(model.num_classes, vol, roi, overlap, dev, dst) if exchange in ("auto", "p2p") else None
+    if exchange == "p2p" and px is None and world > 1:
+        raise ValueError("the peer-memory exchange needs NCCL ranks on CUDA, channels % world == 0 and a width % 4 == 0")
+    if px is not None and px.label_slots < G:
+        px = None
     for g0 in range(0, len(images), G):
         grp = list(range(g0, min(g0 + G, len(images))))
         shares = queue_shares(n_win, len(grp), rank, world)
         bufs = {}
-        for v, lo, hi in shares:
+        for slot, (v, lo, hi) in enumerate(shares):
             img = images[grp[v]]
             if tuple(img.shape[2:]) != vol:
                 raise ValueError("all volumes of a queue must have the same shape")
-            buf = bufs[v] = StitchBuffers(model.num_classes, vol, roi, overlap, dev)
+            if px is not None:
+                if slot >= px.slots:
+                    raise RuntimeError("a rank's queue share spans more volumes than the peer exchange has partial buffers")
+                buf = bufs[v] = StitchBuffers(model.num_classes, vol, roi, overlap, dev, out=px.partial[slot].zero_())
+            else:
+                buf = bufs[v] = StitchBuffers(model.num_classes, vol, roi, overlap, dev)
             bounds = list(range(lo, hi, step)) + [hi]
             if len(bounds) > 2 and bounds[-1] - bounds[-2] == 1 and step + 1 <= model.batch_max:
                 del bounds[-2]  # a single left-over window joins the previous batch instead of running alone
@@ -209,6 +343,26 @@ def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_si
                     buf.add_windows(model, img[0, 0], starts[a:b], noise=noise_fn(base + a, b - a))
                 else:
                     buf.add_windows(model, img[0, 0], starts[a:b], seed=seed, noise_ids=range(base + a, base + b))
+        if px is not None:
+            # ---- fused peer-memory exchange: every rank finalizes its channels of every volume of the group
+            for buf in bufs.values():
+                buf.sync()
+            px.barrier()  # all partial sums of the group are complete on every rank
+            for v in range(len(grp)):
+                sources = []
+                for r in range(world):
+                    for slot, (vv_, lo, hi) in enumerate(queue_shares(n_win, len(grp), r, world)):
+                        if vv_ == v:
+                            sources.append((r, slot, int(starts[lo][0]), int(starts[hi - 1][0]) + roi[0]))
+                px.finalize(sources, v)
+            px.barrier()  # all peer reads and label stores are complete: buffers may be reused, labels consumed
+            if rank == dst:
+                for v in range(len(grp)):
+                    binary = px.labels[v].clone()
+                    if on_result is not None:
+                        on_result(grp[v], binary)
+                    results.append(binary)
+            continue
         zero = None
         for v in range(len(grp)):  # the exchanges of the group, back to back, every rank takes part in every one
             buf = bufs.get(v)

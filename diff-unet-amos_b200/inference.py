@@ -31,12 +31,17 @@ class StitchBuffers:
     count map is their outer product) or an accumulated fp32 weight volume (gaussian blend)."""
 
     def __init__(self, channels: int, vol: Sequence[int], roi: Sequence[int], overlap: float, device, mode: str = "constant",
-                 sigma_scale: float = 0.125):
+                 sigma_scale: float = 0.125, out: Optional[torch.Tensor] = None):
         self.vol = tuple(int(v) for v in vol)
         self.roi = tuple(int(r) for r in roi)
         self.channels = channels
         self.mode = mode
-        self.out = torch.zeros((channels,) + self.vol, dtype=torch.float32, device=device)
+        if out is not None:  # caller-provided (already zeroed) accumulator, e.g. a CUDA-IPC buffer of the peer exchange
+            if tuple(out.shape) != (channels,) + self.vol or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError(f"out must be contiguous fp32 {(channels,) + self.vol}")
+            self.out = out
+        else:
+            self.out = torch.zeros((channels,) + self.vol, dtype=torch.float32, device=device)
         self._finalized = False
         self._pending_model = None
         self._keepalive = []

@@ -196,6 +196,26 @@ int dunet_finalize(float* out_volume, const int32_t vol_dims[3], int32_t channel
                    const int32_t* counts_h, const int32_t* counts_w, uint8_t* binary, uint8_t* argmax_labels,
                    void* stream);
 
+/* Multi-GPU: the exchange of the per-rank partial volumes FUSED with dunet_finalize, over NVLink peer memory.  The calling
+ * rank owns channels [channel_lo, channel_hi).  partial_ptrs (HOST array of n_src device pointers, each the [C, D, H, W] fp32
+ * partial sum volume of one contributing rank -- its own memory or a CUDA-IPC peer mapping) are read directly by the kernel;
+ * source k is only read for dim-0 rows [slab_lo[k], slab_hi[k]) (the slab its windows touched, HOST arrays).  The kernel
+ * adds the contributions in array order, divides by the coverage counts, binarises and stores the uint8 labels (and, if
+ * `blended` is non-NULL, the normalised fp32 logits) into `binary` / `blended`, which may live on another GPU as well.
+ * Replaces ncclReduceScatter + dunet_finalize + gather; cross-rank ordering (all partial sums complete before, all reads
+ * complete after) is the caller's job (dist.py uses two tiny NCCL all-reduces per window-queue group as stream barriers). */
+int dunet_finalize_peers(const float* const* partial_ptrs, const int32_t* slab_lo, const int32_t* slab_hi, int32_t n_src,
+                         const int32_t vol_dims[3], int32_t channel_lo, int32_t channel_hi, const int32_t* counts_d,
+                         const int32_t* counts_h, const int32_t* counts_w, uint8_t* binary, float* blended, void* stream);
+
+/* CUDA-IPC plumbing for dunet_finalize_peers (one process per GPU): dunet_ipc_alloc = cudaMalloc + cudaIpcGetMemHandle
+ * (the 64-byte handle travels to the other ranks through torch.distributed), dunet_ipc_open maps another rank's buffer into
+ * this process with NVLink peer access enabled, dunet_ipc_close / dunet_ipc_free undo them. */
+int dunet_ipc_alloc(void** ptr, size_t bytes, uint8_t handle_out[64]);
+int dunet_ipc_open(const uint8_t handle[64], void** ptr);
+int dunet_ipc_close(void* ptr);
+int dunet_ipc_free(void* ptr);
+
 /* MONAI blend mode "gaussian" (the reference's own call uses the default constant blend): out[slices] += w * pred
  * and count[slices] += w with `weights` the [pd0, pd1, pd2] fp32 importance map of a window; dunet_finalize_weighted divides
  * by the accumulated fp32 count volume [D, H, W] and binarises like dunet_finalize. */
