@@ -723,3 +723,35 @@ def test_smooth_unet_denoiser_seam():
     assert torch.equal(a, b)
     with pytest.raises(NotImplementedError, match="LayerNorm"):
         pkg.SmoothUNetDenoiserB200(m, norm=("layer", {"affine": True}))
+
+
+def test_finalize_peers_kernel_equals_sum_then_finalize():
+    """dunet_finalize_peers (the multi-GPU exchange fused with the finalize step; on a 2+ GPU box the sources are CUDA-IPC
+    peer mappings, tests/test_gpu_multi.py) with all sources in local memory: reading three partial volumes slab-wise,
+    adding them in order, dividing by the counts and binarising must equal sum -> dunet_finalize on the same data."""
+    C, vol, roi = 4, (48, 40, 36), (32, 32, 32)
+    torch.manual_seed(8)
+    slabs = [(0, 32), (8, 40), (16, 48)]  # dim-0 rows each "rank" contributed to
+    parts = []
+    for lo, hi in slabs:
+        p = torch.zeros((C,) + vol, device="cuda")
+        p[:, lo:hi] = torch.randn(C, hi - lo, vol[1], vol[2], device="cuda")
+        parts.append(p)
+    ref_buf = pkg.StitchBuffers(C, vol, roi, 0.25, "cuda")
+    ref_buf.out.copy_((parts[0] + parts[1]) + parts[2])  # rank order
+    ref_blend, ref_bin, _ = ref_buf.finalize(binary=True)
+    lib = _lib.load()
+    counts = ref_buf.counts
+    out_bin = torch.full((C,) + vol, 7, dtype=torch.uint8, device="cuda")
+    out_blend = torch.full((C,) + vol, float("nan"), device="cuda")
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for c_lo, c_hi in ((0, 2), (2, 4)):  # two "ranks" finalize two channels each
+        ptrs = (ctypes.c_void_p * 3)(*[p.data_ptr() for p in parts])
+        lo = (ctypes.c_int32 * 3)(*[s[0] for s in slabs])
+        hi = (ctypes.c_int32 * 3)(*[s[1] for s in slabs])
+        _lib.check(lib.dunet_finalize_peers(ptrs, lo, hi, 3, _lib.i32x3(vol), c_lo, c_hi, _p(counts[0]), _p(counts[1]), _p(counts[2]),
+                                            _p(out_bin), _p(out_blend), stream))
+    torch.cuda.synchronize()
+    assert torch.equal(out_bin, ref_bin) and torch.equal(out_blend, ref_blend)
+    assert lib.dunet_finalize_peers(ptrs, lo, hi, 3, _lib.i32x3((48, 40, 34)), 0, 2, _p(counts[0]), _p(counts[1]), _p(counts[2]),
+                                    _p(out_bin), None, stream) == -4  # width % 4 != 0: DUNET_E_UNSUPPORTED
