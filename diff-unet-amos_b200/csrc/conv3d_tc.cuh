@@ -113,7 +113,6 @@ struct ConvTcArgs {
   int D, H, W;             // INPUT spatial size (the transposed conv writes a 2D x 2H x 2W volume)
   int tiles_x, tiles_y, tiles_z, n_tiles, ksplit, batch;
   long long* dbg;          // optional per-CTA clock64 timeline (8 slots per CTA)
-  int epi2;                // epilogue variant: two TMEM loads in flight per wait
 };
 
 // butterfly transpose-reduce: every lane enters with 32 values, lane l leaves with the warp-wide sum of value l
@@ -365,9 +364,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 32; ++i) st[i] = 0.f;
         const int gcol = ntile * N_TILE + j * 16;
-        auto emit = [&](int s, const float (&v)[16]) {
+#pragma unroll 1
+        for (int s = 0; s < ZT; ++s) {
           const int z = z0 + s;
           const bool ok = xy_ok && z < a.D;
+          float v[16];
+          tmem_ld16(acc + s * N_TILE + j * 16, v);
           if constexpr (MODE == MODE_CONV3) {
             const long long vofs = ((long long)z * a.H + y) * a.W + x;
             if (a.out_partial) {
@@ -412,27 +414,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
               store_split<H>(a.out, a.out_lo, o, c0);
               store_split<H>(a.out, a.out_lo, o + ovox, c1);
             }
-          }
-        };
-        if (a.epi2 && (ZT % 2 == 0)) {  // two TMEM loads in flight per wait (A/B switch DUNET_EPI2)
-#pragma unroll 1
-          for (int s = 0; s + 1 < ZT; s += 2) {
-            uint32_t r0[16], r1[16];
-            tmem_ld16_nowait(acc + s * N_TILE + j * 16, r0);
-            tmem_ld16_nowait(acc + (s + 1) * N_TILE + j * 16, r1);
-            tmem_wait_ld();
-            float v0[16], v1[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
-            emit(s, v0);
-            emit(s + 1, v1);
-          }
-        } else {
-#pragma unroll 1
-          for (int s = 0; s < ZT; ++s) {
-            float v[16];
-            tmem_ld16(acc + s * N_TILE + j * 16, v);
-            emit(s, v);
           }
         }
         if (do_stats) red[q * (N_TILE * 2) + j * 32 + lane] = warp_reduce32(st, lane);

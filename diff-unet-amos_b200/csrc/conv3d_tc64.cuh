@@ -69,7 +69,6 @@ struct ConvTc64Args {
   const float* in_bias;
   int in_bias_n_stride;    // floats between the bias rows of consecutive samples (0: one row for the whole batch)
   float slope;
-  int epi2;                 // epilogue variant: two TMEM loads in flight per wait (A/B switch DUNET_EPI2)
 };
 
 // Static tile schedule.  Within EACH sample the tiles are dealt round-robin over the CTAs, so the set of tiles whose
@@ -362,10 +361,12 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         float st[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) st[i] = 0.f;
-        // one 16-column group of one slab: store the 16-bit outputs, accumulate the InstanceNorm sums
-        auto emit = [&](int s, const float (&v)[16]) {
+#pragma unroll 1
+        for (int s = 0; s < ZT; ++s) {
           const int z = z0 + s;
           const bool ok = xy_ok && z < a.D;
+          float v[16];
+          tmem_ld16(acc + s * 64 + j * 16, v);
           if (ok) {
             const long long o = ((long long)n * 8 + j * 2) * vox + ((long long)z * a.H + y) * a.W + x;
             float c0[8], c1[8];
@@ -382,29 +383,6 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
               st[i] += xv;
               st[16 + i] = fmaf(xv, xv, st[16 + i]);
             }
-          }
-        };
-        if (a.epi2) {
-          // two TMEM loads in flight per wait (DUNET_EPI2): the epilogue is latency-bound, not bandwidth-bound
-          static_assert(ZT % 2 == 0, "paired epilogue needs an even ZT");
-#pragma unroll 1
-          for (int s = 0; s < ZT; s += 2) {
-            uint32_t r0[16], r1[16];
-            tmem_ld16_nowait(acc + s * 64 + j * 16, r0);
-            tmem_ld16_nowait(acc + (s + 1) * 64 + j * 16, r1);
-            tmem_wait_ld();
-            float v0[16], v1[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(r0[i]); v1[i] = __uint_as_float(r1[i]); }
-            emit(s, v0);
-            emit(s + 1, v1);
-          }
-        } else {
-#pragma unroll 1
-          for (int s = 0; s < ZT; ++s) {
-            float v[16];
-            tmem_ld16(acc + s * 64 + j * 16, v);
-            emit(s, v);
           }
         }
         if (a.stats) run[j] += warp_reduce32(st, lane);

@@ -659,10 +659,6 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     memset(&b, 0, sizeof b);
     b.w = c.packed64; b.out = out.hi; b.out_lo = out.lo; b.stats = partial; b.segs = segs;
     b.D = D; b.H = H; b.W = W; b.tiles_x = g.tiles_x; b.tiles_y = g.tiles_y; b.tiles_z = g.tiles_z; b.batch = B;
-    {
-      static const int epi2 = [] { const char* e = getenv("DUNET_EPI2"); return e ? atoi(e) : 0; }();
-      b.epi2 = epi2 & 1;
-    }
     unsigned grid = 0;
     if (fuse) {
       if (c.nb1 != 0 || prec) return fail(DUNET_E_STATE, "normalise-on-load needs a single bf16 source");
@@ -681,10 +677,6 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
   a.cout = c.coutp; a.D = D; a.H = H; a.W = W;
   a.tiles_x = g.tiles_x; a.tiles_y = g.tiles_y; a.tiles_z = g.tiles_z; a.n_tiles = c.n_tiles; a.batch = B;
   a.ksplit = want_split;
-  {
-    static const int epi2 = [] { const char* e = getenv("DUNET_EPI2"); return e ? atoi(e) : 0; }();
-    a.epi2 = epi2 & 2 ? 1 : 0;
-  }
   {  // tools: stamp only the DUNET_DBG_LAUNCH-th generic conv launch since the buffer was set (default: every launch)
     static const int target = [] { const char* e = getenv("DUNET_DBG_LAUNCH"); return e ? atoi(e) : -1; }();
     a.dbg = (g_conv_dbg && (target < 0 || g_conv_dbg_count == target)) ? g_conv_dbg : nullptr;
