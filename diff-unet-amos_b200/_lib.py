@@ -110,6 +110,15 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         except Exception:
             if not os.path.exists(LIB_PATH):  # no compiler on this box: a prebuilt library (it travels with the tree) is fine
                 raise
+    alt = os.environ.get("DUNET_LIB")  # A/B timing of an alternative build of the same ABI (debugging only)
+    if alt:
+        lib = ctypes.CDLL(alt)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing and there is no non-CUDA fallback; run diff-unet-amos_b200/build.py")
     lib = ctypes.CDLL(LIB_PATH)

@@ -415,8 +415,14 @@ __global__ void __launch_bounds__(NORM_THREADS, (ADD || MODE == MODE_FP32X3) ? 3
 // (dz, dy) voxels at its x (lanes run along x: every load/store instruction covers 512 contiguous bytes) and completes
 // the pool with its x^1 neighbour through a shuffle; the pooled tensor is built from the ROUNDED outputs (16-bit, or the
 // hi + lo sum in fp32x3 mode) so that pooled == maxpool(out) exactly.
+// with the residual the kernel holds 8 independent 16-byte loads per thread: at 3 blocks / SM (<= 85 registers) ptxas spills
+// 40-52 bytes into the hot loop; 2 blocks / SM (96 registers, no spills, still 64 KB of loads in flight per SM) measured
+// 4.68 vs 4.24 TB/s on the 96^3 launches
+#ifndef DUNET_NORM_POOL_ADD_MINB
+#define DUNET_NORM_POOL_ADD_MINB 2
+#endif
 template <bool ADD, int MODE>
-__global__ void __launch_bounds__(NORM_THREADS, MODE == MODE_FP32X3 ? 2 : 3) norm_act_pool_kernel(NormActArgs a) {
+__global__ void __launch_bounds__(NORM_THREADS, MODE == MODE_FP32X3 ? 2 : (ADD ? DUNET_NORM_POOL_ADD_MINB : 3)) norm_act_pool_kernel(NormActArgs a) {
   constexpr bool PREC = MODE == MODE_FP32X3, H = MODE == MODE_FP16;
   constexpr bool ADD_PAIR = ADD && PREC, ADD_H = H;
   __shared__ float sc[8], sh[8], bi[8];
@@ -440,10 +446,10 @@ __global__ void __launch_bounds__(NORM_THREADS, MODE == MODE_FP32X3 ? 2 : 3) nor
     const bool valid = p < total;
     const int x = (int)(p % a.W), y2 = (int)((p / a.W) % H2), z2 = (int)(p / ((long long)a.W * H2));
     BF8 xin[4], ain[4], xlo[4], alo[4];
-    long long vv[4];
+    unsigned vv[4];  // voxel offsets inside one 8-channel plane (< 2^31: checked on the host), 32-bit to save registers
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      vv[k] = ((long long)(2 * z2 + (k >> 1)) * a.H + (2 * y2 + (k & 1))) * a.W + x;
+      vv[k] = ((unsigned)(2 * z2 + (k >> 1)) * (unsigned)a.H + (unsigned)(2 * y2 + (k & 1))) * (unsigned)a.W + (unsigned)x;
       if (valid) {
         xin[k] = in[vv[k]];
         if constexpr (PREC) xlo[k] = in_lo[vv[k]];
