@@ -478,7 +478,8 @@ def run_b200(args, cfg):
                                     "frac": fam_b[i] / fam_ms[i] / 1e6 / peaks["hbm_gbs"], "launches": int(fam_n[i]),
                                     "share_of_profiled_pass": fam_ms[i] / ms_prof}
                              for i, name in ((1, "normalise (IN+LeakyReLU+bias+residual+pool), launches >= 64 MB"), (2, "final 1x1 conv + DDIM update + accumulate"),
-                                             (3, "transposed conv k2s2"), (6, "normalise, launches < 64 MB (launch-latency bound)"),
+                                             (3, "transposed conv k2s2"), (4, "split-K reduce (6^3 level only; launch-latency bound)"),
+                                             (6, "normalise, launches < 64 MB (launch-latency bound)"),
                                              (7, "glue: window crop, noise + state init, stitch from the voxel-major accumulator")) if fam_ms[i] > 0},
             "kernel_time_share": dict({n: fam_ms[i] / ms_prof for i, n in enumerate(["conv3x3x3", "normalise_large", "final_ddim", "deconv", "splitk_reduce", "affine_map", "normalise_small", "glue"])},
                                       sum=sum(fam_ms) / ms_prof, profiled_pass_ms=ms_prof,

@@ -697,6 +697,7 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
   TRY(rc);
   if (a.ksplit > 1) {
     const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
+    if (PROF_ON) prof_of(p)->bytes[PROF_SPLITK] += (double)B * c.coutp * (double)p->V[lvl] * (4.0 * a.ksplit + (prec ? 4.0 : 2.0));
     TRY(prof_begin(PROF_SPLITK, st));
     DUNET_FMT(fmt_h(p, prec), launch_k(splitk_reduce_stats_kernel<HF>, dim3(nseg, planes), dim3(STATS_THREADS), 0, st, (const float*)splitk, a.ksplit,
              (long long)B * c.coutp * p->V[lvl], out.hi, out.lo, partial, (long long)p->V[lvl], nseg));
@@ -1143,6 +1144,10 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
 
 void dunet_plan_destroy(dunet_plan* p) {
   if (!p) return;
+  // deferred window work may still be running on the internal streams: it reads the plan's weights and tables
+  for (int i = 0; i < 4; ++i)
+    if (p->half_stream[i]) cudaStreamSynchronize(p->half_stream[i]);
+  if (p->stitch_stream) cudaStreamSynchronize(p->stitch_stream);
   for (void* q : p->owned) cudaFree(q);
   if (p->h_t) cudaFreeHost(p->h_t);
   for (cudaEvent_t e : p->t_ev) if (e) cudaEventDestroy(e);
