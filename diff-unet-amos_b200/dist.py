@@ -175,33 +175,50 @@ class PeerExchange:
         handles = np.zeros((slots + label_slots, 64), dtype=np.uint8)
         self.partial_ptr: List[List[int]] = [[0] * slots for _ in range(self.world)]
         self.label_ptr: List[int] = [0] * label_slots
+        # Every rank goes through the SAME sequence of collectives whether or not its local CUDA-IPC calls succeed (a rank
+        # that raised between two collectives would leave the others hanging); the outcome is agreed on at the end.
+        err = None
         with torch.cuda.device(self.device):
-            for i in range(slots + n_lab):
-                ptr = ctypes.c_void_p()
-                h = (ctypes.c_uint8 * 64)()
-                _lib.check(self.lib.dunet_ipc_alloc(ctypes.byref(ptr), pbytes if i < slots else lbytes, h))
-                self._owned.append(ptr.value)
-                handles[i] = np.frombuffer(bytes(h), dtype=np.uint8)
-                if i < slots:
-                    self.partial_ptr[self.rank][i] = ptr.value
-                else:
-                    self.label_ptr[i - slots] = ptr.value
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, handles.tobytes())
-            for r in range(self.world):
-                if r == self.rank:
-                    continue
-                hs = np.frombuffer(gathered[r], dtype=np.uint8).reshape(slots + label_slots, 64)
-                rng = list(range(slots)) + (list(range(slots, slots + label_slots)) if r == dst else [])
-                for i in rng:
+            try:
+                for i in range(slots + n_lab):
                     ptr = ctypes.c_void_p()
-                    h = (ctypes.c_uint8 * 64).from_buffer_copy(hs[i].tobytes())
-                    _lib.check(self.lib.dunet_ipc_open(h, ctypes.byref(ptr)))
-                    self._opened.append(ptr.value)
+                    h = (ctypes.c_uint8 * 64)()
+                    _lib.check(self.lib.dunet_ipc_alloc(ctypes.byref(ptr), pbytes if i < slots else lbytes, h))
+                    self._owned.append(ptr.value)
+                    handles[i] = np.frombuffer(bytes(h), dtype=np.uint8)
                     if i < slots:
-                        self.partial_ptr[r][i] = ptr.value
+                        self.partial_ptr[self.rank][i] = ptr.value
                     else:
                         self.label_ptr[i - slots] = ptr.value
+            except Exception as e:  # noqa: BLE001
+                err = e
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, None if err is not None else handles.tobytes())
+            if err is None and any(g is None for g in gathered):
+                err = RuntimeError("another rank could not allocate its CUDA-IPC buffers")
+            if err is None:
+                try:
+                    for r in range(self.world):
+                        if r == self.rank:
+                            continue
+                        hs = np.frombuffer(gathered[r], dtype=np.uint8).reshape(slots + label_slots, 64)
+                        rng = list(range(slots)) + (list(range(slots, slots + label_slots)) if r == dst else [])
+                        for i in rng:
+                            ptr = ctypes.c_void_p()
+                            h = (ctypes.c_uint8 * 64).from_buffer_copy(hs[i].tobytes())
+                            _lib.check(self.lib.dunet_ipc_open(h, ctypes.byref(ptr)))
+                            self._opened.append(ptr.value)
+                            if i < slots:
+                                self.partial_ptr[r][i] = ptr.value
+                            else:
+                                self.label_ptr[i - slots] = ptr.value
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            ok = torch.tensor([0.0 if err is not None else 1.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) == 0.0:
+                self._release()
+                raise RuntimeError(f"peer-memory exchange unavailable on this system: {err or 'another rank failed'}")
             # torch views of this rank's own buffers
             self.partial = [torch.as_tensor(_RawCuda(self.partial_ptr[self.rank][i], pbytes), device=self.device).view(torch.float32)
                             .view((self.channels,) + self.vol) for i in range(slots)]
@@ -229,7 +246,16 @@ class PeerExchange:
                                                      ctypes.c_void_p(self.counts[2].data_ptr()), ctypes.c_void_p(self.label_ptr[label_slot]),
                                                      None, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
+    def _release(self) -> None:
+        for p in self._opened:
+            self.lib.dunet_ipc_close(ctypes.c_void_p(p))
+        self._opened = []
+        for p in self._owned:
+            self.lib.dunet_ipc_free(ctypes.c_void_p(p))
+        self._owned = []
+
     def close(self) -> None:
+        """Collective: unmap the peers' buffers, then free the own ones."""
         torch.cuda.synchronize(self.device)
         if dist.is_initialized():
             dist.barrier()
@@ -238,12 +264,10 @@ class PeerExchange:
         self._opened = []
         if dist.is_initialized():
             dist.barrier()
-        for p in self._owned:
-            self.lib.dunet_ipc_free(ctypes.c_void_p(p))
-        self._owned = []
+        self._release()
 
 
-_PEER_CACHE: Dict[tuple, PeerExchange] = {}
+_PEER_CACHE: Dict[tuple, Optional[PeerExchange]] = {}
 
 
 def peer_exchange_for(channels: int, vol, roi, overlap: float, device, dst: int = 0) -> Optional[PeerExchange]:
@@ -253,7 +277,13 @@ def peer_exchange_for(channels: int, vol, roi, overlap: float, device, dst: int 
         return None
     key = (channels, tuple(vol), tuple(roi), float(overlap), str(device), dst, _world())
     if key not in _PEER_CACHE:
-        _PEER_CACHE[key] = PeerExchange(channels, vol, roi, overlap, device, dst=dst)
+        try:  # the constructor is collective and fails on ALL ranks together (e.g. CUDA IPC not permitted in this container)
+            _PEER_CACHE[key] = PeerExchange(channels, vol, roi, overlap, device, dst=dst)
+        except RuntimeError as e:
+            import warnings
+
+            warnings.warn(f"{e}; falling back to the NCCL exchange")
+            _PEER_CACHE[key] = None
     return _PEER_CACHE[key]
 
 
