@@ -29,6 +29,16 @@ struct DeconvTc {
   static constexpr int W_SLOTS = 3;
   static constexpr int ACC_COLS = ZT * N_TILE;
   static constexpr int SMEM_BYTES = A_SLOTS * PLANE_BYTES + W_SLOTS * W_UNIT_BYTES + 1024 + 256;
+  // The epilogue (TMEM -> +bias -> 16-bit -> lane exchange -> 16-byte stores) is one dependent instruction stream per warp:
+  // with one epilogue warp per scheduler it took ~19k clocks per tile against the ~11k the HBM write of the tile needs.
+  // Two warps per TMEM lane quadrant (each takes half of the column groups) hide that latency; the MMAs of this kernel are
+  // tiny, so -- unlike in the conv kernels -- more concurrent TMEM readers do not slow anything down.
+#ifndef DUNET_DECONV_EPI_WARPS
+#define DUNET_DECONV_EPI_WARPS 8
+#endif
+  static constexpr int EPI_WARPS = DUNET_DECONV_EPI_WARPS;
+  static constexpr int THREADS = (3 + EPI_WARPS) * 32;
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quadrant");
   static_assert(2 * ACC_COLS <= 512, "double-buffered accumulators exceed TMEM");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -45,7 +55,7 @@ struct DeconvTcArgs {
 };
 
 template <int NCB, int ZT, bool H>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(DeconvTc<NCB, ZT>::THREADS, 1)
 deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
   using Cfg = DeconvTc<NCB, ZT>;
   extern __shared__ uint8_t smem_raw[];
@@ -65,7 +75,7 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
     if (a.dbg) { a.dbg[blockIdx.x * 64 + 62] = clock64(); unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); a.dbg[blockIdx.x * 64 + 60] = (long long)g; }
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, Cfg::EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -155,7 +165,9 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
     pdl_trigger();  // all MMAs of this CTA are issued: only the last epilogue remains
   } else {
     // =============================== epilogue: TMEM -> +bias -> bf16 -> scatter ===============================
-    const int q = warp & 3;
+    const int q = warp & 3;                            // TMEM lane quadrant this warp may read
+    const int part = (warp - 3) / 4;                   // which share of the four 16-column groups this warp stores
+    constexpr int JP_PER_WARP = 4 * 4 / Cfg::EPI_WARPS;  // 4 (one warp per quadrant) or 2 (two warps per quadrant)
     const int r = q * 32 + lane;
     const long long in_vox = (long long)a.D * a.H * a.W, ovox = in_vox * 8;
     const int out_chunks = a.cout / 8;
@@ -182,16 +194,32 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
           const int yrow = tiy * CONV_TY + (r >> 3);
           const int oy = 2 * yrow + dy;
 #pragma unroll 1
-          for (int jp = 0; jp < 4; ++jp) {
+          for (int jp = part * JP_PER_WARP; jp < (part + 1) * JP_PER_WARP; ++jp) {
             float bl[8], bh[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { bl[i] = __ldg(a.bias + cblk * 64 + jp * 16 + i); bh[i] = __ldg(a.bias + cblk * 64 + jp * 16 + 8 + i); }
+#ifdef DUNET_DECONV_BATCHED_LD
+            // all 2 * ZT TMEM loads of this column group in flight before ONE wait (the MMAs of this kernel are tiny: no
+            // accumulator traffic to collide with, unlike the conv kernels)
+            uint32_t raw[ZT][2][16];
+#pragma unroll
+            for (int s = 0; s < ZT; ++s) {
+              tmem_ld16_nowait(acc + s * Cfg::N_TILE + jp * 16, raw[s][0]);
+              tmem_ld16_nowait(acc + s * Cfg::N_TILE + 64 + jp * 16, raw[s][1]);
+            }
+            tmem_wait_ld();
+#endif
 #pragma unroll
             for (int s = 0; s < ZT; ++s) {
               const int z = z0 + s;
               float v0[16], v1[16];
+#ifdef DUNET_DECONV_BATCHED_LD
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(raw[s][0][i]); v1[i] = __uint_as_float(raw[s][1][i]); }
+#else
               tmem_ld16(acc + s * Cfg::N_TILE + jp * 16, v0);
               tmem_ld16(acc + s * Cfg::N_TILE + 64 + jp * 16, v1);
+#endif
               BF8 pk[2][2];  // [dx][lo | hi chunk]
               {
                 float lo[8], hi[8];

@@ -835,8 +835,8 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
     const unsigned grid = (unsigned)std::min<long long>(tiles, p->num_sms);
     if (PROF_ON) prof_of(p)->bytes[PROF_DECONV] += (double)B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
     TRY(prof_begin(PROF_DECONV, st));
-    if (d.cinp == 64) DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<1, 2, HF>, dim3(grid), dim3(CONV_THREADS), DeconvTc<1, 2>::SMEM_BYTES, st, t[0], b));
-    else DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<2, 2, HF>, dim3(grid), dim3(CONV_THREADS), DeconvTc<2, 2>::SMEM_BYTES, st, t[0], b));
+    if (d.cinp == 64) DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<1, 2, HF>, dim3(grid), dim3(DeconvTc<1, 2>::THREADS), DeconvTc<1, 2>::SMEM_BYTES, st, t[0], b));
+    else DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<2, 2, HF>, dim3(grid), dim3(DeconvTc<2, 2>::THREADS), DeconvTc<2, 2>::SMEM_BYTES, st, t[0], b));
     LAUNCH_CHECK();
     TRY(prof_end(st));
     return 0;

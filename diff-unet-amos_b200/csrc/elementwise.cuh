@@ -795,26 +795,9 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// DDIM state layout conversion: planar fp32 [B][C][vox] (the reference's NCDHW) <-> voxel-major fp32 [B][vox][CP].
-// to_vm: dst_vm = src (or 0 when src == nullptr);  from_vm: dst planar = src_vm.   thread = (voxel, 4 classes)
+// DDIM state layout conversion: voxel-major fp32 [B][vox][CP] -> planar fp32 [B][C][vox] (the reference's NCDHW) for the
+// entry points that return planar tensors (the other direction is part of ddim_init_kernel).   thread = (voxel, 4 classes)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void state_to_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch) {
-  pdl_wait();
-  const int q4 = CP / 4;
-  const long long total = (long long)batch * vox * q4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int qd = (int)(i % q4);
-    const long long v = (i / q4) % vox;
-    const int n = (int)(i / (q4 * vox));
-    float f[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = qd * 4 + j;
-      f[j] = (src && c < C) ? src[((long long)n * C + c) * vox + v] : 0.f;
-    }
-    reinterpret_cast<float4*>(dst)[i] = make_float4(f[0], f[1], f[2], f[3]);
-  }
-}
 // dst = (accumulate ? dst : 0) + scale * src   (ensemble averaging over independent noise draws)
 __global__ void state_from_vm_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int CP, long long vox, int batch,
                                      float scale, int accumulate) {
