@@ -42,6 +42,12 @@ namespace dunet {
 
 constexpr int CONV_TX = 8, CONV_TY = 16;  // output tile in x, y  (= 128 GEMM rows)
 constexpr int CONV_THREADS = 7 * 32;
+// generic kernel: epilogue warps per CTA (4 = one per TMEM lane quadrant, 8 = two, each taking half of the column groups)
+#ifndef DUNET_CONV_EPI_WARPS
+#define DUNET_CONV_EPI_WARPS 4
+#endif
+constexpr int CONV_EPI_WARPS = DUNET_CONV_EPI_WARPS;
+constexpr int CONV_TC_THREADS = (3 + CONV_EPI_WARPS) * 32;
 constexpr int MODE_CONV3 = 0, MODE_DECONV2 = 1;
 
 template <int CB_CH, int N_TILE, int ZT, int MODE>
@@ -173,7 +179,7 @@ __device__ __forceinline__ ConvItem conv_item(const ConvTcArgs& a, int item) {
 // and, when 2 * ZT * N_TILE <= 512, the accumulators are double-buffered in TMEM so the epilogue of one item overlaps
 // the MMAs of the next.  Statistics rows are per spatial tile, so results do not depend on the item -> CTA assignment.
 template <int CB_CH, int N_TILE, int ZT, int MODE, bool H>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+__global__ void __launch_bounds__(CONV_TC_THREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1,
                  const __grid_constant__ CUtensorMap tmap2, const __grid_constant__ CUtensorMap tmap3, ConvTcArgs a) {
   using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
@@ -201,7 +207,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
     if (a.dbg) a.dbg[blockIdx.x * 8 + 0] = clock64();
     for (int i = 0; i < Cfg::A_SLOTS; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < Cfg::W_SLOTS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, CONV_EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -343,6 +349,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
   } else {
     // =============================== epilogue: TMEM -> registers -> HBM ===============================
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const int part = (warp - 3) / 4;  // with two warps per quadrant: which half of the column groups this warp handles
+    constexpr int J_PER_WARP = (N_TILE / 16) * 4 / CONV_EPI_WARPS;
     const int r = q * 32 + lane;  // GEMM row = voxel (y = r / 8, x = r % 8)
     const int out_chunks = a.cout / 8;
     const long long in_vox = (long long)a.D * a.H * a.W;
@@ -359,7 +367,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
       if (a.dbg && li == 0 && threadIdx.x == 3 * 32) a.dbg[blockIdx.x * 8 + 4] = clock64();  // first accumulators complete
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * ACC_COLS;
 #pragma unroll 1
-      for (int j = 0; j < N_TILE / 16; ++j) {
+      for (int j = part * J_PER_WARP; j < (part + 1) * J_PER_WARP; ++j) {
         float st[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) st[i] = 0.f;
@@ -423,16 +431,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
       if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        asm volatile("bar.sync 1, %0;" ::"n"(CONV_EPI_WARPS * 32) : "memory");  // the epilogue warps only
         const int nseg = a.tiles_x * a.tiles_y * a.tiles_z;
         const int tile_lin = (it.tiz * a.tiles_y + it.tiy) * a.tiles_x + it.tix;
-        for (int e = r; e < N_TILE * 2; e += 128) {
+        for (int e = part * 128 + r; e < N_TILE * 2; e += CONV_EPI_WARPS * 32) {
           const float tot = (red[e] + red[N_TILE * 2 + e]) + (red[2 * N_TILE * 2 + e] + red[3 * N_TILE * 2 + e]);
           const int l = e & 31, col = (e >> 5) * 16 + (l & 15), stat = l >> 4;
           const int chunk = (ntile * N_TILE + col) >> 3;
           a.stats[(((long long)n * out_chunks + chunk) * nseg + tile_lin) * 16 + stat * 8 + (col & 7)] = tot;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // red[] is reused by the next item
+        asm volatile("bar.sync 1, %0;" ::"n"(CONV_EPI_WARPS * 32) : "memory");  // red[] is reused by the next item
       }
     }
   }

@@ -198,28 +198,12 @@ deconv2_tc_kernel(const __grid_constant__ CUtensorMap tmap, DeconvTcArgs a) {
             float bl[8], bh[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { bl[i] = __ldg(a.bias + cblk * 64 + jp * 16 + i); bh[i] = __ldg(a.bias + cblk * 64 + jp * 16 + 8 + i); }
-#ifdef DUNET_DECONV_BATCHED_LD
-            // all 2 * ZT TMEM loads of this column group in flight before ONE wait (the MMAs of this kernel are tiny: no
-            // accumulator traffic to collide with, unlike the conv kernels)
-            uint32_t raw[ZT][2][16];
-#pragma unroll
-            for (int s = 0; s < ZT; ++s) {
-              tmem_ld16_nowait(acc + s * Cfg::N_TILE + jp * 16, raw[s][0]);
-              tmem_ld16_nowait(acc + s * Cfg::N_TILE + 64 + jp * 16, raw[s][1]);
-            }
-            tmem_wait_ld();
-#endif
 #pragma unroll
             for (int s = 0; s < ZT; ++s) {
               const int z = z0 + s;
               float v0[16], v1[16];
-#ifdef DUNET_DECONV_BATCHED_LD
-#pragma unroll
-              for (int i = 0; i < 16; ++i) { v0[i] = __uint_as_float(raw[s][0][i]); v1[i] = __uint_as_float(raw[s][1][i]); }
-#else
               tmem_ld16(acc + s * Cfg::N_TILE + jp * 16, v0);
               tmem_ld16(acc + s * Cfg::N_TILE + 64 + jp * 16, v1);
-#endif
               BF8 pk[2][2];  // [dx][lo | hi chunk]
               {
                 float lo[8], hi[8];

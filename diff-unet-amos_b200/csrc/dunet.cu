@@ -569,7 +569,7 @@ static int launch_conv_tc(const dunet_plan* p, const CUtensorMap (&t)[4], const 
   // persistent: one CTA per SM (each may own all 512 TMEM columns) walking the work items round-robin
   const long long grid = std::min<long long>(items, (long long)p->num_sms);
   TRY(prof_begin(MODE == MODE_CONV3 ? PROF_CONV : PROF_DECONV, st));
-  launch_k(kern, dim3((unsigned)grid), dim3(CONV_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
+  launch_k(kern, dim3((unsigned)grid), dim3(CONV_TC_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
   return 0;

@@ -59,10 +59,12 @@ for name, tf32, dt in (("eager torch fp32 (TF32 off)", False, None), ("eager tor
     torch.backends.cudnn.benchmark = True
     s = timeit(lambda: window(dt))
     rows.append((name, s))
-m = pkg.DiffUNetB200(in_channels=1, out_channels=C, image_size=S, spatial_size=S, batch_max=B).to(dev).eval()
-m.load_state_dict({k: v for k, v in sd.items()})
-s = timeit(lambda: m(image=image, pred_type="ddim_sample", noise=noise), reps=5)
-rows.append(("libdunet_b200 (bf16, this repo)", s))
+for prec in ("fp16", "bf16"):
+    m = pkg.DiffUNetB200(in_channels=1, out_channels=C, image_size=S, spatial_size=S, batch_max=B, precision=prec).to(dev).eval()
+    m.load_state_dict({k: v for k, v in sd.items()})
+    s = timeit(lambda: m(image=image, pred_type="ddim_sample", noise=noise), reps=5)
+    rows.append((f"libdunet_b200 ({prec}, this repo)", s))
+    del m
 m32 = pkg.DiffUNetB200(in_channels=1, out_channels=C, image_size=S, spatial_size=S, batch_max=B, precision="fp32x3").to(dev).eval()
 m32.load_state_dict({k: v for k, v in sd.items()})
 s = timeit(lambda: m32(image=image, pred_type="ddim_sample", noise=noise), reps=3)
