@@ -57,6 +57,7 @@ SIGNATURES = {
     "dunet_denoise_step": (c_int32, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_void_p, c_int32, c_void_p, c_void_p]),
     "dunet_ddim_sample": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_int32, c_void_p, c_void_p]),
     "dunet_crop_window": (c_int32, [c_void_p, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    "dunet_zero": (c_int32, [c_void_p, c_size_t, c_void_p]),
     "dunet_crop_windows": (c_int32, [c_void_p, POINTER(c_int32), c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p]),
     "dunet_infer_windows": (c_int32, [c_void_p, c_void_p, POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p, c_uint64, POINTER(c_int64),
                                       c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),

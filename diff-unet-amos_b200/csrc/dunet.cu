@@ -1667,6 +1667,12 @@ int dunet_infer_flush(dunet_plan* p, void* stream) {
   return drain_async(p, static_cast<cudaStream_t>(stream));
 }
 
+int dunet_zero(void* ptr, size_t bytes, void* stream) {
+  if (!ptr) return fail(DUNET_E_INVALID, "NULL argument");
+  CUDA_TRY(cudaMemsetAsync(ptr, 0, bytes, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int dunet_stitch_add(float* out_volume, const int32_t v[3], int32_t channels, const float* patch, const int32_t pd[3],
                      const int32_t s[3], void* stream) {
   if (!out_volume || !patch || !v || !pd || !s || channels < 1) return fail(DUNET_E_INVALID, "bad argument");

@@ -361,7 +361,8 @@ def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_si
             if px is not None:
                 if slot >= px.slots:
                     raise RuntimeError("a rank's queue share spans more volumes than the peer exchange has partial buffers")
-                buf = bufs[v] = StitchBuffers(model.num_classes, vol, roi, overlap, dev, out=px.partial[slot].zero_())
+                buf = bufs[v] = StitchBuffers(model.num_classes, vol, roi, overlap, dev, out=px.partial[slot])
+                buf.zero_()
             else:
                 buf = bufs[v] = StitchBuffers(model.num_classes, vol, roi, overlap, dev)
             bounds = list(range(lo, hi, step)) + [hi]
@@ -400,7 +401,7 @@ def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_si
                 if zero is None:
                     zero = StitchBuffers(model.num_classes, vol, roi, overlap, dev)
                 else:
-                    zero.out.zero_()
+                    zero.zero_()
                     zero._finalized = False
                 buf = zero
             _, binary = exchange_and_finalize(buf, dst, want_blended=False)

@@ -41,7 +41,8 @@ class StitchBuffers:
                 raise ValueError(f"out must be contiguous fp32 {(channels,) + self.vol}")
             self.out = out
         else:
-            self.out = torch.zeros((channels,) + self.vol, dtype=torch.float32, device=device)
+            self.out = torch.empty((channels,) + self.vol, dtype=torch.float32, device=device)
+            self.zero_()
         self._finalized = False
         self._pending_model = None
         self._keepalive = []
@@ -52,6 +53,13 @@ class StitchBuffers:
             self.count_vol = torch.zeros(self.vol, dtype=torch.float32, device=device)
         else:
             raise NotImplementedError(f"blend mode {mode!r}: only 'constant' (the reference's) and 'gaussian' exist")
+
+    def zero_(self) -> None:
+        """Clear the accumulator (cudaMemsetAsync through the C ABI: no library kernel on the path)."""
+        with torch.cuda.device(self.out.device):
+            _lib.check(_lib.load().dunet_zero(_ptr(self.out), self.out.numel() * 4, _stream()))
+        if self.mode == "gaussian" and hasattr(self, "count_vol"):
+            self.count_vol.zero_()
 
     def add(self, patch: torch.Tensor, start) -> None:
         lib = _lib.load()

@@ -162,6 +162,9 @@ int dunet_crop_window(const float* volume, const int32_t vol_dims[3], float* pat
                       const int32_t start[3], void* stream);
 int dunet_stitch_add(float* out_volume, const int32_t vol_dims[3], int32_t channels, const float* patch,
                      const int32_t patch_dims[3], const int32_t start[3], void* stream);
+/* replaces: `output_image = torch.zeros(...)` at the start of sliding_window_inference: clears the caller's accumulator
+ * (cudaMemsetAsync on `stream`; no kernel launch). */
+int dunet_zero(void* ptr, size_t bytes, void* stream);
 /* all windows of a batch in one launch: patches[b] = volume[start_b : start_b + patch_dims]; starts: HOST [batch][3] */
 int dunet_crop_windows(const float* volume, const int32_t vol_dims[3], float* patches, const int32_t patch_dims[3],
                        const int32_t* starts, int32_t batch, void* stream);
