@@ -321,9 +321,12 @@ def infer_volume_distributed(model, image: torch.Tensor, sw_batch_size: int = 4,
 @torch.no_grad()
 def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_size: int = 4, overlap: float = 0.25, dst: int = 0,
                               seed: int = 0, on_result: Optional[Callable[[int, torch.Tensor], None]] = None,
-                              noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None, exchange: str = "auto"):
+                              noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None, exchange: str = "auto",
+                              volume_shape: Optional[Sequence[int]] = None, device=None):
     """Throughput mode: ``images`` (a sequence of [1, 1, D, H, W] volumes of ONE shape, already >= the roi on every axis,
-    present on every rank) are processed as window queues of G volumes (``queue_group_size``) so that every rank does the
+    available on every rank; an entry may also be a zero-argument callable returning the volume, which is then only called
+    on the ranks whose queue share touches that volume -- e.g. a host-to-device copy that the other ranks can skip; pass
+    ``volume_shape=`` in that case) are processed as window queues of G volumes (``queue_group_size``) so that every rank does the
     same number of windows between two exchange points.  ``on_result(volume_index, binary_labels_uint8)`` is called on
     ``dst`` as results become available (e.g. to start the D2H copy); returns the list of label volumes on ``dst``.
     Window w of volume i draws its noise from the stream (``seed``, i * n_windows + w): identical to running the volumes
@@ -336,7 +339,12 @@ def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_si
     roi = model.patch
     if not images:
         return []
-    vol = tuple(images[0].shape[2:])
+    if volume_shape is None:
+        first = images[0]() if callable(images[0]) else images[0]
+        images = [first] + list(images[1:])
+        volume_shape = first.shape[2:]
+        device = first.device
+    vol = tuple(int(v) for v in volume_shape)
     if any(v < r for v, r in zip(vol, roi)):
         raise ValueError("throughput mode needs volumes that are at least the window size on every axis")
     starts = window_starts(vol, roi, overlap)
@@ -344,7 +352,7 @@ def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_si
     G = queue_group_size(n_win, world)
     step = min(int(sw_batch_size), model.batch_max)
     results = []
-    dev = images[0].device
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     px = peer_exchange_for(model.num_classes, vol, roi, overlap, dev, dst) if exchange in ("auto", "p2p") else None
     if exchange == "p2p" and px is None and world > 1:
         raise ValueError("the peer-memory exchange needs NCCL ranks on CUDA, channels % world == 0 and a width % 4 == 0")
@@ -356,6 +364,8 @@ def infer_volumes_distributed(model, images: Sequence[torch.Tensor], sw_batch_si
         bufs = {}
         for slot, (v, lo, hi) in enumerate(shares):
             img = images[grp[v]]
+            if callable(img):
+                img = img()  # materialised only on the ranks that need it
             if tuple(img.shape[2:]) != vol:
                 raise ValueError("all volumes of a queue must have the same shape")
             if px is not None:
