@@ -755,3 +755,12 @@ def test_finalize_peers_kernel_equals_sum_then_finalize():
     assert torch.equal(out_bin, ref_bin) and torch.equal(out_blend, ref_blend)
     assert lib.dunet_finalize_peers(ptrs, lo, hi, 3, _lib.i32x3((48, 40, 34)), 0, 2, _p(counts[0]), _p(counts[1]), _p(counts[2]),
                                     _p(out_bin), None, stream) == -4  # width % 4 != 0: DUNET_E_UNSUPPORTED
+
+
+def test_stitch_buffers_finalize_only_once():
+    """a second finalize() would divide by the counts again -- it raises instead."""
+    buf = pkg.StitchBuffers(2, (32, 32, 32), (32, 32, 32), 0.25, "cuda")
+    assert float(buf.out.abs().sum()) == 0.0  # cleared through dunet_zero
+    buf.finalize(binary=True)
+    with pytest.raises(RuntimeError, match="already called"):
+        buf.finalize()
