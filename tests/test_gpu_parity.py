@@ -764,3 +764,47 @@ def test_stitch_buffers_finalize_only_once():
     buf.finalize(binary=True)
     with pytest.raises(RuntimeError, match="already called"):
         buf.finalize()
+
+
+def test_fused_window_loop_with_ensemble_draws():
+    """BASELINE config 4 on the fused path: R noise draws per window accumulate in the voxel-major accumulator and are scaled
+    by 1/R when stitched; the generic path scales every draw and accumulates planar tensors -- same value up to fp32
+    rounding of the two orders."""
+    cout, S, vol, R = 2, 32, (32, 32, 56), 3
+    m = _build(cout, S, SMALL, batch_max=4)
+    image = seeded_image((1, 1) + vol).cuda()
+    n_win = len(pkg.window_starts(vol, (S, S, S), 0.25))
+    noise = seeded_noise((R, n_win, cout, S, S, S)).cuda()
+    fused = pkg.sliding_window_inference(image, (S, S, S), 4, m, 0.25, noise_fn=lambda w, b: noise[:, w:w + b].contiguous(), ensemble=R,
+                                         pred_type="ddim_sample")
+    cursor = {"w": 0}
+
+    def predictor(b, pred_type=None):
+        nz = noise[:, cursor["w"]:cursor["w"] + b.shape[0]].contiguous()
+        cursor["w"] += b.shape[0]
+        return m(image=b, pred_type=pred_type, noise=nz, ensemble=R)
+
+    generic = pkg.sliding_window_inference(image, (S, S, S), 4, predictor, 0.25, pred_type="ddim_sample")
+    assert rel_l2(fused, generic) < 1e-6
+    # and the library generator: draws are distinct streams (seed, window, draw)
+    a = pkg.sliding_window_inference(image, (S, S, S), 4, m, 0.25, seed=3, ensemble=R, pred_type="ddim_sample")
+    b = pkg.sliding_window_inference(image, (S, S, S), 4, m, 0.25, seed=3, ensemble=1, pred_type="ddim_sample")
+    assert torch.isfinite(a).all() and not torch.equal(a, b)
+
+
+def test_infer_windows_argument_checks():
+    m = _build(2, 32, SMALL, batch_max=2)
+    vol = torch.rand(40, 40, 40, device="cuda")
+    out = torch.zeros(2, 40, 40, 40, device="cuda")
+    with pytest.raises(ValueError, match="batch_max"):
+        m.infer_windows(vol, [(0, 0, 0)] * 3, out, noise_ids=[0, 1, 2])
+    with pytest.raises(ValueError, match="noise_ids"):
+        m.infer_windows(vol, [(0, 0, 0)], out)
+    with pytest.raises(_lib.DunetError, match="outside volume"):
+        m.infer_windows(vol, [(16, 0, 0)], out, noise_ids=[0])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.infer_windows(vol.cpu(), [(0, 0, 0)], out, noise_ids=[0])
+    m.infer_windows(vol, [(8, 8, 8)], out, noise_ids=[0])
+    m.infer_flush()
+    torch.cuda.synchronize()
+    assert float(out[:, :8].abs().sum()) == 0.0 and float(out[:, 8:40, 8:40, 8:40].abs().sum()) > 0.0
