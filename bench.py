@@ -391,7 +391,7 @@ def run_b200(args, cfg):
         ms_prof = p0.elapsed_time(p1)
         conv_ms, conv_n, conv_fl = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
         _lib.check(lib.dunet_profile_read(plan, ctypes.byref(conv_ms), ctypes.byref(conv_n), ctypes.byref(conv_fl)))
-        fam_ms, fam_n, fam_b = (ctypes.c_double * 8)(), (ctypes.c_uint64 * 8)(), (ctypes.c_double * 8)()
+        fam_ms, fam_n, fam_b = (ctypes.c_double * 12)(), (ctypes.c_uint64 * 12)(), (ctypes.c_double * 12)()
         _lib.check(lib.dunet_profile_read_all(plan, fam_ms, fam_n, fam_b))
         _lib.check(lib.dunet_profile_enable(plan, 0))
     if world > 1:
@@ -473,12 +473,16 @@ def run_b200(args, cfg):
             "gpu_launches": int(launches),
             "parity": parity,
             "checksum": checksum,
-            "roofline": {"bound": "tensor", "kernel": "conv3d_tc64_kernel + conv3d_tc_kernel: every 3x3x3 conv launch of rank 0 in the profiled pass (CUDA events around each launch)",
+            "roofline": {"bound": "tensor", "kernel": "conv3d_tc64_kernel + conv3d_tc_kernel: every 16-bit-operand 3x3x3 conv launch of rank 0 in the profiled pass (CUDA events "
+                                                      "around each launch); the encoder's split-precision convs (fp16 mode: 3 MMAs per product, 2.6 % of the FLOPs) are listed under split_precision_convs",
                          "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
                          "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kind::f16 MMAs run fp16 and bf16 at the same rate)",
                          "launches": int(conv_n.value), "avg_launch_ms": conv_ms.value / max(conv_n.value, 1),
-                         "conv_share_of_profiled_pass": conv_ms.value / ms_prof,
+                         "conv_share_of_profiled_pass": (fam_ms[0] + fam_ms[8]) / ms_prof,
                          "frac_of_burst_peak": conv_tflops / peaks["bf16_tflops"],
+                         "split_precision_convs": ({"algorithmic_tflops": fam_b[8] / fam_ms[8] / 1e9, "executed_mma_tflops": 3 * fam_b[8] / fam_ms[8] / 1e9,
+                                                    "launches": int(fam_n[8]), "share_of_profiled_pass": fam_ms[8] / ms_prof} if fam_ms[8] > 0 else None),
+                         "all_convs_algorithmic_tflops": (fam_b[0] + fam_b[8]) / (fam_ms[0] + fam_ms[8]) / 1e9 if fam_ms[0] + fam_ms[8] > 0 else None,
                          "traffic": None, "traffic_source": "profiles/ (ncu --set full captures per kernel: dram__bytes_read.sum + dram__bytes_write.sum); not read live"},
             "roofline_hbm": {name: {"bound": "hbm", "achieved": fam_b[i] / fam_ms[i] / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": fam_b[i] / fam_ms[i] / 1e6 / peaks["hbm_gbs"], "launches": int(fam_n[i]),
@@ -487,7 +491,8 @@ def run_b200(args, cfg):
                                              (3, "transposed conv k2s2"), (4, "split-K reduce (6^3 level only; launch-latency bound)"),
                                              (6, "normalise, launches < 64 MB (launch-latency bound)"),
                                              (7, "glue: window crop, noise + state init, stitch from the voxel-major accumulator")) if fam_ms[i] > 0},
-            "kernel_time_share": dict({n: fam_ms[i] / ms_prof for i, n in enumerate(["conv3x3x3", "normalise_large", "final_ddim", "deconv", "splitk_reduce", "affine_map", "normalise_small", "glue"])},
+            "kernel_time_share": dict({n: fam_ms[i] / ms_prof for i, n in enumerate(["conv3x3x3", "normalise_large", "final_ddim", "deconv", "splitk_reduce", "affine_map", "normalise_small", "glue",
+                                                                                     "conv3x3x3_split_precision_encoder"])},
                                       sum=sum(fam_ms) / ms_prof, profiled_pass_ms=ms_prof,
                                       note="profiled pass: single stream, events around every launch; shares are of that pass's own elapsed time"),
         }

@@ -60,13 +60,16 @@ static int fail(int code, const char* fmt, ...) {
 
 // ---- optional live profiling of the launches of ONE plan (bench.py roofline): CUDA events around every launch ----
 struct ProfRec { cudaEvent_t a, b; int tag; };
-enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_NORM_SMALL = 6, PROF_GLUE = 7, PROF_TAGS = 8 };
+// PROF_CONV_SPLIT: 3x3x3 convs that run in split precision inside a 16-bit plan (the encoder in fp16 mode): 3 MMAs per
+// algorithmic product, reported apart from the 16-bit convs whose roofline is the tensor peak
+enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_NORM_SMALL = 6, PROF_GLUE = 7,
+       PROF_CONV_SPLIT = 8, PROF_TAGS = 12 };
 struct Prof {
   bool on = false;
   std::vector<ProfRec> recs;       // event pool, reused across enable() calls
   size_t used = 0;
   double flops = 0.0;
-  double bytes[PROF_TAGS] = {0, 0, 0, 0, 0, 0, 0, 0};  // ALGORITHMIC HBM bytes per kernel family (see dunet_profile_read_all)
+  double bytes[PROF_TAGS] = {};  // ALGORITHMIC HBM bytes per kernel family; for the two conv families: ALGORITHMIC FLOPs
 };
 struct dunet_plan;
 static Prof* prof_of(const dunet_plan* p);
@@ -562,13 +565,13 @@ static int dev_prepare(int* sms_out) {
 }
 
 template <int CB_CH, int N_TILE, int ZT, int MODE, bool H>
-static int launch_conv_tc(const dunet_plan* p, const CUtensorMap (&t)[4], const ConvTcArgs& a, cudaStream_t st) {
+static int launch_conv_tc(const dunet_plan* p, const CUtensorMap (&t)[4], const ConvTcArgs& a, cudaStream_t st, int conv_tag = PROF_CONV) {
   using Cfg = ConvTc<CB_CH, N_TILE, ZT, MODE>;
   auto kern = conv3d_tc_kernel<CB_CH, N_TILE, ZT, MODE, H>;
   const long long items = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
   // persistent: one CTA per SM (each may own all 512 TMEM columns) walking the work items round-robin
   const long long grid = std::min<long long>(items, (long long)p->num_sms);
-  TRY(prof_begin(MODE == MODE_CONV3 ? PROF_CONV : PROF_DECONV, st));
+  TRY(prof_begin(MODE == MODE_CONV3 ? conv_tag : PROF_DECONV, st));
   launch_k(kern, dim3((unsigned)grid), dim3(CONV_TC_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
@@ -576,13 +579,14 @@ static int launch_conv_tc(const dunet_plan* p, const CUtensorMap (&t)[4], const 
 }
 
 template <int CB_CH, bool FUSE, bool H>
-static int launch_conv_tc64(const dunet_plan* p, const CUtensorMap (&t)[4], const ConvTc64Args& a, unsigned* grid_out, cudaStream_t st) {
+static int launch_conv_tc64(const dunet_plan* p, const CUtensorMap (&t)[4], const ConvTc64Args& a, unsigned* grid_out, cudaStream_t st,
+                            int conv_tag = PROF_CONV) {
   using Cfg = ConvTc64<CB_CH, CONV_ZT>;
   auto kern = conv3d_tc64_kernel<CB_CH, CONV_ZT, FUSE, H>;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.batch;
   const unsigned grid = (unsigned)std::min<long long>(tiles, p->num_sms);
   *grid_out = grid;
-  TRY(prof_begin(PROF_CONV, st));
+  TRY(prof_begin(conv_tag, st));
   launch_k(kern, dim3(grid), dim3(FUSE ? Cfg::THREADS_FUSED : CONV_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
@@ -640,7 +644,12 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     }
     return 0;
   }
-  if (PROF_ON) prof_of(p)->flops += 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
+  const int conv_tag = (prec && !is_prec(p)) ? PROF_CONV_SPLIT : PROF_CONV;
+  if (PROF_ON) {
+    const double fl = 2.0 * B * (double)p->V[lvl] * c.coutr * 27.0 * (c.c0r + c.c1r);
+    prof_of(p)->bytes[conv_tag] += fl;
+    if (conv_tag == PROF_CONV) prof_of(p)->flops += fl;
+  }
   const ConvGeom g = conv_geom(p, c, lvl, B);
   const int want_split = (splitk && partial) ? g.ksplit : 1;
   const bool use64 = c.packed64 && want_split == 1 && g.zt == CONV_ZT && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV);
@@ -663,9 +672,9 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     if (fuse) {
       if (c.nb1 != 0 || prec) return fail(DUNET_E_STATE, "normalise-on-load needs a single bf16 source");
       b.in_affine = fuse->affine; b.in_bias = fuse->bias.p; b.in_bias_n_stride = fuse->bias.n_stride; b.slope = 0.1f;
-      DUNET_FMT(fmt_h(p, prec), TRY(cb == 32 ? (launch_conv_tc64<32, true, HF>(p, t, b, &grid, st)) : (launch_conv_tc64<64, true, HF>(p, t, b, &grid, st))));
+      DUNET_FMT(fmt_h(p, prec), TRY(cb == 32 ? (launch_conv_tc64<32, true, HF>(p, t, b, &grid, st, conv_tag)) : (launch_conv_tc64<64, true, HF>(p, t, b, &grid, st, conv_tag))));
     } else {
-      DUNET_FMT(fmt_h(p, prec), TRY(cb == 32 ? (launch_conv_tc64<32, false, HF>(p, t, b, &grid, st)) : (launch_conv_tc64<64, false, HF>(p, t, b, &grid, st))));
+      DUNET_FMT(fmt_h(p, prec), TRY(cb == 32 ? (launch_conv_tc64<32, false, HF>(p, t, b, &grid, st, conv_tag)) : (launch_conv_tc64<64, false, HF>(p, t, b, &grid, st, conv_tag))));
     }
     if (partial) *nseg_out = (int)grid;  // one statistics row per persistent CTA and sample
     return 0;
@@ -686,12 +695,12 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
   else a.stats = partial;
   int rc = 0;
   DUNET_FMT(fmt_h(p, prec), {
-    if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
-    else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
-    else if (c.cb_ch == 64 && c.n_tile == 64 && g.zt == 2) rc = launch_conv_tc<64, 64, 2, MODE_CONV3, HF>(p, t, a, st);
-    else if (c.cb_ch == 64 && c.n_tile == 128 && g.zt == 2) rc = launch_conv_tc<64, 128, 2, MODE_CONV3, HF>(p, t, a, st);
-    else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
-    else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3, HF>(p, t, a, st);
+    if (c.cb_ch == 32 && c.n_tile == 64) rc = launch_conv_tc<32, 64, CONV_ZT, MODE_CONV3, HF>(p, t, a, st, conv_tag);
+    else if (c.cb_ch == 32 && c.n_tile == 128) rc = launch_conv_tc<32, 128, CONV_ZT, MODE_CONV3, HF>(p, t, a, st, conv_tag);
+    else if (c.cb_ch == 64 && c.n_tile == 64 && g.zt == 2) rc = launch_conv_tc<64, 64, 2, MODE_CONV3, HF>(p, t, a, st, conv_tag);
+    else if (c.cb_ch == 64 && c.n_tile == 128 && g.zt == 2) rc = launch_conv_tc<64, 128, 2, MODE_CONV3, HF>(p, t, a, st, conv_tag);
+    else if (c.cb_ch == 64 && c.n_tile == 64) rc = launch_conv_tc<64, 64, CONV_ZT, MODE_CONV3, HF>(p, t, a, st, conv_tag);
+    else if (c.cb_ch == 64 && c.n_tile == 128) rc = launch_conv_tc<64, 128, CONV_ZT, MODE_CONV3, HF>(p, t, a, st, conv_tag);
     else rc = fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
   });
   TRY(rc);

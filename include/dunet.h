@@ -299,8 +299,11 @@ int dunet_debug_set_conv_timeline(int64_t* dev_buffer);
  * of conv launches, and their ALGORITHMIC flops 2*B*V*Cout*27*Cin (real channels only). */
 int dunet_profile_enable(dunet_plan* plan, int32_t on);
 int dunet_profile_read(dunet_plan* plan, double* conv_ms, uint64_t* conv_launches, double* conv_flops);
-/* per kernel family [8]: 0 conv3x3x3, 1 normalise (launches moving >= 64 MB), 2 final+DDIM, 3 transposed conv, 4 split-K reduce,
- * 5 other (affine-map kernel), 6 normalise launches below 64 MB (launch-latency bound), 7 glue (state layout, pack, noise).
+/* per kernel family, arrays of 12 entries: 0 conv3x3x3 (16-bit operands; also fp32x3 plans), 1 normalise (launches moving
+ * >= 64 MB), 2 final+DDIM, 3 transposed conv, 4 split-K reduce, 5 other (affine-map kernel), 6 normalise launches below 64 MB
+ * (launch-latency bound), 7 glue (window crop, noise + state init, stitch), 8 conv3x3x3 running in split precision inside a
+ * 16-bit plan (the encoder in fp16 mode: 3 MMAs per algorithmic product), 9-11 unused.  For the two conv families
+ * bytes_by_tag holds ALGORITHMIC FLOPs instead of bytes.
  * bytes_by_tag (nullable): ALGORITHMIC HBM bytes of the bandwidth-bound families (normalise: 4 B/element (+2 residual,
  * +0.25 pooled); final+DDIM: per voxel 2F + 16C (+2C re-pack); transposed conv: 2(Cin + 8 Cout) per input voxel). */
 int dunet_profile_read_all(dunet_plan* plan, double* ms_by_tag, uint64_t* launches_by_tag, double* bytes_by_tag);

@@ -47,14 +47,14 @@ if a.prof:
     with torch.no_grad():
         m(image=image, pred_type="ddim_sample", noise=noise)
     torch.cuda.synchronize()
-    msb = (ctypes.c_double * 8)(); cnt = (ctypes.c_uint64 * 8)(); byt = (ctypes.c_double * 8)()
+    msb = (ctypes.c_double * 12)(); cnt = (ctypes.c_uint64 * 12)(); byt = (ctypes.c_double * 12)()
     _lib.check(lib.dunet_profile_read_all(plan, msb, cnt, byt))
     lib.dunet_profile_enable(plan, 0)
-    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "affine-map", "norm-small", "glue"]
+    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "affine-map", "norm-small", "glue", "conv-split-enc", "-", "-", "-"]
     tot = sum(msb)
     print("in-situ CUDA-event time per kernel family (one call, batch %d):" % a.batch)
     for i, nme in enumerate(names):
-        bw = f"  {byt[i] / msb[i] / 1e6:7.0f} GB/s algorithmic" if byt[i] > 0 and msb[i] > 0 else ""
+        bw = (f"  {byt[i] / msb[i] / 1e9:7.0f} TFLOP/s algorithmic" if i in (0, 8) else f"  {byt[i] / msb[i] / 1e6:7.0f} GB/s algorithmic") if byt[i] > 0 and msb[i] > 0 else ""
         print(f"  {nme:14s} {msb[i]:8.3f} ms  {100 * msb[i] / tot:5.1f}%  launches {cnt[i]}{bw}")
     print(f"  sum {tot:.3f} ms")
     if a.dump:
