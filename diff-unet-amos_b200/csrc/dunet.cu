@@ -167,7 +167,7 @@ __device__ __forceinline__ bf16 weight_part(float v, int part, int fp16) {
   return part < 2 ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles, int rot, int parts, int fp16) {
+                                   int c0p, int c1r, int cb_ch, int n_tile, int ncb, int n_tiles, int rot, int parts, int fp16, int triple) {
   const int kch = cb_ch / 8;
   const int ncb1 = ncb / parts;
   const long long total = (long long)n_tiles * ncb * 27 * kch * n_tile * 8;
@@ -183,18 +183,20 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, bf16* __restrict
     const int co = nt * n_tile + col;
     const int cb = cbg % ncb1, part = parts == 1 ? 0 : cbg / ncb1;
     const int lc = cb * cb_ch + k * 8 + j;
-    int ci = -1;
-    if (lc < c0p) { if (lc < c0r) ci = rot ? (lc + 1) % c0r : lc; }  // rot: packed order is [x.., image], reference [image, x..]
+    int ci = -1, wpart = part;
+    if (triple) {  // one block holds [A.hi | A.lo | A.hi] of the c0r real channels against [W.hi | W.hi | W.lo] (see ConvW::triple)
+      if (lc < 3 * c0r) { ci = lc % c0r; wpart = lc / c0r == 2 ? 2 : 0; }
+    } else if (lc < c0p) { if (lc < c0r) ci = rot ? (lc + 1) % c0r : lc; }  // rot: packed order is [x.., image], reference [image, x..]
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
-    out[i] = weight_part(v, part, fp16);
+    out[i] = weight_part(v, wpart, fp16);
   }
 }
 // conv weights for the Cout = 64 z-stacked kernel (conv3d_tc64.cuh): bf16 [cin block][ty*3+tx][k chunk][192][8] with
 // row = (2 - tz) * 64 + cout
 __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restrict__ out, int coutr, int cinr, int c0r,
-                                     int c0p, int c1r, int cb_ch, int ncb, int rot, int parts, int fp16) {
+                                     int c0p, int c1r, int cb_ch, int ncb, int rot, int parts, int fp16, int triple) {
   const int kch = cb_ch / 8;
   const int ncb1 = ncb / parts;
   const long long total = (long long)ncb * 9 * kch * 192 * 8;
@@ -210,12 +212,14 @@ __global__ void pack_conv_w64_kernel(const float* __restrict__ w, bf16* __restri
     const int tz = 2 - row / 64, co = row % 64;
     const int tap = tz * 9 + tyx;
     const int lc = cb * cb_ch + k * 8 + j;
-    int ci = -1;
-    if (lc < c0p) { if (lc < c0r) ci = rot ? (lc + 1) % c0r : lc; }  // rot: packed order is [x.., image], reference [image, x..]
+    int ci = -1, wpart = part;
+    if (triple) {  // one block holds [A.hi | A.lo | A.hi] of the c0r real channels against [W.hi | W.hi | W.lo] (see ConvW::triple)
+      if (lc < 3 * c0r) { ci = lc % c0r; wpart = lc / c0r == 2 ? 2 : 0; }
+    } else if (lc < c0p) { if (lc < c0r) ci = rot ? (lc + 1) % c0r : lc; }  // rot: packed order is [x.., image], reference [image, x..]
     else { const int l1 = lc - c0p; if (l1 < c1r) ci = c0r + l1; }
     float v = 0.f;
     if (co < coutr && ci >= 0) v = w[((long long)co * cinr + ci) * 27 + tap];
-    out[i] = weight_part(v, part, fp16);
+    out[i] = weight_part(v, wpart, fp16);
   }
 }
 // transposed-conv weights fp32 [cinr][coutr][8] -> bf16 [tap][cinp][coutp]
@@ -270,7 +274,12 @@ __global__ void copy_pad_rows_kernel(const float* __restrict__ src, float* __res
 struct ConvW {
   int c0r = 0, c1r = 0, c0p = 0, c1p = 0, coutr = 0, coutp = 0;
   int cb_ch = 64, n_tile = 64, nb0 = 0, nb1 = 0, n_tiles = 1;
-  int parts = 1;  // 3 in fp32x3 mode: weight block list [W.hi | W.hi | W.lo]
+  int parts = 1;  // 3 in split precision: weight block list [W.hi | W.hi | W.lo]
+  bool split = false;   // this conv reads and writes hi + lo bf16 pairs (fp32x3 mode; the encoder in fp16 mode)
+  // split precision with very few real input channels (the encoder's first conv, Cin = 1): the three products hi*hi + lo*hi +
+  // hi*lo fit into ONE input-channel block -- packed activation channels [A.hi | A.lo | A.hi] (3 * c0r of the 32) against
+  // weights [W.hi | W.hi | W.lo] -- instead of three mostly-zero 32-channel blocks: a third of the MMAs, a single source tensor
+  bool triple = false;
   bf16* packed = nullptr;
   bf16* packed64 = nullptr;  // z-stacked layout for the Cout = 64 kernel (coutp == 64 only)
   float* w32 = nullptr;  // debug copy of the original fp32 weight
@@ -279,6 +288,8 @@ struct ConvW {
   bool have_w = false, have_cb = false, have_g = false, have_b = false;
   void shape(int c0r_, int c0p_, int c1r_, int c1p_, int coutr_, int parts_ = 1, int cb64_ = 32) {
     c0r = c0r_; c0p = c0p_; c1r = c1r_; c1p = c1p_; coutr = coutr_; parts = parts_;
+    split = parts_ == 3;
+    triple = false;
     cb64 = (c1p == 0 && c0p == 32) ? 32 : cb64_;
     coutp = pad_to(coutr, 64);
     cb_ch = (c1p == 0 && c0p == 32) ? 32 : 64;
@@ -487,7 +498,7 @@ static WsLayout ws_layout(const dunet_plan* p, int B) {
   L.in_pack = take(act_m(p->in_pad, 0, std::max(pm, pme)));
   size_t raw_max = 0, part_max = 0, ss_max = 0, split_max = 0;
   auto upd = [&](const ConvW& c, int lvl) {
-    raw_max = std::max(raw_max, act_m(c.coutp, lvl, c.parts == 3 ? 2 : 1));
+    raw_max = std::max(raw_max, act_m(c.coutp, lvl, c.split ? 2 : 1));
     const ConvGeom g = conv_geom(p, c, lvl, B);
     const size_t planes = (size_t)B * (c.coutp / 8);
     part_max = std::max(part_max, planes * std::max(g.tiles, 160) * 16 * sizeof(float));  // rows: tiles, reduction segments (<= 128) or persistent CTAs (<= #SMs)
@@ -616,7 +627,7 @@ struct FuseIn {
 // can conv `c` at level `lvl` take its input through the normalise-on-load path of the Cout = 64 kernel?
 static bool conv_can_fuse_input(const dunet_plan* p, const ConvW& c, int lvl, int B) {
   if (p->cfg.flags & (DUNET_FLAG_REF_CONV | DUNET_FLAG_GENERIC_CONV | DUNET_FLAG_FP32X3 | DUNET_FLAG_NO_FUSED_NORM)) return false;
-  if (c.parts != 1 || c.coutp != 64 || c.nb1 != 0 || !c.packed64) return false;
+  if (c.split || c.parts != 1 || c.coutp != 64 || c.nb1 != 0 || !c.packed64) return false;
   const ConvGeom g = conv_geom(p, c, lvl, B);
   return g.ksplit == 1 && g.zt == CONV_ZT;
 }
@@ -626,8 +637,8 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
                     int* nseg_out, int lvl, int B, cudaStream_t st, const FuseIn* fuse = nullptr) {
   const int D = p->D[lvl], H = p->H[lvl], W = p->W[lvl];
   const int planes = B * (c.coutp / 8);
-  const bool prec = c.parts == 3;
-  if (prec && (!src0.lo || !out.lo || (c.nb1 > 0 && !src1.lo))) return fail(DUNET_E_STATE, "fp32x3 conv needs hi + lo tensors");
+  const bool prec = c.split, pairs_in = prec && !c.triple;  // triple: one packed source tensor already holds hi, lo, hi
+  if (prec && (!out.lo || (pairs_in && (!src0.lo || (c.nb1 > 0 && !src1.lo))))) return fail(DUNET_E_STATE, "split-precision conv needs hi + lo tensors");
   if (p->cfg.flags & DUNET_FLAG_REF_CONV) {
     if (prec) return fail(DUNET_E_UNSUPPORTED, "DUNET_FLAG_REF_CONV and DUNET_FLAG_FP32X3 are mutually exclusive");
     if (!c.w32) return fail(DUNET_E_STATE, "DUNET_FLAG_REF_CONV needs DUNET_FLAG_KEEP_FP32_WEIGHTS");
@@ -658,11 +669,11 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
   TRY(make_act_tmap(&t[0], src0.hi, B * (c.c0p / 8), D, H, W, cb / 8, 1));
   t[1] = t[2] = t[3] = t[0];
   if (c.nb1 > 0) TRY(make_act_tmap(&t[1], src1.hi, B * (c.c1p / 8), D, H, W, cb / 8, 1));
-  if (prec) {
+  if (pairs_in) {
     TRY(make_act_tmap(&t[2], src0.lo, B * (c.c0p / 8), D, H, W, cb / 8, 1));
     if (c.nb1 > 0) TRY(make_act_tmap(&t[3], src1.lo, B * (c.c1p / 8), D, H, W, cb / 8, 1));
   }
-  const ConvSegs segs = make_segs(c.c0p / cb, c.c0p / 8, c.c1p / cb, c.c1p / 8, prec);
+  const ConvSegs segs = make_segs(c.c0p / cb, c.c0p / 8, c.c1p / cb, c.c1p / 8, pairs_in);
   if (use64) {
     ConvTc64Args b;
     memset(&b, 0, sizeof b);
@@ -776,7 +787,7 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
 static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src1, BiasRef temb_bias, Act add, Act out,
                        Act pooled, int lvl, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st,
                        bool defer_last_norm = false, int* nseg_out = nullptr, Act* raw_out = nullptr) {
-  const bool tp = t.a.parts == 3;  // this block runs in split precision (hi + lo tensors)
+  const bool tp = t.a.split;  // this block runs in split precision (hi + lo tensors)
   const Act raw_a = ws_act_x(p, ws, L.raw, t.a.coutp, lvl, B, tp), mid = ws_act_x(p, ws, L.mid, t.a.coutp, lvl, B, tp);
   const Act raw_b = ws_act_x(p, ws, L.raw, t.b.coutp, lvl, B, tp);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
@@ -894,17 +905,17 @@ static int drain_async(dunet_plan* p, cudaStream_t st) {
 }
 
 static int launch_pack(const dunet_plan* p, const float* src0, int c0, const float* src1, int c1, Act dst, int c_pad,
-                       long long vox, int B, cudaStream_t st) {
-  DUNET_FMT(fmt_h(p, dst.lo != nullptr), launch_k(pack_c8_kernel<HF>, dim3(grid_for((long long)B * (c_pad / 8) * vox, 256)), dim3(256), 0, st, src0, c0, src1, c1,
-                                 dst.hi, dst.lo, c_pad, vox, B));
+                       long long vox, int B, cudaStream_t st, bool triple = false) {
+  DUNET_FMT(fmt_h(p, dst.lo != nullptr || triple), launch_k(pack_c8_kernel<HF>, dim3(grid_for((long long)B * (c_pad / 8) * vox, 256)), dim3(256), 0, st,
+                                 src0, c0, src1, c1, dst.hi, dst.lo, c_pad, vox, B, triple ? 1 : 0));
   LAUNCH_CHECK();
   return 0;
 }
 
 static int encode_impl(dunet_plan* p, const float* image, int B, uint8_t* ws, const WsLayout& L, cudaStream_t st) {
-  const bool ep = enc_prec(p);
-  const Act in_pack = ws_act_x(p, ws, L.in_pack, p->in_pad, 0, B, ep);
-  TRY(launch_pack(p, image, p->cfg.in_channels, nullptr, 0, in_pack, p->in_pad, p->V[0], B, st));
+  const bool ep = enc_prec(p), triple = p->enc[0].a.triple;
+  const Act in_pack = ws_act_x(p, ws, L.in_pack, p->in_pad, 0, B, ep && !triple);
+  TRY(launch_pack(p, image, p->cfg.in_channels, nullptr, 0, in_pack, p->in_pad, p->V[0], B, st, triple));
   for (int l = 0; l < 5; ++l) {
     const Act src = l ? ws_act_x(p, ws, L.epool[l], p->fp[l - 1], l, B, ep) : in_pack;
     const Act pooled = l < 4 ? ws_act_x(p, ws, L.epool[l + 1], p->fp[l], l + 1, B, ep) : Act();
@@ -1105,8 +1116,13 @@ int dunet_plan_create(dunet_plan** out, const dunet_cfg* cfg) {
   // encoder (no temb), pretrained/basic_unet.py:491-494
   for (int l = 0; l < 5; ++l) {
     TwoConvW& e = p->enc[l];
-    if (l == 0) e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], parts_enc, cb64);
-    else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts_enc, cb64);
+    if (l == 0) {
+      e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], parts_enc, cb64);
+      if (e.a.split && 3 * cfg->in_channels <= 32 && !(cfg->flags & DUNET_FLAG_REF_CONV)) {  // hi, lo, hi of the image in ONE block
+        e.a.shape(cfg->in_channels, p->in_pad, 0, 0, p->fr[0], 1, cb64);
+        e.a.split = true; e.a.triple = true;
+      }
+    } else e.a.shape(p->fr[l - 1], p->fp[l - 1], 0, 0, p->fr[l], parts_enc, cb64);
     e.b.shape(p->fr[l], p->fp[l], 0, 0, p->fr[l], parts_enc, cb64);
     TwoConvW& d = p->den[l];
     d.has_temb = true;
@@ -1193,13 +1209,13 @@ int dunet_plan_set_weight(dunet_plan* p, const char* key, const float* src, cons
       if (!c->packed) TRY(dev_alloc(p, (void**)&c->packed, c->packed_elems() * sizeof(bf16)));
       const int cinr = c->c0r + c->c1r;
       pack_conv_w_kernel<<<grid_for((long long)c->packed_elems(), 256), 256, 0, st>>>(
-          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->ncb(), c->n_tiles, c->rot, c->parts, fmt_h(p, c->parts == 3) ? 1 : 0);
+          src, c->packed, c->coutr, cinr, c->c0r, c->c0p, c->c1r, c->cb_ch, c->n_tile, c->ncb(), c->n_tiles, c->rot, c->parts, fmt_h(p, c->split) ? 1 : 0, c->triple ? 1 : 0);
       LAUNCH_CHECK();
       if (c->coutp == 64) {
         const size_t n64 = c->packed64_elems();
         if (!c->packed64) TRY(dev_alloc(p, (void**)&c->packed64, n64 * sizeof(bf16)));
         pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(src, c->packed64, c->coutr, cinr, c->c0r, c->c0p,
-                                                                             c->c1r, c->cb64, c->ncb64(), c->rot, c->parts, fmt_h(p, c->parts == 3) ? 1 : 0);
+                                                                             c->c1r, c->cb64, c->ncb64(), c->rot, c->parts, fmt_h(p, c->split) ? 1 : 0, c->triple ? 1 : 0);
         LAUNCH_CHECK();
       }
       if (p->cfg.flags & DUNET_FLAG_KEEP_FP32_WEIGHTS) {
@@ -1887,13 +1903,13 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   } else {
     CUDA_TRY(cudaMallocAsync((void**)&c.packed, c.packed_elems() * sizeof(bf16), st));
     pack_conv_w_kernel<<<grid_for((long long)c.packed_elems(), 256), 256, 0, st>>>(
-        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.ncb(), c.n_tiles, 0, c.parts, fp16 ? 1 : 0);
+        weight, c.packed, c.coutr, c0 + c1, c.c0r, c.c0p, c.c1r, c.cb_ch, c.n_tile, c.ncb(), c.n_tiles, 0, c.parts, fp16 ? 1 : 0, 0);
     LAUNCH_CHECK();
     if (c.coutp == 64 && !generic_only) {
       const size_t n64 = c.packed64_elems();
       CUDA_TRY(cudaMallocAsync((void**)&c.packed64, n64 * sizeof(bf16), st));
       pack_conv_w64_kernel<<<grid_for((long long)n64, 256), 256, 0, st>>>(weight, c.packed64, c.coutr, c0 + c1, c.c0r, c.c0p,
-                                                                           c.c1r, c.cb64, c.ncb64(), 0, c.parts, fp16 ? 1 : 0);
+                                                                           c.c1r, c.cb64, c.ncb64(), 0, c.parts, fp16 ? 1 : 0, 0);
       LAUNCH_CHECK();
     }
   }

@@ -99,10 +99,12 @@ __device__ __forceinline__ void load_split(const __nv_bfloat16* hi, const __nv_b
 // pack: fp32 NCDHW (two concatenated sources) -> bf16 C8-planar with c_pad channels (zero padded).
 // Used for the denoiser input cat([image, x_t]) (reference denoiser.py:298) and for boundary tensors.
 // ---------------------------------------------------------------------------------------------------------------
+// triple != 0 (split precision, c0 real channels, c1 == 0, bf16): ONE tensor with channels [hi(c0) | lo(c0) | hi(c0) | 0 ..],
+// hi = bf16(v), lo = v - hi -- the operand of a ConvW::triple conv (the encoder's first conv).
 template <bool H>
 __global__ void pack_c8_kernel(const float* __restrict__ src0, int c0, const float* __restrict__ src1, int c1,
                                __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_lo, int c_pad, long long vox,
-                               int batch) {
+                               int batch, int triple) {
   pdl_wait();
   const int chunks = c_pad / 8;
   long long total = (long long)batch * chunks * vox;
@@ -116,11 +118,17 @@ __global__ void pack_c8_kernel(const float* __restrict__ src0, int c0, const flo
     for (int j = 0; j < 8; ++j) {
       int c = ck * 8 + j;
       float val = 0.f;
-      if (c < c0) val = src0[((long long)n * c0 + c) * vox + v];
+      if (triple) {
+        if (c < 3 * c0) {
+          const float x = src0[((long long)n * c0 + c % c0) * vox + v];
+          const float hi = round_16<false>(x);
+          val = (c / c0 == 1) ? x - hi : hi;
+        }
+      } else if (c < c0) val = src0[((long long)n * c0 + c) * vox + v];
       else if (c < c0 + c1) val = src1[((long long)n * c1 + (c - c0)) * vox + v];
       f[j] = val;
     }
-    store_split<H>(dst, dst_lo, i, f);
+    store_split<H>(dst, triple ? nullptr : dst_lo, i, f);
   }
 }
 
