@@ -20,6 +20,7 @@
 #include "conv3d_ref.cuh"
 #include "conv3d_tc.cuh"
 #include "conv3d_tc64.cuh"
+#include "conv3d_flat.cuh"
 #include "deconv2_tc.cuh"
 #include "elementwise.cuh"
 
@@ -151,6 +152,21 @@ static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, in
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(DUNET_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d D=%d planes=%d)",
                                      (int)r, W, H, D, planes);
+  return 0;
+}
+
+// Tensor map for the flattened-plane kernel (conv3d_flat.cuh): box = (W + 2 positions, ty + 2 rows, one z, 8 chunks)
+static int make_flat_tmap(CUtensorMap* m, const bf16* base, int planes, int D, int H, int W, int hx, int ty) {
+  TRY(load_driver_entry());
+  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+  cuuint32_t box[4] = {(cuuint32_t)hx * 8, (cuuint32_t)(ty + 2), 1, 8};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(DUNET_E_CUDA, "cuTensorMapEncodeTiled (flat) failed with CUresult %d (W=%d H=%d D=%d planes=%d hx=%d ty=%d)",
+                                     (int)r, W, H, D, planes, hx, ty);
   return 0;
 }
 
@@ -418,7 +434,12 @@ static void add_twoconv_slots(dunet_plan* p, const std::string& pre, TwoConvW* t
 
 constexpr int CONV_ZT = 4;
 
-struct ConvGeom { int tiles_x, tiles_y, tiles_z, tiles, ksplit, zt; };
+struct ConvGeom {
+  int tiles_x, tiles_y, tiles_z, tiles, ksplit, zt;
+  // flattened-plane kernel (conv3d_flat.cuh) selected for this layer: tiles_y x tiles_z items per (sample, cout tile)
+  bool flat = false;
+  int hx = 0, ty = 0, npos = 0, lbo = 0, a_slots = 0, w_slots = 0, flat_smem = 0, ksub = 1;
+};
 
 // tiling + split-K decision for one conv layer at U-Net level `lvl` with batch B (deterministic: depends on shapes only)
 static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
@@ -445,6 +466,49 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
   const int ctas = g.tiles * c.n_tiles, ncb = c.ncb();
   g.ksplit = 1;
   if (ncb >= 2 && ctas < split_items) g.ksplit = std::max(1, std::min(ncb, 96 / ctas));
+  // Deep levels (row of at most 30 voxels, Cout a multiple of 128): swapped-operand flattened-plane kernel.  N = positions
+  // of a (ty rows x W + 2) halo-plane strip, as many rows as fit N <= 256; ZT slabs so that ZT * N <= 512 TMEM columns
+  // (ZT dividing D when possible); split-K until a sample has ~48 items.  Again per-sample shapes only.
+  static const bool flat_on = [] { const char* e = getenv("DUNET_FLAT"); return !(e && e[0] == '0'); }();
+  static const int flat_split_items = [] { const char* e = getenv("DUNET_FLAT_SPLIT_ITEMS"); return e ? atoi(e) : 36; }();
+  static const int flat_target_items = [] { const char* e = getenv("DUNET_FLAT_TARGET_ITEMS"); return e ? atoi(e) : 48; }();
+  if (flat_on && !(p->cfg.flags & (DUNET_FLAG_REF_CONV | DUNET_FLAG_GENERIC_CONV)) && c.cb_ch == 64 && c.n_tile == 128 &&
+      p->W[lvl] + 2 <= 32) {
+    const int Dl = p->D[lvl], Hl = p->H[lvl];
+    const int hx = p->W[lvl] + 2, ty_max = 258 / hx;
+    const int tiles_y = (Hl + ty_max - 1) / ty_max, ty = (Hl + tiles_y - 1) / tiles_y;
+    const int npos = pad_to(std::max(ty * hx - 2, 1), 16);
+    int zt = 1;
+    static const int zt_max = [] { const char* e = getenv("DUNET_FLAT_ZT_MAX"); return e ? atoi(e) : 6; }();
+    static const int zt_max_npos = [] { const char* e = getenv("DUNET_FLAT_ZT_MAX_NPOS"); return e ? atoi(e) : 0; }();  // ... only where npos >= this
+    for (int cand : {6, 4, 3, 2}) {
+      if (cand > zt_max && npos >= zt_max_npos) continue;
+      if (cand * npos <= 512 && cand <= Dl && Dl % cand == 0) { zt = cand; break; }
+    }
+    const int planes = zt + 2, lbo = (ty + 2) * hx * 16, plane_bytes = 8 * lbo;
+    const int budget = FLAT_SMEM_MAX - 1024 - 512 - FLAT_EPI_SMEM - FLAT_A_SLACK;
+    int a_slots = std::min(std::min(16, 2 * planes), (budget - 4 * FLAT_W_BYTES) / plane_bytes);
+    if (a_slots < planes) a_slots = planes;
+    const int w_slots = std::min(8, (budget - a_slots * plane_bytes) / FLAT_W_BYTES);
+    if (w_slots >= 2) {
+      g.flat = true;
+      g.hx = hx; g.ty = ty; g.npos = npos; g.lbo = lbo; g.a_slots = a_slots; g.w_slots = w_slots; g.zt = zt;
+      g.flat_smem = 1024 + a_slots * plane_bytes + FLAT_A_SLACK + w_slots * FLAT_W_BYTES + FLAT_EPI_SMEM + 512;
+      g.tiles_x = 1; g.tiles_y = tiles_y; g.tiles_z = (Dl + zt - 1) / zt;
+      g.tiles = g.tiles_y * g.tiles_z;
+      const int items1 = g.tiles * c.n_tiles;
+      g.ksplit = 1;
+      g.ksub = 1;
+      if (items1 < flat_split_items) {
+        // K is split in units of 64-channel blocks; when a sample still has too few items, in units of one tz slice of a
+        // block (9 taps), up to 16 ways
+        const int want = (flat_target_items + items1 - 1) / items1;
+        static const bool tz_split = [] { const char* e = getenv("DUNET_FLAT_TZ_SPLIT"); return !(e && e[0] == '0'); }();
+        if (want > ncb && tz_split) { g.ksub = 3; g.ksplit = std::max(1, std::min(std::min(3 * ncb, 16), want)); }
+        else g.ksplit = std::max(1, std::min(ncb, want));
+      }
+    }
+  }
   return g;
 }
 
@@ -550,7 +614,12 @@ static int g_conv_dbg_count = 0;
   X((conv3d_tc64_kernel<64, CONV_ZT, false, H>), (ConvTc64<64, CONV_ZT>::SMEM_BYTES))                          \
   X((conv3d_tc64_kernel<64, CONV_ZT, true, H>), (ConvTc64<64, CONV_ZT>::SMEM_BYTES))                           \
   X((deconv2_tc_kernel<1, 2, H>), (DeconvTc<1, 2>::SMEM_BYTES))                                                \
-  X((deconv2_tc_kernel<2, 2, H>), (DeconvTc<2, 2>::SMEM_BYTES))
+  X((deconv2_tc_kernel<2, 2, H>), (DeconvTc<2, 2>::SMEM_BYTES))                                                \
+  X((conv3d_flat_kernel<1, H>), FLAT_SMEM_MAX)                                                                 \
+  X((conv3d_flat_kernel<2, H>), FLAT_SMEM_MAX)                                                                 \
+  X((conv3d_flat_kernel<3, H>), FLAT_SMEM_MAX)                                                                 \
+  X((conv3d_flat_kernel<4, H>), FLAT_SMEM_MAX)                                                                 \
+  X((conv3d_flat_kernel<6, H>), FLAT_SMEM_MAX)
 
 // Per-DEVICE one-time setup (the dynamic shared memory opt-in of a kernel is a per-device attribute): keyed by device
 // id, mutex-protected.  Called from dunet_plan_create and the standalone dunet_op_* entry points, never on the per-step
@@ -633,8 +702,15 @@ static bool conv_can_fuse_input(const dunet_plan* p, const ConvW& c, int lvl, in
 }
 
 // 3x3x3 conv -> raw output (bf16, or hi + lo in fp32x3 mode) + InstanceNorm partial statistics [plane][*nseg_out][16]
+// With `pending_split` a K-split conv of a small level may leave its fp32 partial tiles un-reduced (*pending_split = ksplit):
+// the caller's run_norm then sums, normalises and activates them in one launch (splitk_norm_kernel).
+static bool splitk_norm_ok(const dunet_plan* p, bool prec, int lvl) {
+  static const bool on = [] { const char* e = getenv("DUNET_FUSED_SPLITK_NORM"); return !(e && e[0] == '0'); }();
+  return on && !prec && p->V[lvl] <= SKN_MAX_VOX && p->D[lvl] % 2 == 0 && p->H[lvl] % 2 == 0 && p->W[lvl] % 2 == 0;
+}
 static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act out, float* partial, float* splitk,
-                    int* nseg_out, int lvl, int B, cudaStream_t st, const FuseIn* fuse = nullptr) {
+                    int* nseg_out, int lvl, int B, cudaStream_t st, const FuseIn* fuse = nullptr, int* pending_split = nullptr) {
+  if (pending_split) *pending_split = 0;
   const int D = p->D[lvl], H = p->H[lvl], W = p->W[lvl];
   const int planes = B * (c.coutp / 8);
   const bool prec = c.split, pairs_in = prec && !c.triple;  // triple: one packed source tensor already holds hi, lo, hi
@@ -691,6 +767,60 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     return 0;
   }
   if (fuse) return fail(DUNET_E_STATE, "normalise-on-load requested for a conv outside the Cout = 64 kernel");
+  if (g.flat) {
+    // deep levels: swapped-operand flattened-plane kernel (conv3d_flat.cuh)
+    for (int i = 0; i < 4; ++i) {
+      const bf16* base = i == 0 ? src0.hi : i == 1 ? src1.hi : i == 2 ? src0.lo : src1.lo;
+      const bool used = i == 0 || (i == 1 && c.nb1 > 0) || (pairs_in && (i == 2 || c.nb1 > 0));
+      if (used) TRY(make_flat_tmap(&t[i], base, B * ((i & 1 ? c.c1p : c.c0p) / 8), D, H, W, g.hx, g.ty));
+      else t[i] = t[0];
+    }
+    ConvFlatArgs f;
+    memset(&f, 0, sizeof f);
+    f.w = c.packed; f.out = out.hi; f.out_lo = out.lo; f.segs = segs;
+    f.cout = c.coutp; f.D = D; f.H = H; f.W = W;
+    f.hx = g.hx; f.ty = g.ty; f.tiles_y = g.tiles_y; f.tiles_z = g.tiles_z; f.n_tiles = c.n_tiles; f.batch = B;
+    f.npos = g.npos; f.lbo = g.lbo; f.a_slots = g.a_slots; f.w_slots = g.w_slots;
+    f.ksplit = want_split;
+    f.ksub = want_split > 1 ? g.ksub : 1;
+    {
+      static const int target = [] { const char* e = getenv("DUNET_DBG_LAUNCH"); return e ? atoi(e) : -1; }();
+      f.dbg = (g_conv_dbg && (target < 0 || g_conv_dbg_count == target)) ? g_conv_dbg : nullptr;
+      if (g_conv_dbg) ++g_conv_dbg_count;
+    }
+    if (f.ksplit > 1) f.out_partial = splitk;
+    else f.stats = partial;
+    const long long items = (long long)g.tiles * c.n_tiles * f.ksplit * B;
+    const unsigned grid = (unsigned)std::min<long long>(items, p->num_sms);
+    TRY(prof_begin(conv_tag, st));
+    DUNET_FMT(fmt_h(p, prec), {
+      switch (g.zt) {
+        case 1: launch_k(conv3d_flat_kernel<1, HF>, dim3(grid), dim3(FLAT_THREADS), (size_t)g.flat_smem, st, t[0], t[1], t[2], t[3], f); break;
+        case 2: launch_k(conv3d_flat_kernel<2, HF>, dim3(grid), dim3(FLAT_THREADS), (size_t)g.flat_smem, st, t[0], t[1], t[2], t[3], f); break;
+        case 3: launch_k(conv3d_flat_kernel<3, HF>, dim3(grid), dim3(FLAT_THREADS), (size_t)g.flat_smem, st, t[0], t[1], t[2], t[3], f); break;
+        case 4: launch_k(conv3d_flat_kernel<4, HF>, dim3(grid), dim3(FLAT_THREADS), (size_t)g.flat_smem, st, t[0], t[1], t[2], t[3], f); break;
+        default: launch_k(conv3d_flat_kernel<6, HF>, dim3(grid), dim3(FLAT_THREADS), (size_t)g.flat_smem, st, t[0], t[1], t[2], t[3], f); break;
+      }
+    });
+    LAUNCH_CHECK();
+    TRY(prof_end(st));
+    if (f.ksplit > 1 && pending_split && splitk_norm_ok(p, prec, lvl)) {
+      *pending_split = f.ksplit;
+      *nseg_out = 0;
+    } else if (f.ksplit > 1) {
+      const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
+      if (PROF_ON) prof_of(p)->bytes[PROF_SPLITK] += (double)B * c.coutp * (double)p->V[lvl] * (4.0 * f.ksplit + (prec ? 4.0 : 2.0));
+      TRY(prof_begin(PROF_SPLITK, st));
+      DUNET_FMT(fmt_h(p, prec), launch_k(splitk_reduce_stats_kernel<HF>, dim3(nseg, planes), dim3(STATS_THREADS), 0, st, (const float*)splitk, f.ksplit,
+               (long long)B * c.coutp * p->V[lvl], out.hi, out.lo, partial, (long long)p->V[lvl], nseg));
+      LAUNCH_CHECK();
+      TRY(prof_end(st));
+      *nseg_out = nseg;
+    } else if (partial) {
+      *nseg_out = g.tiles;
+    }
+    return 0;
+  }
   ConvTcArgs a;
   memset(&a, 0, sizeof a);
   a.w = c.packed; a.out = out.hi; a.out_lo = out.lo; a.segs = segs;
@@ -715,7 +845,10 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
     else rc = fail(DUNET_E_UNSUPPORTED, "no conv instantiation for cb_ch=%d n_tile=%d", c.cb_ch, c.n_tile);
   });
   TRY(rc);
-  if (a.ksplit > 1) {
+  if (a.ksplit > 1 && pending_split && splitk_norm_ok(p, prec, lvl)) {
+    *pending_split = a.ksplit;
+    *nseg_out = 0;
+  } else if (a.ksplit > 1) {
     const int nseg = (int)std::min<long long>(std::max<long long>((p->V[lvl] + 255) / 256, 1), 128);
     if (PROF_ON) prof_of(p)->bytes[PROF_SPLITK] += (double)B * c.coutp * (double)p->V[lvl] * (4.0 * a.ksplit + (prec ? 4.0 : 2.0));
     TRY(prof_begin(PROF_SPLITK, st));
@@ -732,14 +865,32 @@ static int run_conv(const dunet_plan* p, const ConvW& c, Act src0, Act src1, Act
 
 // statistics (reduced in the kernel prologue) -> fused normalise/activation(/bias/add/pool)
 static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* partial, int nseg, BiasRef bias, Act add,
-                    Act out, Act pooled, int lvl, int B, cudaStream_t st) {
+                    Act out, Act pooled, int lvl, int B, cudaStream_t st, int pending_split = 0, const float* splitk = nullptr) {
   const int planes = B * (c.coutp / 8);
   const bool prec = raw.lo != nullptr;
   NormActArgs a;
+  memset(&a, 0, sizeof a);
   a.raw = raw.hi; a.partial = partial; a.nseg = nseg; a.gamma = c.gamma; a.beta = c.beta; a.bias = bias.p; a.bias_n_stride = bias.n_stride; a.add = add.hi;
   a.out = out.hi; a.pooled = pooled.hi; a.raw_lo = raw.lo; a.add_lo = add.lo; a.out_lo = out.lo; a.pooled_lo = pooled.lo;
   a.chunks = c.coutp / 8; a.D = p->D[lvl]; a.H = p->H[lvl]; a.W = p->W[lvl];
   a.eps = 1e-5f; a.slope = 0.1f;
+  if (pending_split > 1) {
+    // the conv left its K-split partial tiles un-reduced: sum + statistics + normalise (+ pool) in one launch
+    if (prec || !splitk || add.lo || p->V[lvl] > SKN_MAX_VOX) return fail(DUNET_E_STATE, "fused split-K normalise: unsupported configuration");
+    SplitkNormArgs k;
+    k.part = splitk; k.ksplit = pending_split; k.split_stride = (long long)B * c.coutp * p->V[lvl]; k.n = a;
+    if (PROF_ON) prof_of(p)->bytes[PROF_NORM_SMALL] += (double)B * c.coutp * (double)p->V[lvl] * (4.0 * pending_split + 2.0 + (add.hi ? 2.0 : 0.0) + (pooled.hi ? 0.25 : 0.0));
+    TRY(prof_begin(PROF_NORM_SMALL, st));
+#define DUNET_SKN(ADDF, POOLF) DUNET_FMT(is_fp16(p), launch_k(splitk_norm_kernel<ADDF, POOLF, HF>, dim3(planes), dim3(256), 0, st, k))
+    if (add.hi && pooled.hi) DUNET_SKN(true, true);
+    else if (add.hi) DUNET_SKN(true, false);
+    else if (pooled.hi) DUNET_SKN(false, true);
+    else DUNET_SKN(false, false);
+#undef DUNET_SKN
+    LAUNCH_CHECK();
+    TRY(prof_end(st));
+    return 0;
+  }
   // ~4 resident blocks per SM in total, each streaming a long contiguous range of one 8-channel plane (the
   // statistics prologue is paid once per block)
   const int per_plane = std::max(1, (148 * 8 + planes - 1) / planes);
@@ -792,9 +943,10 @@ static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src
   const Act raw_b = ws_act_x(p, ws, L.raw, t.b.coutp, lvl, B, tp);
   float* partial = reinterpret_cast<float*>(ws + L.partial);
   float* splitk = reinterpret_cast<float*>(ws + L.splitk);
-  int nseg = 0;
-  TRY(run_conv(p, t.a, src0, src1, raw_a, partial, splitk, &nseg, lvl, B, st));
-  if (conv_can_fuse_input(p, t.b, lvl, B)) {
+  int nseg = 0, ps_a = 0;
+  const bool b_fuses = conv_can_fuse_input(p, t.b, lvl, B);
+  TRY(run_conv(p, t.a, src0, src1, raw_a, partial, splitk, &nseg, lvl, B, st, nullptr, b_fuses ? nullptr : &ps_a));
+  if (b_fuses) {
     // conv_1 normalises conv_0's raw output on load: only the affine map is materialised.  conv_1 writes its own raw
     // output to ws.mid (ws.raw is still being read) -- callers get the buffer through *raw_out.
     float* affine = reinterpret_cast<float*>(ws + L.affine);
@@ -817,13 +969,14 @@ static int run_twoconv(const dunet_plan* p, const TwoConvW& t, Act src0, Act src
     return 0;
   }
   if (raw_out) *raw_out = raw_b;
-  TRY(run_norm(p, t.a, raw_a, partial, nseg, temb_bias, Act(), mid, Act(), lvl, B, st));
-  TRY(run_conv(p, t.b, mid, Act(), raw_b, partial, splitk, &nseg, lvl, B, st));
+  int ps = 0;  // K-split partial tiles left for the normalise pass (deep levels, see run_conv)
+  TRY(run_norm(p, t.a, raw_a, partial, nseg, temb_bias, Act(), mid, Act(), lvl, B, st, ps_a, splitk));
+  TRY(run_conv(p, t.b, mid, Act(), raw_b, partial, splitk, &nseg, lvl, B, st, nullptr, (defer_last_norm || raw_out) ? nullptr : &ps));
   if (defer_last_norm) {
     *nseg_out = nseg;
     return 0;
   }
-  TRY(run_norm(p, t.b, raw_b, partial, nseg, BiasRef(), add, out, pooled, lvl, B, st));
+  TRY(run_norm(p, t.b, raw_b, partial, nseg, BiasRef(), add, out, pooled, lvl, B, st, ps, splitk));
   return 0;
 }
 
@@ -1879,6 +2032,7 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
   memset(&tmp.cfg, 0, sizeof tmp.cfg);
   TRY(dev_prepare(&tmp.num_sms));
   tmp.cfg.flags = use_ref == 1 ? (DUNET_FLAG_REF_CONV | DUNET_FLAG_KEEP_FP32_WEIGHTS) : (prec ? DUNET_FLAG_FP32X3 : (fp16 ? DUNET_FLAG_FP16 : 0));
+  if (generic_only) tmp.cfg.flags |= DUNET_FLAG_GENERIC_CONV;  // voxel-as-M generic kernel only (no Cout = 64 / flattened-plane kernels)
   tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
   tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
   ConvW c;

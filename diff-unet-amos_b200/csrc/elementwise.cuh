@@ -525,6 +525,129 @@ __global__ void __launch_bounds__(NORM_THREADS, MODE == MODE_FP32X3 ? 2 : (ADD ?
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Split-K epilogue FUSED with the normalise pass, for the deepest levels (<= 2048 voxels per sample: 12^3, 6^3 of a 96^3
+// window).  One block owns one (sample, 8-channel plane): it sums the fp32 K-split partial tiles in a fixed order into
+// registers, reduces the InstanceNorm statistics of the plane on the spot (the whole plane is in this block), and writes
+// y = LeakyReLU(norm(x)) [+ temb bias] [+ encoder feature] (and its 2x2x2 max-pool) directly -- replacing
+// splitk_reduce_stats_kernel + norm_act(_pool)_kernel and the 16-bit round trip of the raw conv output between them
+// (two launch-latency-bound launches per layer; same reference lines as norm_act_kernel).
+// ---------------------------------------------------------------------------------------------------------------
+struct SplitkNormArgs {
+  const float* part;        // [ks][plane][vox][8] fp32
+  int ksplit;
+  long long split_stride;   // floats between consecutive K-split buffers
+  NormActArgs n;            // raw / partial / nseg unused
+};
+constexpr int SKN_VPT = 8;                  // voxels per thread
+constexpr int SKN_MAX_VOX = 256 * SKN_VPT;  // 2048
+
+template <bool ADD, bool POOL, bool H>
+__global__ void __launch_bounds__(256) splitk_norm_kernel(SplitkNormArgs a) {
+  __shared__ float sc[8], sh[8], bi[8];
+  __shared__ double red[8][16];
+  __shared__ BF8 tile[POOL ? SKN_MAX_VOX : 1];
+  const int plane = blockIdx.x;
+  const int vox = a.n.D * a.n.H * a.n.W;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  if (threadIdx.x < 8)
+    bi[threadIdx.x] = a.n.bias ? a.n.bias[(long long)(plane / a.n.chunks) * a.n.bias_n_stride + (plane % a.n.chunks) * 8 + threadIdx.x] : 0.f;
+  const float4* __restrict__ p = reinterpret_cast<const float4*>(a.part) + (long long)plane * vox * 2;
+  const long long kstride = a.split_stride / 4;
+  float f[SKN_VPT][8];
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+#pragma unroll
+  for (int u = 0; u < SKN_VPT; ++u) {
+    const int v = threadIdx.x + u * 256;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[u][j] = 0.f;
+    if (v < vox) {
+      for (int k = 0; k < a.ksplit; ++k) {
+        const float4 a0 = p[k * kstride + v * 2], a1 = p[k * kstride + v * 2 + 1];
+        f[u][0] += a0.x; f[u][1] += a0.y; f[u][2] += a0.z; f[u][3] += a0.w;
+        f[u][4] += a1.x; f[u][5] += a1.y; f[u][6] += a1.z; f[u][7] += a1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[u][j];
+        q[j] = fmaf(f[u][j], f[u][j], q[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o2);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o2);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[warp][j] = (double)s[j];
+      red[warp][8 + j] = (double)q[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      ts += red[w][threadIdx.x];
+      tq += red[w][8 + threadIdx.x];
+    }
+    const int c = (plane % a.n.chunks) * 8 + threadIdx.x;
+    const double mean = ts / (double)vox;
+    double var = tq / (double)vox - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)a.n.eps));
+    const float scale = rstd * a.n.gamma[c];
+    sc[threadIdx.x] = scale;
+    sh[threadIdx.x] = a.n.beta[c] - (float)mean * scale;
+  }
+  __syncthreads();
+  const BF8* __restrict__ add = reinterpret_cast<const BF8*>(a.n.add) + (long long)plane * vox;
+  BF8* __restrict__ out = reinterpret_cast<BF8*>(a.n.out) + (long long)plane * vox;
+#pragma unroll
+  for (int u = 0; u < SKN_VPT; ++u) {
+    const int v = threadIdx.x + u * 256;
+    if (v < vox) {
+      norm_apply(f[u], sc, sh, bi, a.n.slope);
+      if constexpr (ADD) {
+        float g[8];
+        bf8_to_float<H>(add[v], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[u][j] += g[j];
+      }
+      const BF8 o = float_to_bf8<H>(f[u]);
+      out[v] = o;
+      if constexpr (POOL) tile[v] = o;
+    }
+  }
+  if constexpr (POOL) {  // pooled == maxpool(out) of the ROUNDED outputs, as in norm_act_pool_kernel
+    __syncthreads();
+    const int D2 = a.n.D / 2, H2 = a.n.H / 2, W2 = a.n.W / 2;
+    const int pvox = D2 * H2 * W2;
+    for (int pv = threadIdx.x; pv < pvox; pv += 256) {
+      const int x2 = pv % W2, y2 = (pv / W2) % H2, z2 = pv / (W2 * H2);
+      float m[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float r[8];
+        bf8_to_float<H>(tile[((2 * z2 + (k >> 2)) * a.n.H + 2 * y2 + ((k >> 1) & 1)) * a.n.W + 2 * x2 + (k & 1)], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], r[j]);
+      }
+      store_split<H>(a.n.pooled, nullptr, (long long)plane * pvox + pv, m);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // ConvTranspose3d k=2 s=2 + bias (MONAI UpSample "deconv", denoiser.py:161-170,181).  CUDA-core version:
 // thread = (input voxel, tap, 8 output channels).  weights packed [tap][cin][cout] bf16.
 // ---------------------------------------------------------------------------------------------------------------

@@ -46,7 +46,13 @@ def _bf(t, fmt="bf16"):
                                               (1, 0, 64, 2, (16, 16, 16)), (64, 64, 64, 1, (16, 16, 16)),
                                               (128, 0, 128, 1, (12, 12, 12)), (256, 256, 256, 1, (6, 6, 6)),
                                               (512, 0, 512, 2, (2, 2, 2)), (64, 0, 64, 1, (32, 48, 40)),
-                                              (8, 0, 16, 1, (16, 16, 16))])
+                                              (8, 0, 16, 1, (16, 16, 16)),
+                                              # deep-level shapes: the flattened-plane kernel (conv3d_flat.cuh) for kernel 0 / 5
+                                              (64, 0, 128, 2, (24, 24, 24)), (128, 128, 128, 1, (24, 24, 24)),
+                                              (256, 0, 256, 2, (12, 12, 12)), (128, 0, 256, 1, (8, 8, 8)),
+                                              (128, 0, 128, 1, (16, 16, 16)), (64, 0, 128, 1, (5, 7, 9)),
+                                              (128, 0, 128, 1, (9, 20, 24)), (64, 0, 128, 3, (3, 3, 3)),
+                                              (64, 0, 128, 1, (4, 4, 30))])
 @pytest.mark.parametrize("fmt", ["bf16", "fp16"])
 def test_conv3x3x3_tensor_core_vs_fp64(c0, c1, cout, B, dims, fmt):
     """tcgen05 implicit-GEMM conv == conv3d of the 16-bit-rounded operands (fp64 accumulate), to one output rounding."""
