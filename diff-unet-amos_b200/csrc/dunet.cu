@@ -479,11 +479,17 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
     const int tiles_y = (Hl + ty_max - 1) / ty_max, ty = (Hl + tiles_y - 1) / tiles_y;
     const int npos = pad_to(std::max(ty * hx - 2, 1), 16);
     int zt = 1;
-    static const int zt_max = [] { const char* e = getenv("DUNET_FLAT_ZT_MAX"); return e ? atoi(e) : 6; }();
-    static const int zt_max_npos = [] { const char* e = getenv("DUNET_FLAT_ZT_MAX_NPOS"); return e ? atoi(e) : 0; }();  // ... only where npos >= this
-    for (int cand : {6, 4, 3, 2}) {
-      if (cand > zt_max && npos >= zt_max_npos) continue;
-      if (cand * npos <= 512 && cand <= Dl && Dl % cand == 0) { zt = cand; break; }
+    // ZT: the SMALLEST slab count (dividing D) whose ZT * npos accumulator columns keep the weight stream affordable -- a
+    // 16 KB weight tile feeds ZT * npos / 2 MMA clocks; at >= 160 columns (<= ~50 B/clk/SM; measured at 24^3 with 144 CTAs
+    // streaming concurrently: no slowdown, L2 serves CTAs that walk the same tiles in step) more items beat more re-use:
+    // 24^3 at ZT = 1 has 72 items per sample instead of 36 and the four layers take 132 us instead of 200 (2 windows).
+    static const int min_cols = [] { const char* e = getenv("DUNET_FLAT_MIN_COLS"); return e ? atoi(e) : 160; }();
+    zt = 0;
+    for (int cand : {1, 2, 3, 4, 6})
+      if (cand * npos <= 512 && cand <= Dl && Dl % cand == 0 && cand * npos >= min_cols) { zt = cand; break; }
+    if (!zt) {  // min_cols out of reach: the largest feasible slab count
+      zt = 1;
+      for (int cand : {2, 3, 4, 6}) if (cand * npos <= 512 && cand <= Dl && Dl % cand == 0) zt = cand;
     }
     const int planes = zt + 2, lbo = (ty + 2) * hx * 16, plane_bytes = 8 * lbo;
     const int budget = FLAT_SMEM_MAX - 1024 - 512 - FLAT_EPI_SMEM - FLAT_A_SLACK;
