@@ -473,7 +473,7 @@ def run_b200(args, cfg):
             "gpu_launches": int(launches),
             "parity": parity,
             "checksum": checksum,
-            "roofline": {"bound": "tensor", "kernel": "conv3d_tc64_kernel + conv3d_tc_kernel: every 16-bit-operand 3x3x3 conv launch of rank 0 in the profiled pass (CUDA events "
+            "roofline": {"bound": "tensor", "kernel": "conv3d_tc64_kernel + conv3d_flat_kernel (+ conv3d_tc_kernel): every 16-bit-operand 3x3x3 conv launch of rank 0 in the profiled pass (CUDA events "
                                                       "around each launch); the encoder's split-precision convs (fp16 mode: 3 MMAs per product, 2.6 % of the FLOPs) are listed under split_precision_convs",
                          "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
                          "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kind::f16 MMAs run fp16 and bf16 at the same rate)",
@@ -488,11 +488,12 @@ def run_b200(args, cfg):
                                     "frac": fam_b[i] / fam_ms[i] / 1e6 / peaks["hbm_gbs"], "launches": int(fam_n[i]),
                                     "share_of_profiled_pass": fam_ms[i] / ms_prof}
                              for i, name in ((1, "normalise (IN+LeakyReLU+bias+residual+pool), launches >= 64 MB"), (2, "final 1x1 conv + DDIM update + accumulate"),
-                                             (3, "transposed conv k2s2"), (4, "split-K reduce (6^3 level only; launch-latency bound)"),
+                                             (3, "transposed conv k2s2, launches >= 64 MB"), (9, "transposed conv k2s2, launches < 64 MB (launch-latency bound)"),
+                                             (4, "split-K reduce (split-precision encoder only; the denoiser's is fused into the normalise pass)"),
                                              (6, "normalise, launches < 64 MB (launch-latency bound)"),
                                              (7, "glue: window crop, noise + state init, stitch from the voxel-major accumulator")) if fam_ms[i] > 0},
             "kernel_time_share": dict({n: fam_ms[i] / ms_prof for i, n in enumerate(["conv3x3x3", "normalise_large", "final_ddim", "deconv", "splitk_reduce", "affine_map", "normalise_small", "glue",
-                                                                                     "conv3x3x3_split_precision_encoder"])},
+                                                                                     "conv3x3x3_split_precision_encoder", "deconv_small"])},
                                       sum=sum(fam_ms) / ms_prof, profiled_pass_ms=ms_prof,
                                       note="profiled pass: single stream, events around every launch; shares are of that pass's own elapsed time"),
         }

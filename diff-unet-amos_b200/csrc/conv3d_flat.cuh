@@ -47,6 +47,8 @@ struct ConvFlatArgs {
   int cout, D, H, W;
   int hx, ty, tiles_y, tiles_z, n_tiles, ksplit, batch;
   int ksub;                // K units per 64-channel block: 1 (all 27 taps) or 3 (one tz plane of taps each: finer split-K)
+  int deconv;              // 1: ConvTranspose3d k2 s2 (MODE below): one tap, no halo, rows = (tap, cout), scatter epilogue + bias
+  const float* bias;       // deconv: bias[cout]
   int npos;                // GEMM N: positions per slab (multiple of 16, <= 256)
   int lbo;                 // bytes between the 8-channel chunks of a plane in shared memory: (ty + 2) * hx * 16
   int a_slots, w_slots;    // ring sizes (planes / weight tiles)
@@ -160,7 +162,8 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         const int y0 = it.tiy * a.ty, z0 = it.tiz * ZT;
         for (int u = it.u_lo; u < it.u_hi; ++u) {
           const int cb = a.ksub == 3 ? u / 3 : u, tz = a.ksub == 3 ? u - cb * 3 : 0;
-          const int np = a.ksub == 3 ? ZT : PLANES;
+          const int np = (a.ksub == 3 || a.deconv) ? ZT : PLANES;
+          const int halo = a.deconv ? 0 : 1;
           int ti, chunk0, chunks;
           conv_seg_lookup(a.segs, cb, 8, ti, chunk0, chunks);
           const CUtensorMap* tm = tms[ti];
@@ -168,7 +171,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
           for (int p = 0; p < np; ++p) {
             if (rnd > 0) mbar_wait(a_empty + 8 * slot, (rnd - 1) & 1);
             mbar_arrive_expect_tx(a_full + 8 * slot, plane_bytes);
-            tma_load_4d(a_smem + slot * plane_bytes, tm, a_full + 8 * slot, -8, y0 - 1, z0 + tz + p - 1, c3);
+            tma_load_4d(a_smem + slot * plane_bytes, tm, a_full + 8 * slot, -8 * halo, y0 - halo, z0 + tz + p - halo, c3);
             if (++slot == a.a_slots) { slot = 0; ++rnd; }
           }
         }
@@ -181,8 +184,8 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const FlatItem it = flat_item(a, item);
         // units are contiguous in the packed order [cin block][tap]: a unit is 27 / ksub consecutive tap tiles
-        const int tpu = 27 / a.ksub;
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((size_t)it.ntile * ncb * 27 + (size_t)it.u_lo * tpu) * FLAT_W_BYTES;
+        const int taps = a.deconv ? 1 : 27, tpu = taps / a.ksub;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + ((size_t)it.ntile * ncb * taps + (size_t)it.u_lo * tpu) * FLAT_W_BYTES;
         const int nw = (it.u_hi - it.u_lo) * tpu;
         for (int i = 0; i < nw; ++i) {
           if (rnd > 0) mbar_wait(w_empty + 8 * slot, (rnd - 1) & 1);
@@ -207,8 +210,9 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
         const FlatItem it = flat_item(a, item);
         if (li > 0) { mbar_wait(acc_empty, (li - 1) & 1); tc_fence_after(); }
-        if (a.ksub == 3) {
-          // one tz slice per unit: ZT planes (slab sl reads plane sl), 9 taps
+        if (a.ksub == 3 || a.deconv) {
+          // one tz slice per unit: ZT planes (slab sl reads plane sl), 9 taps -- or the single tap of the transposed conv
+          const int ntap = a.deconv ? 1 : 9;
           for (int u = it.u_lo; u < it.u_hi; ++u) {
             uint32_t pl_lo[ZT], pl_bar[ZT], par[ZT];
 #pragma unroll
@@ -219,7 +223,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
               if (++aslot == a.a_slots) { aslot = 0; ++arnd; }
             }
 #pragma unroll 1
-            for (int tyx = 0; tyx < 9; ++tyx) {
+            for (int tyx = 0; tyx < ntap; ++tyx) {
               mbar_wait(w_full + 8 * wslot, wrnd & 1);
               tc_fence_after();
               if (tyx == 0) {
@@ -325,7 +329,9 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       const int ty_valid = min(a.ty, a.H - y0);
       {  // position table of this item (overlaps the MMAs)
         const int py = et / a.hx, px = et - py * a.hx;
-        tab[et] = (et < a.npos && px < a.W && py < ty_valid) ? py * a.W + px : -1;
+        const bool ok = et < a.npos && px < a.W && py < ty_valid;
+        // conv: voxel offset inside the y-strip; transposed conv: offset of output voxel (2 py, 2 px) in the 2H x 2W slab
+        tab[et] = !ok ? -1 : (a.deconv ? (2 * py) * (2 * a.W) + 2 * px : py * a.W + px);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(FLAT_EPI_WARPS * 32) : "memory");
       mbar_wait(acc_full, li & 1);
@@ -333,9 +339,16 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       if (a.dbg && li == 0 && threadIdx.x == 3 * 32) a.dbg[blockIdx.x * 8 + 4] = clock64();
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
       float s1 = 0.f, s2 = 0.f;
-      const long long plane0 = (long long)it.n * out_chunks + it.ntile * 16 + q * 4;  // C8 plane of this warp's first chunk
-      const long long v0 = ((long long)z0 * a.H + y0) * a.W;                           // voxel (z0, y0, 0)
-      const long long slab = (long long)a.H * a.W;
+      // conv: rows of tile nt are couts nt*128..; transposed conv: tile nt = ((dz, dy), 64-cout block), row = dx * 64 + cout % 64
+      // (pack_deconv_tc_w_kernel), output volume 2D x 2H x 2W
+      const int nblk = a.cout / 64, dzdy = it.ntile / nblk, cblk = it.ntile - dzdy * nblk;
+      const long long plane0 = a.deconv ? (long long)it.n * out_chunks + cblk * 8 + (q & 1) * 4
+                                        : (long long)it.n * out_chunks + it.ntile * 16 + q * 4;  // C8 plane of this warp's first chunk
+      const long long v0 = a.deconv ? ((long long)(2 * z0 + (dzdy >> 1)) * (2 * a.H) + 2 * y0 + (dzdy & 1)) * (2 * a.W) + (q >> 1)
+                                    : ((long long)z0 * a.H + y0) * a.W;                           // voxel (z0, y0, 0)
+      const long long slab = a.deconv ? (long long)8 * a.H * a.W : (long long)a.H * a.W;          // one input z step
+      const long long out_vox = a.deconv ? in_vox * 8 : in_vox;
+      const float my_bias = a.deconv ? a.bias[cblk * 64 + (q & 1) * 32 + lane] : 0.f;
       auto process = [&](int g, const uint32_t (&r)[16]) {
         const int s = g / ngroups, j = g - s * ngroups;
         if (z0 + s >= a.D) return;
@@ -346,7 +359,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
           const int o[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii) {
-            const float v = __uint_as_float(r[i4 * 4 + ii]);
+            const float v = __uint_as_float(r[i4 * 4 + ii]) + my_bias;
             if (o[ii] >= 0) {
               s1 += v;
               s2 = fmaf(v, v, s2);
@@ -370,7 +383,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
               dst[1] = f1;
             } else {
               const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-              store_split<H>(a.out, a.out_lo, (plane0 + chunk) * in_vox + vofs, f);
+              store_split<H>(a.out, a.out_lo, (plane0 + chunk) * out_vox + vofs, f);
             }
           }
         }

@@ -64,7 +64,7 @@ struct ProfRec { cudaEvent_t a, b; int tag; };
 // PROF_CONV_SPLIT: 3x3x3 convs that run in split precision inside a 16-bit plan (the encoder in fp16 mode): 3 MMAs per
 // algorithmic product, reported apart from the 16-bit convs whose roofline is the tensor peak
 enum { PROF_CONV = 0, PROF_NORM = 1, PROF_FINAL = 2, PROF_DECONV = 3, PROF_SPLITK = 4, PROF_OTHER = 5, PROF_NORM_SMALL = 6, PROF_GLUE = 7,
-       PROF_CONV_SPLIT = 8, PROF_TAGS = 12 };
+       PROF_CONV_SPLIT = 8, PROF_DECONV_SMALL = 9, PROF_TAGS = 12 };
 struct Prof {
   bool on = false;
   std::vector<ProfRec> recs;       // event pool, reused across enable() calls
@@ -156,11 +156,11 @@ static int make_act_tmap(CUtensorMap* m, const bf16* base, int planes, int D, in
 }
 
 // Tensor map for the flattened-plane kernel (conv3d_flat.cuh): box = (W + 2 positions, ty + 2 rows, one z, 8 chunks)
-static int make_flat_tmap(CUtensorMap* m, const bf16* base, int planes, int D, int H, int W, int hx, int ty) {
+static int make_flat_tmap(CUtensorMap* m, const bf16* base, int planes, int D, int H, int W, int hx, int ty, int halo = 1) {
   TRY(load_driver_entry());
   cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)planes};
   cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-  cuuint32_t box[4] = {(cuuint32_t)hx * 8, (cuuint32_t)(ty + 2), 1, 8};
+  cuuint32_t box[4] = {(cuuint32_t)hx * 8, (cuuint32_t)(ty + 2 * halo), 1, 8};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -657,7 +657,7 @@ static int launch_conv_tc(const dunet_plan* p, const CUtensorMap (&t)[4], const 
   const long long items = (long long)a.tiles_x * a.tiles_y * a.tiles_z * a.n_tiles * a.ksplit * a.batch;
   // persistent: one CTA per SM (each may own all 512 TMEM columns) walking the work items round-robin
   const long long grid = std::min<long long>(items, (long long)p->num_sms);
-  TRY(prof_begin(MODE == MODE_CONV3 ? conv_tag : PROF_DECONV, st));
+  TRY(prof_begin(conv_tag, st));  // MODE_DECONV2 callers pass their PROF_DECONV / PROF_DECONV_SMALL tag
   launch_k(kern, dim3((unsigned)grid), dim3(CONV_TC_THREADS), Cfg::SMEM_BYTES, st, t[0], t[1], t[2], t[3], a);
   LAUNCH_CHECK();
   TRY(prof_end(st));
@@ -1012,13 +1012,60 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
     b.n_tiles = 8 * d.coutp / 128; b.batch = B; b.dbg = getenv("DUNET_DBG_DECONV") ? g_conv_dbg : nullptr;
     const long long tiles = (long long)b.tiles_x * b.tiles_y * b.tiles_z * B;
     const unsigned grid = (unsigned)std::min<long long>(tiles, p->num_sms);
-    if (PROF_ON) prof_of(p)->bytes[PROF_DECONV] += (double)B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
-    TRY(prof_begin(PROF_DECONV, st));
+    // like the normalise launches: below 64 MB a launch is latency bound and is reported as its own family
+    const double dbytes = (double)B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
+    const int dtag = dbytes >= 64e6 ? PROF_DECONV : PROF_DECONV_SMALL;
+    if (PROF_ON) prof_of(p)->bytes[dtag] += dbytes;
+    TRY(prof_begin(dtag, st));
     if (d.cinp == 64) DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<1, 2, HF>, dim3(grid), dim3(DeconvTc<1, 2>::THREADS), DeconvTc<1, 2>::SMEM_BYTES, st, t[0], b));
     else DUNET_FMT(is_fp16(p), launch_k(deconv2_tc_kernel<2, 2, HF>, dim3(grid), dim3(DeconvTc<2, 2>::THREADS), DeconvTc<2, 2>::SMEM_BYTES, st, t[0], b));
     LAUNCH_CHECK();
     TRY(prof_end(st));
     return 0;
+  }
+  static const bool flat_on = [] { const char* e = getenv("DUNET_FLAT_DECONV"); return !(e && e[0] == '0'); }();
+  if (flat_on && !prec && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV) && W <= 32) {
+    // deep levels (Cin > 128): the flattened-plane kernel in transposed-conv mode (rows = (tap, cout), positions as N, no halo)
+    const int hx = W, ty_max = std::max(1, 256 / hx);
+    const int tiles_y = (H + ty_max - 1) / ty_max, ty = (H + tiles_y - 1) / tiles_y;
+    const int npos = pad_to(ty * hx, 16);
+    int zt = 0;
+    for (int cand : {1, 2, 3, 4, 6}) if (cand * npos <= 512 && cand <= D && D % cand == 0 && cand * npos >= 128) { zt = cand; break; }
+    if (!zt) { zt = 1; for (int cand : {2, 3, 4, 6}) if (cand * npos <= 512 && cand <= D && D % cand == 0) zt = cand; }
+    const int lbo = ty * hx * 16, plane_bytes = 8 * lbo;
+    const int budget = FLAT_SMEM_MAX - 1024 - 512 - FLAT_EPI_SMEM - FLAT_A_SLACK;
+    const int a_slots = std::max(zt, std::min(std::min(16, 3 * zt), (budget - 4 * FLAT_W_BYTES) / plane_bytes));
+    const int w_slots = std::min(8, (budget - a_slots * plane_bytes) / FLAT_W_BYTES);
+    if (w_slots >= 2) {
+      TRY(make_flat_tmap(&t[0], in.hi, B * (d.cinp / 8), D, H, W, hx, ty, 0));
+      t[1] = t[2] = t[3] = t[0];
+      ConvFlatArgs f;
+      memset(&f, 0, sizeof f);
+      f.w = d.packed_tc; f.out = out.hi; f.bias = d.bias; f.deconv = 1;
+      f.segs = make_segs(d.cinp / 64, d.cinp / 8, 0, 0, false);
+      f.cout = d.coutp; f.D = D; f.H = H; f.W = W;
+      f.hx = hx; f.ty = ty; f.tiles_y = tiles_y; f.tiles_z = D / zt; f.n_tiles = 8 * d.coutp / 128; f.batch = B;
+      f.npos = npos; f.lbo = lbo; f.a_slots = a_slots; f.w_slots = w_slots; f.ksplit = 1; f.ksub = 1;
+      const size_t smem = 1024 + (size_t)a_slots * plane_bytes + FLAT_A_SLACK + (size_t)w_slots * FLAT_W_BYTES + FLAT_EPI_SMEM + 512;
+      const long long items = (long long)f.tiles_y * f.tiles_z * f.n_tiles * B;
+      const unsigned grid = (unsigned)std::min<long long>(items, p->num_sms);
+      const double dbytes = (double)B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
+      const int dtag = dbytes >= 64e6 ? PROF_DECONV : PROF_DECONV_SMALL;
+      if (PROF_ON) prof_of(p)->bytes[dtag] += dbytes;
+      TRY(prof_begin(dtag, st));
+      DUNET_FMT(is_fp16(p), {
+        switch (zt) {
+          case 1: launch_k(conv3d_flat_kernel<1, HF>, dim3(grid), dim3(FLAT_THREADS), smem, st, t[0], t[1], t[2], t[3], f); break;
+          case 2: launch_k(conv3d_flat_kernel<2, HF>, dim3(grid), dim3(FLAT_THREADS), smem, st, t[0], t[1], t[2], t[3], f); break;
+          case 3: launch_k(conv3d_flat_kernel<3, HF>, dim3(grid), dim3(FLAT_THREADS), smem, st, t[0], t[1], t[2], t[3], f); break;
+          case 4: launch_k(conv3d_flat_kernel<4, HF>, dim3(grid), dim3(FLAT_THREADS), smem, st, t[0], t[1], t[2], t[3], f); break;
+          default: launch_k(conv3d_flat_kernel<6, HF>, dim3(grid), dim3(FLAT_THREADS), smem, st, t[0], t[1], t[2], t[3], f); break;
+        }
+      });
+      LAUNCH_CHECK();
+      TRY(prof_end(st));
+      return 0;
+    }
   }
   ConvTcArgs a;
   memset(&a, 0, sizeof a);
@@ -1033,9 +1080,11 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
   a.cout = d.coutp; a.D = D; a.H = H; a.W = W;
   a.tiles_x = (W + CONV_TX - 1) / CONV_TX; a.tiles_y = (H + CONV_TY - 1) / CONV_TY; a.tiles_z = (D + 1) / 2;
   a.n_tiles = 8 * d.coutp / 128; a.ksplit = 1; a.batch = B; a.dbg = nullptr;
-  if (PROF_ON) prof_of(p)->bytes[PROF_DECONV] += (prec ? 2.0 : 1.0) * B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
+  const double dbytes = (prec ? 2.0 : 1.0) * B * (double)p->V[lvl_in] * 2.0 * (d.cinp + 8.0 * d.coutp);
+  const int dtag = dbytes >= 64e6 ? PROF_DECONV : PROF_DECONV_SMALL;
+  if (PROF_ON) prof_of(p)->bytes[dtag] += dbytes;
   int rc = 0;
-  DUNET_FMT(fmt_h(p, prec), rc = launch_conv_tc<64, 128, 2, MODE_DECONV2, HF>(p, t, a, st));
+  DUNET_FMT(fmt_h(p, prec), rc = launch_conv_tc<64, 128, 2, MODE_DECONV2, HF>(p, t, a, st, dtag));
   return rc;
 }
 

@@ -82,7 +82,10 @@ def test_conv_zero_padding_is_exact():
 
 @pytest.mark.parametrize("cin,cout,B,dims", [(64, 64, 1, (8, 16, 8)), (128, 64, 2, (6, 6, 6)), (512, 256, 1, (2, 2, 2)),
                                              (256, 128, 1, (12, 12, 12)), (16, 8, 1, (8, 8, 8)), (64, 64, 3, (24, 40, 24)),
-                                             (128, 128, 1, (7, 9, 5))])
+                                             (128, 128, 1, (7, 9, 5)),
+                                             # Cin > 128: the flattened-plane kernel in transposed-conv mode for kernel 0 / 5
+                                             (512, 256, 2, (6, 6, 6)), (256, 128, 2, (12, 12, 12)), (192, 64, 1, (5, 7, 9)),
+                                             (256, 64, 1, (3, 20, 24)), (1024, 512, 1, (6, 6, 6))])
 @pytest.mark.parametrize("fmt", ["bf16", "fp16"])
 def test_deconv2x2x2_tensor_core_vs_fp64(cin, cout, B, dims, fmt):
     """tcgen05 transposed conv (GEMM + scatter epilogue + bias) == conv_transpose3d of the 16-bit-rounded operands."""

@@ -50,7 +50,7 @@ if a.prof:
     msb = (ctypes.c_double * 12)(); cnt = (ctypes.c_uint64 * 12)(); byt = (ctypes.c_double * 12)()
     _lib.check(lib.dunet_profile_read_all(plan, msb, cnt, byt))
     lib.dunet_profile_enable(plan, 0)
-    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "affine-map", "norm-small", "glue", "conv-split-enc", "-", "-", "-"]
+    names = ["conv3x3x3", "normalise", "final+ddim", "deconv", "splitk-reduce", "affine-map", "norm-small", "glue", "conv-split-enc", "deconv-small", "-", "-"]
     tot = sum(msb)
     print("in-situ CUDA-event time per kernel family (one call, batch %d):" % a.batch)
     for i, nme in enumerate(names):
