@@ -315,6 +315,10 @@ def run_b200(args, cfg):
             run_queue([dev_vol])
         # ---------------- device-resident leg: `value` (product configuration, nothing profiled) ----------------
         clocks = ClockSampler(local) if rank == 0 else None  # started BEFORE the barrier: spawning nvidia-smi takes ~0.1 s on rank 0
+        if n_win * cfg["ddim"] * ens < 200:
+            # a step of a few tens of ms (the single-window config): the GPU idled while nvidia-smi was spawned and the clocks
+            # dropped -- one more untimed step right before the timed region (the long configs re-ramp within 1 % of a step)
+            run_queue([dev_vol])
         barrier()
         l0 = lib.dunet_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -79,7 +79,19 @@ enum {
 #define DUNET_FLAG_TC64_CB64 64u /* debug / A-B timing: the Cout = 64 kernel walks 64-channel blocks with a 7-slot plane ring
                                    instead of 32-channel blocks with a 13-slot ring */
 
-/* Environment switches read once by the library (debugging / A-B timing only; none changes results):
+/* Environment switches read once by the library (debugging / A-B timing only).  The first group changes no result; the
+ * DUNET_FLAT* / DUNET_FUSED_SPLITK_NORM switches select a different (equally valid) kernel decomposition of the deep U-Net
+ * levels, i.e. another fp32 summation order: results stay within the tested tolerances but are not bit-identical across
+ * settings (they ARE bit-identical across batch sizes under any one setting: every rule depends on per-sample shapes only).
+ *   DUNET_FLAT=0                 deep levels (row <= 30 voxels, Cout % 128 == 0) on the voxel-as-M generic kernel instead of the
+ *                                swapped-operand flattened-plane kernel (csrc/conv3d_flat.cuh)
+ *   DUNET_FLAT_DECONV=0          transposed convs with Cin > 128 on the generic kernel instead of the flattened-plane kernel
+ *   DUNET_FLAT_MIN_COLS=n        smallest ZT * N accumulator columns an item may have (default 160; weight re-use vs parallelism)
+ *   DUNET_FLAT_SPLIT_ITEMS=n, DUNET_FLAT_TARGET_ITEMS=n, DUNET_FLAT_TZ_SPLIT=0   split-K rule of the flattened-plane kernel
+ *                                (split when a sample has < 36 items, until it has ~48; K units of one tz tap slice)
+ *   DUNET_FUSED_SPLITK_NORM=0    K-split convs reduce their partial tiles in splitk_reduce_stats_kernel + a separate normalise
+ *                                launch instead of the fused splitk_norm_kernel
+ *   DUNET_GEOM_ZT_ITEMS=n, DUNET_GEOM_SPLIT_ITEMS=n   ZT / split-K rule of the generic kernel
  *   DUNET_NO_PDL=1      launch without programmatic stream serialization
  *   DUNET_DUAL_MIN=n    smallest batch DUNET_FLAG_DUAL_STREAM splits (default 4; 2-3 measured within noise)
  *   DUNET_NSTREAMS=2..4 number of sub-batches / internal streams used by DUNET_FLAG_DUAL_STREAM (default 2; 3 and 4 measured slower)
