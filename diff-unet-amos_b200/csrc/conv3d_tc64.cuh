@@ -283,7 +283,12 @@ conv3d_tc64_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         {
           const int gch = cb * Cfg::KCH + chunk;  // 8-channel chunk of the source tensor
           const float4* src = reinterpret_cast<const float4*>(a.in_affine + ((long long)n * (ncb * Cfg::KCH) + gch) * 16);
+          // L2 loads (not the read-only path): the map was written by the kernel this one was pre-launched behind
+#ifdef DUNET_AFFINE_LDG  // A/B build switch
           const float4 s0 = __ldg(src), s1 = __ldg(src + 1), h0 = __ldg(src + 2), h1 = __ldg(src + 3);
+#else
+          const float4 s0 = __ldcg(src), s1 = __ldcg(src + 1), h0 = __ldcg(src + 2), h1 = __ldcg(src + 3);
+#endif
           sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
           sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
 #pragma unroll

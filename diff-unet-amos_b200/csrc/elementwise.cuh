@@ -293,33 +293,90 @@ constexpr int NORM_THREADS = 256;
 // reduction of the partial rows into the affine map of the normalisation (biased variance, eps inside the sqrt, as
 // F.instance_norm).  nseg <= a few hundred rows (one per conv CTA / reduction segment), so this is ~10 KB from L2.
 // sc/sh: 8 floats each; scratch: 16*16 doubles.  Needs >= 256 threads; ends with __syncthreads().
+// One thread's share of the fixed-order reduction: rows g0, g0 + 16, ... of statistic e.  The loads are issued in batches of ten
+// before the first add, so the chain is one L2 round trip per 160 rows instead of one per row (measured: the dependent-load loop
+// cost every consumer block ~4 us of prologue at 148 rows); missing rows add +0.0, so the sum is the same as the plain loop's.
+__device__ __forceinline__ double stats_row_sum(const float* __restrict__ partial, int nseg, int plane, int g0, int e) {
+  const float* __restrict__ p = partial + ((long long)plane * nseg) * 16 + e;
+  double acc = 0.0;
+  for (int base = g0; base < nseg; base += 160) {
+    float v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const int g = base + 16 * i;
+      v[i] = g < nseg ? __ldcg(p + (long long)g * 16) : 0.f;  // L2: rows written by the kernel this one was pre-launched behind
+    }
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc += (double)v[i];
+  }
+  return acc;
+}
+// second stage for one plane: 16 x 16 partial sums in scratch -> scale / shift of its 8 channels (threads 0..7)
+__device__ __forceinline__ void stats_finish(const double* scratch, int plane, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, int chunks, double count, float eps, float* sc,
+                                             float* sh, int j) {
+  double s = 0.0, q = 0.0;
+  for (int g = 0; g < 16; ++g) {
+    s += scratch[g * 16 + j];
+    q += scratch[g * 16 + 8 + j];
+  }
+  const int c = (plane % chunks) * 8 + j;
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float scale = rstd * gamma[c];
+  sc[j] = scale;
+  sh[j] = beta[c] - (float)mean * scale;
+}
 __device__ __forceinline__ void stats_to_affine(const float* __restrict__ partial, int nseg, int plane,
                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                 int chunks, double count, float eps, float* sc, float* sh,
                                                 double* scratch) {
   if (threadIdx.x < 256) {
     const int e = threadIdx.x & 15, g0 = threadIdx.x >> 4;
-    double acc = 0.0;
-    for (int g = g0; g < nseg; g += 16) acc += (double)partial[((long long)plane * nseg + g) * 16 + e];
-    scratch[g0 * 16 + e] = acc;
+    scratch[g0 * 16 + e] = stats_row_sum(partial, nseg, plane, g0, e);
   }
   __syncthreads();
-  if (threadIdx.x < 8) {
-    double s = 0.0, q = 0.0;
-    for (int g = 0; g < 16; ++g) {
-      s += scratch[g * 16 + threadIdx.x];
-      q += scratch[g * 16 + 8 + threadIdx.x];
+  if (threadIdx.x < 8) stats_finish(scratch, plane, gamma, beta, chunks, count, eps, sc, sh, threadIdx.x);
+  __syncthreads();
+}
+// The same for `np` consecutive planes (the final kernel needs all 64 channels of its sample): four planes per pass, their
+// row loads all in flight together.  sc / sh: np * 8 floats; scratch: 4 * 256 doubles.  Same arithmetic, same order per plane.
+__device__ __forceinline__ void stats_to_affine_planes(const float* __restrict__ partial, int nseg, int plane0, int np,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int chunks, double count, float eps, float* sc, float* sh,
+                                                       double* scratch) {
+  for (int k0 = 0; k0 < np; k0 += 4) {
+    if (threadIdx.x < 256) {
+      const int e = threadIdx.x & 15, g0 = threadIdx.x >> 4;
+      if (nseg <= 160) {
+        float v[4][10];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int i = 0; i < 10; ++i) {
+            const int g = g0 + 16 * i;
+            v[k][i] = (k0 + k < np && g < nseg) ? __ldcg(partial + ((long long)(plane0 + k0 + k) * nseg + g) * 16 + e) : 0.f;
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < 10; ++i) acc += (double)v[k][i];
+          scratch[k * 256 + g0 * 16 + e] = acc;
+        }
+      } else {
+        for (int k = 0; k < 4 && k0 + k < np; ++k) scratch[k * 256 + g0 * 16 + e] = stats_row_sum(partial, nseg, plane0 + k0 + k, g0, e);
+      }
     }
-    const int c = (plane % chunks) * 8 + threadIdx.x;
-    const double mean = s / count;
-    double var = q / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float scale = rstd * gamma[c];
-    sc[threadIdx.x] = scale;
-    sh[threadIdx.x] = beta[c] - (float)mean * scale;
+    __syncthreads();
+    if (threadIdx.x < 32 && k0 + (threadIdx.x >> 3) < np) {
+      const int k = threadIdx.x >> 3, j = threadIdx.x & 7;
+      stats_finish(scratch + k * 256, plane0 + k0 + k, gamma, beta, chunks, count, eps, sc + (k0 + k) * 8, sh + (k0 + k) * 8, j);
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // The affine map alone, for consumers that normalise on load (conv3d_tc64 FUSE): out[plane][16] = scale[8], shift[8].
@@ -565,7 +622,7 @@ __global__ void __launch_bounds__(256) splitk_norm_kernel(SplitkNormArgs a) {
     for (int j = 0; j < 8; ++j) f[u][j] = 0.f;
     if (v < vox) {
       for (int k = 0; k < a.ksplit; ++k) {
-        const float4 a0 = p[k * kstride + v * 2], a1 = p[k * kstride + v * 2 + 1];
+        const float4 a0 = __ldcg(p + k * kstride + v * 2), a1 = __ldcg(p + k * kstride + v * 2 + 1);
         f[u][0] += a0.x; f[u][1] += a0.y; f[u][2] += a0.z; f[u][3] += a0.w;
         f[u][4] += a1.x; f[u][5] += a1.y; f[u][6] += a1.z; f[u][7] += a1.w;
       }
@@ -750,7 +807,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
   __shared__ uint32_t wfrag[(FINAL_MAX_F / 16) * NT * 2 * 2 * 32];
   __shared__ float sbias[NT * 8];
   __shared__ __align__(8) float nsc[FINAL_MAX_F], nsh[FINAL_MAX_F];
-  __shared__ double scratch[256];
+  __shared__ double scratch[4 * 256];
   constexpr int nks = NKS;
   const int fch = a.F / 8;
   const int n = blockIdx.y;
@@ -778,10 +835,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) final_ddim_kernel(FinalDdimArgs
   }
   for (int i = threadIdx.x; i < NT * 8; i += FINAL_THREADS) sbias[i] = i < a.C ? a.b[i] : 0.f;
   pdl_wait();  // the weight fragments above are plan constants; everything below depends on the previous kernels
-  if (a.partial) {
-    for (int k = 0; k < fch; ++k)
-      stats_to_affine(a.partial, a.nseg, n * fch + k, a.gamma, a.beta, fch, (double)a.vox, a.eps, nsc + k * 8, nsh + k * 8, scratch);
-  }
+  if (a.partial) stats_to_affine_planes(a.partial, a.nseg, n * fch, fch, a.gamma, a.beta, fch, (double)a.vox, a.eps, nsc, nsh, scratch);
   __syncthreads();
 
   const float s_abp = sqrtf(a.abp), s_1mabp = sqrtf(1.f - a.abp - 0.f);
