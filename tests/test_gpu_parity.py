@@ -556,6 +556,27 @@ def test_workspace_and_output_guards_stay_untouched(precision):
     assert bool(torch.isnan(obig[:G // 4]).all()) and bool(torch.isnan(obig[G // 4 + n_out:]).all())
 
 
+@pytest.mark.parametrize("S,B,precision", [(32, 3, "fp16"), (96, 2, "fp16"), (48, 2, "bf16"), (32, 2, "fp32x3")])
+def test_uninitialised_workspace_is_never_read(S, B, precision):
+    """Every byte of the workspace a kernel reads was written earlier in the same call: a workspace pre-filled with NaN
+    patterns (0xFF: NaN as fp16, bf16 and fp32) gives bit for bit the result of a zero-filled one.  Covers the halo-plane
+    over-reads of the flattened-plane kernel (discarded columns only), padded channel planes, K-split partial tiles and the
+    statistics rows at the production 96^3 level shapes (24^3 / 12^3 / 6^3)."""
+    cout = 3
+    m = _build(cout, S, oracle_model.DEFAULT_FEATURES, batch_max=B, num_steps=2, precision=precision)
+    image, noise = seeded_image((B, 1, S, S, S)).cuda(), seeded_noise((B, cout, S, S, S)).cuda()
+    m(image=image, pred_type="ddim_sample", noise=noise)  # allocates the workspace, packs the weights
+    ws = m._rt.workspaces["max"]
+    outs = []
+    for fill in (0x00, 0xFF, 0x7B):
+        ws.fill_(fill)
+        m._rt.ws_batch = None  # embeddings held in the workspace are gone
+        m._rt.emb_token = None
+        outs.append(m(image=image, pred_type="ddim_sample", noise=noise).clone())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # round 2: fused window loop, library noise generator, per-sample timesteps, use_amp mapping
 # ---------------------------------------------------------------------------------------------------------------------
