@@ -81,6 +81,7 @@ SIGNATURES = {
     "dunet_dice_counts": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "dunet_op_conv3x3x3": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, POINTER(c_int32), c_int32, c_void_p]),
     "dunet_op_deconv2x2x2": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int32, POINTER(c_int32), c_int32, c_void_p]),
+    "dunet_debug_conv_geometry": (c_int32, [POINTER(c_int32), c_int32, c_int32, c_uint32, POINTER(c_int32)]),
     "dunet_debug_set_conv_timeline": (c_int32, [c_void_p]),
     "dunet_profile_enable": (c_int32, [c_void_p, c_int32]),
     "dunet_profile_read": (c_int32, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(ctypes.c_double)]),

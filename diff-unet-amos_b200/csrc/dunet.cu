@@ -2180,6 +2180,24 @@ int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, con
   return rc;
 }
 
+int dunet_debug_conv_geometry(const int32_t dims[3], int32_t cin, int32_t cout, uint32_t flags, int32_t out[16]) {
+  if (!dims || !out || cin < 1 || cout < 1 || dims[0] < 1 || dims[1] < 1 || dims[2] < 1) return fail(DUNET_E_INVALID, "bad argument");
+  dunet_plan tmp;  // geometry fields only; no CUDA call is made
+  memset(&tmp.cfg, 0, sizeof tmp.cfg);
+  tmp.cfg.flags = flags;
+  tmp.D[0] = dims[0]; tmp.H[0] = dims[1]; tmp.W[0] = dims[2];
+  tmp.V[0] = (long long)dims[0] * dims[1] * dims[2];
+  ConvW c;
+  c.shape(cin, cin <= 32 ? 32 : pad_to(cin, 64), 0, 0, cout, (flags & DUNET_FLAG_FP32X3) ? 3 : 1);
+  const ConvGeom g = conv_geom(&tmp, c, 0, 1);
+  const bool tc64 = !g.flat && c.coutp == 64 && g.ksplit == 1 && g.zt == CONV_ZT && !(flags & (DUNET_FLAG_GENERIC_CONV | DUNET_FLAG_REF_CONV));
+  out[0] = g.flat ? 2 : (tc64 ? 0 : 1);
+  out[1] = g.zt; out[2] = g.tiles_x; out[3] = g.tiles_y; out[4] = g.tiles_z; out[5] = g.ksplit; out[6] = g.flat ? g.ksub : 1;
+  out[7] = g.hx; out[8] = g.ty; out[9] = g.npos; out[10] = g.a_slots; out[11] = g.w_slots; out[12] = g.flat_smem;
+  out[13] = g.tiles * c.n_tiles; out[14] = c.n_tiles; out[15] = c.ncb();
+  return 0;
+}
+
 int dunet_debug_set_conv_timeline(int64_t* dev_buffer) {
   g_conv_dbg = reinterpret_cast<long long*>(dev_buffer);
   g_conv_dbg_count = 0;

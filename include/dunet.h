@@ -300,6 +300,14 @@ int dunet_op_conv3x3x3(const float* src0, int32_t c0, const float* src1, int32_t
 int dunet_op_deconv2x2x2(const float* src, int32_t cin, const float* weight, const float* bias, int32_t cout, float* out,
                          int32_t batch, const int32_t dims[3], int32_t use_ref_kernel, void* stream);
 
+/* Host-only (no CUDA call, works without a GPU): the kernel and tiling a 3x3x3 conv layer cin -> cout gets on a U-Net level of
+ * dims = (D, H, W) voxels per sample under plan flags `flags`.  The decision is a function of per-sample shapes only (never of
+ * the batch), which is what keeps batching bit-transparent.  out[16] = { kernel (0 = Cout-64 z-stacked conv3d_tc64, 1 = generic
+ * voxel-as-M conv3d_tc, 2 = flattened-plane conv3d_flat), zt, tiles_x, tiles_y, tiles_z, ksplit, K units per 64-channel block
+ * (1 or 3), hx, ty, npos, plane-ring slots, weight-ring slots, dynamic shared memory bytes (kernel 2), work items per sample and
+ * K split, cout tiles, 64-channel input blocks }.  Fields 7-12 are 0 unless kernel == 2. */
+int dunet_debug_conv_geometry(const int32_t dims[3], int32_t cin, int32_t cout, uint32_t flags, int32_t out[16]);
+
 /* tools only: when non-NULL every conv CTA writes 8 clock64 stamps to dev_buffer[cta * 8 ..] (kernel start, first MMA
  * batch issued, last MMA committed, accumulators complete, epilogue done).  PROCESS-GLOBAL debugging hook (the one
  * piece of library state that is not per plan): it applies to every plan's generic conv launches until reset. */
@@ -314,7 +322,8 @@ int dunet_profile_read(dunet_plan* plan, double* conv_ms, uint64_t* conv_launche
 /* per kernel family, arrays of 12 entries: 0 conv3x3x3 (16-bit operands; also fp32x3 plans), 1 normalise (launches moving
  * >= 64 MB), 2 final+DDIM, 3 transposed conv, 4 split-K reduce, 5 other (affine-map kernel), 6 normalise launches below 64 MB
  * (launch-latency bound), 7 glue (window crop, noise + state init, stitch), 8 conv3x3x3 running in split precision inside a
- * 16-bit plan (the encoder in fp16 mode: 3 MMAs per algorithmic product), 9-11 unused.  For the two conv families
+ * 16-bit plan (the encoder in fp16 mode: 3 MMAs per algorithmic product), 9 transposed-conv launches below 64 MB (tag 3 then
+ * holds the launches >= 64 MB), 10-11 unused.  For the two conv families
  * bytes_by_tag holds ALGORITHMIC FLOPs instead of bytes.
  * bytes_by_tag (nullable): ALGORITHMIC HBM bytes of the bandwidth-bound families (normalise: 4 B/element (+2 residual,
  * +0.25 pooled); final+DDIM: per voxel 2F + 16C (+2C re-pack); transposed conv: 2(Cin + 8 Cout) per input voxel). */

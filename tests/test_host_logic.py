@@ -201,3 +201,54 @@ def test_window_queue_shares_balance_and_cover():
             assert max(per_rank) == min(per_rank)
         flat = owner.reshape(-1)
         assert (np.diff(flat) >= 0).all()  # contiguous, rank order = queue order
+
+
+def _conv_geometry(dims, cin, cout, flags=0):
+    out = (ctypes.c_int32 * 16)()
+    _lib.check(_lib.load().dunet_debug_conv_geometry(_lib.i32x3(dims), cin, cout, flags, out))
+    keys = ["kernel", "zt", "tiles_x", "tiles_y", "tiles_z", "ksplit", "ksub", "hx", "ty", "npos", "a_slots", "w_slots", "smem",
+            "items", "n_tiles", "ncb"]
+    return dict(zip(keys, list(out)))
+
+
+def test_deep_level_conv_geometry_known_answers():
+    """The tiling of the deep U-Net levels of a 96^3 window (host logic of csrc/conv3d_flat.cuh):
+    flattened-plane kernel, N = positions of a (ty x W+2) halo-plane strip, smallest ZT with >= 160 accumulator columns,
+    split-K until a sample has ~48 items.  No GPU needed: the decision is a pure function of per-sample shapes."""
+    g = _conv_geometry((24, 24, 24), 128, 128)
+    assert (g["kernel"], g["hx"], g["ty"], g["npos"], g["zt"], g["tiles_y"], g["tiles_z"], g["ksplit"]) == (2, 26, 8, 208, 1, 3, 24, 1)
+    assert g["items"] == 72
+    g = _conv_geometry((12, 12, 12), 256, 256)
+    assert (g["kernel"], g["hx"], g["ty"], g["npos"], g["zt"], g["ksplit"], g["ksub"], g["items"]) == (2, 14, 12, 176, 1, 2, 1, 24)
+    g = _conv_geometry((12, 12, 12), 128, 256)  # 24 items per sample: split in two, one 64-channel block each
+    assert (g["kernel"], g["ksplit"], g["ksub"]) == (2, 2, 1)
+    g = _conv_geometry((6, 6, 6), 512, 512)
+    assert (g["kernel"], g["hx"], g["ty"], g["npos"], g["zt"], g["ksplit"], g["ksub"], g["items"]) == (2, 8, 6, 48, 6, 12, 3, 4)
+    # not on the flattened-plane kernel: Cout = 64 layers (z-stacked kernel), rows longer than 30 voxels, debug flags
+    assert _conv_geometry((96, 96, 96), 64, 64)["kernel"] == 0
+    assert _conv_geometry((48, 48, 48), 64, 128)["kernel"] == 1
+    assert _conv_geometry((24, 24, 24), 128, 128, flags=_lib.DUNET_FLAG_GENERIC_CONV)["kernel"] == 1
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 128), (128, 128), (256, 128), (256, 256), (512, 256), (512, 512), (1024, 1024), (96, 384)])
+def test_flat_conv_geometry_invariants(cin, cout):
+    """For every level shape the flattened-plane kernel accepts: the strip covers the volume, N and the accumulators fit the
+    instruction / TMEM limits, the rings hold one K unit, the shared memory fits, the split leaves every K slice non-empty."""
+    for D in (2, 3, 4, 6, 8, 9, 12, 16, 20, 24, 30):
+        for H in (2, 5, 6, 8, 12, 16, 24, 30, 48, 96):
+            for W in (2, 3, 6, 8, 12, 16, 24, 30):
+                g = _conv_geometry((D, H, W), cin, cout)
+                assert g["kernel"] == 2, (D, H, W)
+                assert g["hx"] == W + 2 and g["hx"] * 8 <= 256                      # TMA box: inner dimension <= 256 elements
+                assert g["npos"] % 16 == 0 and 16 <= g["npos"] <= 256              # tcgen05 N at M = 128
+                assert g["ty"] * g["hx"] - 2 <= g["npos"] < g["ty"] * g["hx"] - 2 + 16
+                assert g["ty"] + 2 <= 256                                          # TMA box rows
+                assert g["tiles_y"] * g["ty"] >= H > (g["tiles_y"] - 1) * g["ty"]  # strips cover H, none is empty
+                assert g["zt"] in (1, 2, 3, 4, 6) and D % g["zt"] == 0 and g["tiles_z"] * g["zt"] == D
+                assert g["zt"] * g["npos"] <= 512                                  # TMEM columns
+                assert g["a_slots"] >= g["zt"] + 2 and g["w_slots"] >= 2 and g["smem"] <= 232448
+                assert g["smem"] > 116 * 1024                                      # one CTA per SM (each allocates all of TMEM)
+                assert g["ksub"] in (1, 3) and 1 <= g["ksplit"] <= g["ncb"] * g["ksub"] and g["ksplit"] <= 16
+                assert g["items"] == g["tiles_y"] * g["tiles_z"] * g["n_tiles"]
+    # rows of more than 30 voxels stay on the voxel-as-M kernels
+    assert _conv_geometry((8, 8, 31), cin, cout)["kernel"] != 2
