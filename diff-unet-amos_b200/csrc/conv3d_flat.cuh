@@ -116,9 +116,13 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
   const uint32_t bars = stage_smem + FLAT_EPI_SMEM;
   const uint32_t a_full = bars, a_empty = bars + 8 * a.a_slots;
   const uint32_t w_full = bars + 16 * a.a_slots, w_empty = w_full + 8 * a.w_slots;
-  const uint32_t acc_full = w_empty + 8 * a.w_slots;
-  const uint32_t acc_empty = acc_full + 8;
-  const uint32_t tmem_slot = acc_empty + 8;
+  const uint32_t acc_full = w_empty + 8 * a.w_slots;   // [2]
+  const uint32_t acc_empty = acc_full + 16;              // [2]
+  const uint32_t tmem_slot = acc_empty + 16;
+  // accumulators double-buffered in TMEM when two sets fit: the epilogue of an item then overlaps the MMAs of the CTA's next
+  // item (launches with more items than SMs: 4+ windows per launch, the wide variant)
+  const int acc_cols = ZT * a.npos;
+  const int nbuf = 2 * acc_cols <= 512 ? 2 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncb = a.segs.ncb;
@@ -128,8 +132,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
     if (a.dbg) a.dbg[blockIdx.x * 8 + 0] = clock64();
     for (int i = 0; i < a.a_slots; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < a.w_slots; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(w_empty + 8 * i, 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, FLAT_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, FLAT_EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -209,7 +212,9 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       bool first_w = true;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
         const FlatItem it = flat_item(a, item);
-        if (li > 0) { mbar_wait(acc_empty, (li - 1) & 1); tc_fence_after(); }
+        const int buf = li % nbuf, use = li / nbuf;
+        if (use > 0) { mbar_wait(acc_empty + 8 * buf, (use - 1) & 1); tc_fence_after(); }
+        const uint32_t acc_base = tmem_base + buf * acc_cols;
         if (a.ksub == 3 || a.deconv) {
           // one tz slice per unit: ZT planes (slab sl reads plane sl), 9 taps -- or the single tap of the transposed conv
           const int ntap = a.deconv ? 1 : 9;
@@ -242,7 +247,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
                 const uint32_t pl = pl_lo[sl] + tap16;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16_lh(tmem_base + sl * a.npos, wl + k * k_step_w, w_hi, pl + k * k_step_p, p_hi, idesc, k == 0 ? acc0 : 1u);
+                  umma_bf16_lh(acc_base + sl * a.npos, wl + k * k_step_w, w_hi, pl + k * k_step_p, p_hi, idesc, k == 0 ? acc0 : 1u);
               }
               umma_commit(w_empty + 8 * wslot);
               if (++wslot == a.w_slots) { wslot = 0; ++wrnd; }
@@ -281,7 +286,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
               const uint32_t pl = pl_lo[sl + TZI] + tap16;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16_lh(tmem_base + sl * a.npos, wl + k * k_step_w, w_hi, pl + k * k_step_p, p_hi, idesc, k == 0 ? acc0 : 1u);
+                umma_bf16_lh(acc_base + sl * a.npos, wl + k * k_step_w, w_hi, pl + k * k_step_p, p_hi, idesc, k == 0 ? acc0 : 1u);
             }
             umma_commit(w_empty + 8 * wslot);
             if (++wslot == a.w_slots) { wslot = 0; ++wrnd; }
@@ -297,7 +302,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
 #pragma unroll
           for (int p = 2; p < PLANES; ++p) umma_commit(a_empty + pl_bar[p]);
         }
-        umma_commit(acc_full);
+        umma_commit(acc_full + 8 * buf);
       }
       if (a.dbg) a.dbg[blockIdx.x * 8 + 2] = clock64();
     }
@@ -334,10 +339,11 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
         tab[et] = !ok ? -1 : (a.deconv ? (2 * py) * (2 * a.W) + 2 * px : py * a.W + px);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(FLAT_EPI_WARPS * 32) : "memory");
-      mbar_wait(acc_full, li & 1);
+      const int buf = li % nbuf, use = li / nbuf;
+      mbar_wait(acc_full + 8 * buf, use & 1);
       tc_fence_after();
       if (a.dbg && li == 0 && threadIdx.x == 3 * 32) a.dbg[blockIdx.x * 8 + 4] = clock64();
-      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols;
       float s1 = 0.f, s2 = 0.f;
       // conv: rows of tile nt are couts nt*128..; transposed conv: tile nt = ((dz, dy), 64-cout block), row = dx * 64 + cout % 64
       // (pack_deconv_tc_w_kernel), output volume 2D x 2H x 2W
@@ -407,7 +413,7 @@ conv3d_flat_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
+      if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
       // the two warps of a quadrant each hold the sums of their column groups: added in a fixed order (part 0 + part 1)
       if (part == 1) { xch[(q * 32 + lane) * 2] = s1; xch[(q * 32 + lane) * 2 + 1] = s2; }
       asm volatile("bar.sync 1, %0;" ::"n"(FLAT_EPI_WARPS * 32) : "memory");  // also: the table is free for the next item
