@@ -17,8 +17,12 @@
 //   * epilogue: a thread owns one output CHANNEL (TMEM lane), so the InstanceNorm statistics are plain per-thread sums (no
 //     butterfly); the [channel][position] accumulators are transposed through a small per-warp staging buffer into the
 //     C8-planar 16-byte vectors of the activation layout.
-//   * split-K (12^3 / 6^3: too few positions to fill the GPU otherwise) writes fp32 partial tiles for
-//     splitk_reduce_stats_kernel, exactly like the voxel-as-M kernel.
+//   * split-K (12^3 / 6^3: too few positions to fill the GPU otherwise), in units of 64-channel blocks or of one tz slice
+//     of taps, writes fp32 partial tiles [ks][n][cout/8][voxels][8] like the voxel-as-M kernel; splitk_norm_kernel (or
+//     splitk_reduce_stats_kernel in split precision) sums them in a fixed order.
+//   * accumulators are double-buffered in TMEM when two sets fit, for CTAs that own several items.
+//   * transposed-conv mode (ConvTranspose3d k2 s2 with Cin > 128, reference denoiser.py:161-170): one tap, no halo, rows =
+//     (tap, cout) of the packed deconv weight tile, epilogue adds the bias and scatters to (2z+dz, 2y+dy, 2x+dx).
 //
 // Warp roles: 0 = plane producer (TMA), 1 = weight producer (bulk copy), 2 = MMA issuer + TMEM owner, 3..10 = epilogue
 // (two warps per TMEM lane quadrant, alternating 16-column groups).
@@ -47,7 +51,7 @@ struct ConvFlatArgs {
   int cout, D, H, W;
   int hx, ty, tiles_y, tiles_z, n_tiles, ksplit, batch;
   int ksub;                // K units per 64-channel block: 1 (all 27 taps) or 3 (one tz plane of taps each: finer split-K)
-  int deconv;              // 1: ConvTranspose3d k2 s2 (MODE below): one tap, no halo, rows = (tap, cout), scatter epilogue + bias
+  int deconv;              // 1: ConvTranspose3d k2 s2: one tap, no halo, rows = (tap, cout), scatter epilogue + bias
   const float* bias;       // deconv: bias[cout]
   int npos;                // GEMM N: positions per slab (multiple of 16, <= 256)
   int lbo;                 // bytes between the 8-channel chunks of a plane in shared memory: (ty + 2) * hx * 16
@@ -55,17 +59,6 @@ struct ConvFlatArgs {
   long long* dbg;
 };
 
-// one value of one channel -> the activation tensor (16-bit, or a bf16 hi + lo pair in split precision)
-template <bool H>
-__device__ __forceinline__ void store_one(__nv_bfloat16* out, __nv_bfloat16* out_lo, long long idx, float v) {
-  if constexpr (H) {
-    reinterpret_cast<__half*>(out)[idx] = __float2half_rn(v);
-  } else {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[idx] = h;
-    if (out_lo) out_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
-  }
-}
 // TMEM -> registers split into issue and wait, so that the next load is in flight while the previous registers are used.
 // The wait takes the registers as read-write operands: nothing that uses them can be scheduled above it.
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
