@@ -899,7 +899,8 @@ static int run_norm(const dunet_plan* p, const ConvW& c, Act raw, const float* p
   }
   // ~4 resident blocks per SM in total, each streaming a long contiguous range of one 8-channel plane (the
   // statistics prologue is paid once per block)
-  const int per_plane = std::max(1, (148 * 8 + planes - 1) / planes);
+  static const int norm_grid = [] { const char* e = getenv("DUNET_NORM_GRID"); return e ? atoi(e) : 8; }();  // blocks per SM (A/B timing)
+  const int per_plane = std::max(1, (148 * norm_grid + planes - 1) / planes);
   // one bf16 read + one bf16 write per element (+ read of the residual, + 1/8 write of the pooled tensor); launches that move
   // less than 64 MB are launch-latency bound and are reported as their own family so that the HBM roofline of the large
   // ones stays readable
@@ -1179,7 +1180,8 @@ static void final_args_common(dunet_plan* p, FinalDdimArgs& a, uint8_t* ws, cons
 }
 
 static int launch_final(dunet_plan* p, const FinalDdimArgs& a, cudaStream_t st) {
-  const dim3 grid(grid_for((a.vox + 15) / 16 * 32, FINAL_THREADS, std::max(1, 148 * 3 / a.batch)), a.batch);
+  static const int final_grid = [] { const char* e = getenv("DUNET_FINAL_GRID"); return e ? atoi(e) : 3; }();  // blocks per SM (A/B timing)
+  const dim3 grid(grid_for((a.vox + 15) / 16 * 32, FINAL_THREADS, std::max(1, 148 * final_grid / a.batch)), a.batch);
   if (a.F != 64 && a.F != 128) return fail(DUNET_E_UNSUPPORTED, "final conv: padded features[5] must be 64 or 128");
   const bool prec = a.feat_lo != nullptr;
 #define DUNET_FINAL(NT)                                                                            \

@@ -95,6 +95,7 @@ enum {
  *   DUNET_NO_PDL=1      launch without programmatic stream serialization
  *   DUNET_DUAL_MIN=n    smallest batch DUNET_FLAG_DUAL_STREAM splits (default 4; 2-3 measured within noise)
  *   DUNET_NSTREAMS=2..4 number of sub-batches / internal streams used by DUNET_FLAG_DUAL_STREAM (default 2; 3 and 4 measured slower)
+ *   DUNET_NORM_GRID=n, DUNET_FINAL_GRID=n   blocks per SM of the normalise / final+DDIM launches (defaults 8 / 3; 2-32 measured slower)
  *   DUNET_DBG_LAUNCH=k, DUNET_DBG_DECONV=1   which launch writes the per-CTA timeline (dunet_debug_set_conv_timeline) */
 
 typedef struct dunet_plan dunet_plan;
