@@ -43,7 +43,8 @@ enum {
 #define DUNET_FLAG_REF_CONV 1u /* debug: run 3x3x3 convs on the CUDA-core reference kernel instead of tcgen05 (tests) */
 #define DUNET_FLAG_KEEP_FP32_WEIGHTS 2u /* debug: keep fp32 copies of conv weights (needed by DUNET_FLAG_REF_CONV) */
 
-#define DUNET_FLAG_GENERIC_CONV 4u /* debug: route Cout = 64 convs through the generic tcgen05 kernel (no z-stacking) */
+#define DUNET_FLAG_GENERIC_CONV 4u /* debug: every 3x3x3 / transposed conv on the generic voxel-as-M tcgen05 kernel (no Cout = 64
+                                     z-stacked kernel, no flattened-plane kernel for the deep levels) */
 
 #define DUNET_FLAG_DUAL_STREAM 8u /* batches of >= 4 windows run as two half batches on two internal streams (forked from /
                                     joined into the caller's stream with events, no host synchronisation): the HBM-bound
