@@ -556,6 +556,19 @@ def test_workspace_and_output_guards_stay_untouched(precision):
     assert bool(torch.isnan(obig[:G // 4]).all()) and bool(torch.isnan(obig[G // 4 + n_out:]).all())
 
 
+def test_results_are_deterministic_run_to_run():
+    """Fixed-order reductions everywhere (statistics rows, K-split partial tiles, stitching): the same call gives the same bits
+    every time, with unrelated traffic in between (tools/determinism_soak.py runs hundreds of repetitions of this)."""
+    cout, S = 3, 96
+    m = _build(cout, S, oracle_model.DEFAULT_FEATURES, batch_max=2, num_steps=2)
+    image, noise = seeded_image((2, 1, S, S, S)).cuda(), seeded_noise((2, cout, S, S, S)).cuda()
+    ref = m(image=image, pred_type="ddim_sample", noise=noise).clone()
+    junk = torch.empty(32 << 20, device="cuda")
+    for _ in range(6):
+        junk.normal_()
+        assert torch.equal(m(image=image, pred_type="ddim_sample", noise=noise), ref)
+
+
 @pytest.mark.parametrize("S,B,precision", [(32, 3, "fp16"), (96, 2, "fp16"), (48, 2, "bf16"), (32, 2, "fp32x3")])
 def test_uninitialised_workspace_is_never_read(S, B, precision):
     """Every byte of the workspace a kernel reads was written earlier in the same call: a workspace pre-filled with NaN
