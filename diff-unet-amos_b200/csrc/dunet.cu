@@ -1005,7 +1005,10 @@ static int run_deconv(const dunet_plan* p, const DeconvW& d, Act in, Act out, in
     if (!in.lo || !out.lo) return fail(DUNET_E_STATE, "fp32x3 transposed conv needs hi + lo tensors");
     TRY(make_act_tmap(&t[1], in.lo, B * (d.cinp / 8), D, H, W, 8, 0));
   }
-  if (d.cinp <= 128 && !prec && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {  // persistent, HBM-write-bound variant
+  // A/B: transposed convs with Cin >= this and a row of <= 32 voxels go to the flattened-plane kernel (default: only Cin > 128)
+  static const int flat_min_cin = [] { const char* e = getenv("DUNET_FLAT_DECONV_MIN_CIN"); return e ? atoi(e) : 129; }();
+  const bool flat_first = d.cinp >= flat_min_cin && W <= 32;
+  if (d.cinp <= 128 && !flat_first && !prec && !(p->cfg.flags & DUNET_FLAG_GENERIC_CONV)) {  // persistent, HBM-write-bound variant
     DeconvTcArgs b;
     memset(&b, 0, sizeof b);
     b.w = d.packed_tc; b.out = out.hi; b.bias = d.bias; b.chunks_in = d.cinp / 8; b.cout = d.coutp; b.D = D; b.H = H; b.W = W;

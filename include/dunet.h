@@ -87,6 +87,8 @@ enum {
  *   DUNET_FLAT=0                 deep levels (row <= 30 voxels, Cout % 128 == 0) on the voxel-as-M generic kernel instead of the
  *                                swapped-operand flattened-plane kernel (csrc/conv3d_flat.cuh)
  *   DUNET_FLAT_DECONV=0          transposed convs with Cin > 128 on the generic kernel instead of the flattened-plane kernel
+ *   DUNET_FLAT_DECONV_MIN_CIN=n  smallest Cin the flattened-plane kernel takes in transposed-conv mode (default 129; with 64 the
+ *                                24 -> 48 up-conv moves off the persistent deconv2_tc kernel: measured 37 vs 19 us, 2 windows)
  *   DUNET_FLAT_MIN_COLS=n        smallest ZT * N accumulator columns an item may have (default 160; weight re-use vs parallelism)
  *   DUNET_FLAT_SPLIT_ITEMS=n, DUNET_FLAT_TARGET_ITEMS=n, DUNET_FLAT_TZ_SPLIT=0   split-K rule of the flattened-plane kernel
  *                                (split when a sample has < 36 items, until it has ~48; K units of one tz tap slice)
