@@ -467,8 +467,8 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
   g.ksplit = 1;
   if (ncb >= 2 && ctas < split_items) g.ksplit = std::max(1, std::min(ncb, 96 / ctas));
   // Deep levels (row of at most 30 voxels, Cout a multiple of 128): swapped-operand flattened-plane kernel.  N = positions
-  // of a (ty rows x W + 2) halo-plane strip, as many rows as fit N <= 256; ZT slabs so that ZT * N <= 512 TMEM columns
-  // (ZT dividing D when possible); split-K until a sample has ~48 items.  Again per-sample shapes only.
+  // of a (ty rows x W + 2) halo-plane strip, as many rows as fit N <= 256; ZT slabs (a divisor of D, ZT * N <= 512 TMEM
+  // columns, rule below); split-K until a sample has ~48 items.  Again per-sample shapes only.
   static const bool flat_on = [] { const char* e = getenv("DUNET_FLAT"); return !(e && e[0] == '0'); }();
   static const int flat_split_items = [] { const char* e = getenv("DUNET_FLAT_SPLIT_ITEMS"); return e ? atoi(e) : 36; }();
   static const int flat_target_items = [] { const char* e = getenv("DUNET_FLAT_TARGET_ITEMS"); return e ? atoi(e) : 48; }();
@@ -478,13 +478,12 @@ static ConvGeom conv_geom(const dunet_plan* p, const ConvW& c, int lvl, int B) {
     const int hx = p->W[lvl] + 2, ty_max = 258 / hx;
     const int tiles_y = (Hl + ty_max - 1) / ty_max, ty = (Hl + tiles_y - 1) / tiles_y;
     const int npos = pad_to(std::max(ty * hx - 2, 1), 16);
-    int zt = 1;
     // ZT: the SMALLEST slab count (dividing D) whose ZT * npos accumulator columns keep the weight stream affordable -- a
     // 16 KB weight tile feeds ZT * npos / 2 MMA clocks; at >= 160 columns (<= ~50 B/clk/SM; measured at 24^3 with 144 CTAs
     // streaming concurrently: no slowdown, L2 serves CTAs that walk the same tiles in step) more items beat more re-use:
     // 24^3 at ZT = 1 has 72 items per sample instead of 36 and the four layers take 132 us instead of 200 (2 windows).
     static const int min_cols = [] { const char* e = getenv("DUNET_FLAT_MIN_COLS"); return e ? atoi(e) : 160; }();
-    zt = 0;
+    int zt = 0;
     for (int cand : {1, 2, 3, 4, 6})
       if (cand * npos <= 512 && cand <= Dl && Dl % cand == 0 && cand * npos >= min_cols) { zt = cand; break; }
     if (!zt) {  // min_cols out of reach: the largest feasible slab count
